@@ -1,0 +1,134 @@
+"""ctypes binding of libchess_b200.so (the C ABI in include/chess_b200.h).
+
+There is no CPU fallback: importing this module without the shared library
+raises, and creating a context without a B200 raises.  The library is built
+in-tree by `python -m chess_b200.build` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libchess_b200.so")
+
+
+class ChessNativeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        # build on first use when a compiler is around; never fall back to CPU code
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:  # pragma: no cover - depends on the toolchain
+            raise ImportError(
+                "chess_b200: native library {} is missing and could not be built ({}). "
+                "Run `python -m chess_b200.build`; there is no CPU fallback.".format(LIB_PATH, exc))
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+
+class chess_pair(C.Structure):
+    _fields_ = [("ref_off", C.c_int64), ("qry_off", C.c_int64),
+                ("ref_pitch", C.c_int32), ("qry_pitch", C.c_int32),
+                ("ref_n", C.c_int32), ("qry_n", C.c_int32),
+                ("flip", C.c_int32), ("reserved", C.c_int32)]
+
+
+class chess_params(C.Structure):
+    _fields_ = [("min_bins", C.c_int32), ("keep_unmappable", C.c_int32),
+                ("abs_window", C.c_int32), ("compute_sn", C.c_int32),
+                ("rel_window", C.c_double), ("mappability_cutoff", C.c_double),
+                ("default_value", C.c_double), ("kernel", C.c_int32), ("reserved", C.c_int32)]
+
+
+PAIR_DTYPE = np.dtype([("ref_off", "<i8"), ("qry_off", "<i8"), ("ref_pitch", "<i4"),
+                       ("qry_pitch", "<i4"), ("ref_n", "<i4"), ("qry_n", "<i4"),
+                       ("flip", "<i4"), ("reserved", "<i4")], align=True)
+assert PAIR_DTYPE.itemsize == C.sizeof(chess_pair) == 40
+
+PAIR_OK, PAIR_NOT_FOUND, PAIR_TOO_SMALL, PAIR_UNMAPPABLE, PAIR_WINDOW_EXCEEDS = range(5)
+
+_vp, _i32, _i64, _dbl, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_size_t
+_PP = C.POINTER(chess_params)
+
+# name -> (restype, argtypes); every symbol include/chess_b200.h declares
+SIGNATURES = {
+    "chess_abi_version": (C.c_int, []),
+    "chess_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "chess_ctx_destroy": (None, [_vp]),
+    "chess_last_error": (C.c_char_p, [_vp]),
+    "chess_launch_count": (_i64, [_vp]),
+    "chess_expected_workspace_bytes": (_sz, [_i64]),
+    "chess_expected_from_coo": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "chess_possible_contacts": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "chess_oe_values": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "chess_band_build": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _dbl, _vp, _vp]),
+    "chess_gather_submatrix": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
+    "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
+    "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error(ctx=None):
+    msg = lib.chess_last_error(ctx)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, ctx=None, what=""):
+    if rc != 0:
+        raise ChessNativeError("{} failed (code {}): {}".format(what or "chess_b200 call", rc, last_error(ctx)))
+
+
+class Context(object):
+    """One library context = one GPU.  Not thread-safe."""
+
+    def __init__(self, device=0):
+        handle = _vp()
+        rc = lib.chess_ctx_create(int(device), C.byref(handle))
+        if rc != 0:
+            raise ChessNativeError("chess_ctx_create(device={}) failed (code {}): {}".format(
+                device, rc, last_error(None)))
+        self.handle = handle
+        self.device = int(device)
+
+    def launches(self):
+        return int(lib.chess_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.chess_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_params(min_bins=20, keep_unmappable_bins=False, absolute_window_size=None,
+                relative_window_size=1.0, mappability_cutoff=0.1, default_value=1,
+                compute_sn=True, kernel=0):
+    p = chess_params()
+    p.min_bins = int(min_bins)
+    p.keep_unmappable = 1 if keep_unmappable_bins else 0
+    p.abs_window = int(absolute_window_size) if absolute_window_size else 0
+    p.compute_sn = 1 if compute_sn else 0
+    p.rel_window = float(relative_window_size)
+    p.mappability_cutoff = float(mappability_cutoff)
+    p.default_value = float(default_value)
+    p.kernel = int(kernel)
+    p.reserved = 0
+    return p

@@ -1,0 +1,53 @@
+"""Build chess_b200/csrc/libchess_b200.so with nvcc for sm_100a (in-tree).
+
+    python -m chess_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The shared library links only the CUDA
+runtime (static) -- no torch, no Python headers: it is the C-ABI boundary
+declared in include/chess_b200.h.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libchess_b200.so")
+SOURCES = ["api.cu", "oe.cu", "compare_generic.cu", "compare_fast.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chess_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--shared", "-cudart", "static"]
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    stamp_file = LIB + ".stamp"
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file):
+        if open(stamp_file).read().strip() == stamp:
+            return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed building libchess_b200.so")
+    if verbose:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

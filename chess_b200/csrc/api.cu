@@ -1,0 +1,177 @@
+// C-ABI entry points that are not tied to one kernel family: context life
+// cycle, kernel dispatch for the compare path, host-buffer variants.
+#include <math_constants.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+thread_local std::string g_last_error;
+
+int grow(chess_ctx *ctx, void **ptr, size_t *have, size_t need, bool pinned) {
+  if (*have >= need) return CHESS_OK;
+  if (*ptr) {
+    if (pinned) cudaFreeHost(*ptr);
+    else cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+  }
+  size_t want = need + need / 2 + 4096;
+  cudaError_t e = pinned ? cudaMallocHost(ptr, want) : cudaMalloc(ptr, want);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("allocation of staging buffer failed: ") + cudaGetErrorString(e);
+    return CHESS_ERR_NOMEM;
+  }
+  *have = want;
+  return CHESS_OK;
+}
+}  // namespace
+
+extern "C" int chess_abi_version(void) { return CHESS_B200_ABI_VERSION; }
+
+extern "C" int chess_ctx_create(int device, chess_ctx **out) {
+  if (!out) return CHESS_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_last_error = std::string("no CUDA device available: ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                   " (chess_b200 has no CPU fallback)";
+    return CHESS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_last_error = "chess_ctx_create: device index out of range";
+    return CHESS_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_last_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return CHESS_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_last_error = std::string("chess_b200 is built for sm_100a only; device is ") + prop.name;
+    return CHESS_ERR_UNSUPPORTED;
+  }
+  chess_ctx *ctx = new chess_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = ctx;
+  return CHESS_OK;
+}
+
+extern "C" void chess_ctx_destroy(chess_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+  if (ctx->d_results) cudaFree(ctx->d_results);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  delete ctx;
+}
+
+extern "C" const char *chess_last_error(const chess_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" int64_t chess_launch_count(const chess_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int validate(chess_ctx *ctx, const chess_params *p) {
+  if (!p) { ctx->err = "params is NULL"; return CHESS_ERR_ARG; }
+  if (p->abs_window < 0) { ctx->err = "abs_window must be >= 0"; return CHESS_ERR_ARG; }
+  return CHESS_OK;
+}
+
+extern "C" int chess_compare_batch(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                                   const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                                   const chess_params *params, double *ssim, double *sn,
+                                   int32_t *status, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  int rc = validate(ctx, params);
+  if (rc) return rc;
+  if (n_pairs < 0 || (n_pairs > 0 && (!ref_base || !qry_base || !pairs || !ssim || !sn || !status))) {
+    ctx->err = "chess_compare_batch: NULL buffer";
+    return CHESS_ERR_ARG;
+  }
+  if (n_pairs == 0) return CHESS_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (params->kernel != 1) {
+    bool handled = false;
+    rc = chess_launch_compare_fast(ctx, ref_base, qry_base, pairs, n_pairs, max_n, *params, ssim, sn,
+                                   status, stream, &handled);
+    if (rc) return rc;
+    if (handled) return CHESS_OK;
+  }
+  return chess_launch_compare_generic(ctx, ref_base, qry_base, pairs, n_pairs, max_n, *params, ssim,
+                                      sn, status, stream);
+}
+
+extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
+                                        const double *qry_base, const chess_pair *pairs_host,
+                                        int64_t n_pairs, int32_t max_n, const chess_params *params,
+                                        double *ssim_host, double *sn_host, int32_t *status_host,
+                                        void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
+    ctx->err = "chess_compare_batch_host: NULL buffer";
+    return CHESS_ERR_ARG;
+  }
+  if (n_pairs == 0) return CHESS_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t pair_bytes = (size_t)n_pairs * sizeof(chess_pair);
+  const size_t res_bytes = (size_t)n_pairs * (2 * sizeof(double) + sizeof(int32_t));
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_pairs, &ctx->d_pairs_bytes, pair_bytes, false))) return rc;
+  if ((rc = grow(ctx, &ctx->d_results, &ctx->d_results_bytes, res_bytes, false))) return rc;
+  if ((rc = grow(ctx, &ctx->h_pinned, &ctx->h_pinned_bytes, pair_bytes > res_bytes ? pair_bytes : res_bytes, true)))
+    return rc;
+  // pageable -> pinned -> device (one memcpy on the host, one DMA)
+  std::memcpy(ctx->h_pinned, pairs_host, pair_bytes);
+  CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, ctx->h_pinned, pair_bytes, cudaMemcpyHostToDevice, stream));
+  double *d_ssim = reinterpret_cast<double *>(ctx->d_results);
+  double *d_sn = d_ssim + n_pairs;
+  int32_t *d_status = reinterpret_cast<int32_t *>(d_sn + n_pairs);
+  rc = chess_compare_batch(ctx, ref_base, qry_base, reinterpret_cast<const chess_pair *>(ctx->d_pairs),
+                           n_pairs, max_n, params, d_ssim, d_sn, d_status, stream_);
+  if (rc) return rc;
+  CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_results, res_bytes, cudaMemcpyDeviceToHost, stream));
+  CHESS_CUDA(ctx, cudaStreamSynchronize(stream));
+  const char *h = reinterpret_cast<const char *>(ctx->h_pinned);
+  std::memcpy(ssim_host, h, (size_t)n_pairs * sizeof(double));
+  std::memcpy(sn_host, h + (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(double));
+  std::memcpy(status_host, h + 2 * (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(int32_t));
+  return CHESS_OK;
+}
+
+extern "C" int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n,
+                              double *out, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n < 3 || !m1 || !m2 || !out) {
+    ctx->err = "chess_sn_dense: need n >= 3 and non-NULL buffers";
+    return CHESS_ERR_ARG;
+  }
+  // One dense pair through the generic kernel with masking off; the SSIM it also
+  // computes is discarded (device scratch from the results staging buffer).
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_pairs, &ctx->d_pairs_bytes, sizeof(chess_pair), false))) return rc;
+  if ((rc = grow(ctx, &ctx->d_results, &ctx->d_results_bytes, 64, false))) return rc;
+  chess_pair pr;
+  std::memset(&pr, 0, sizeof(pr));
+  pr.ref_pitch = n; pr.qry_pitch = n; pr.ref_n = n; pr.qry_n = n;
+  CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, &pr, sizeof(pr), cudaMemcpyHostToDevice, stream));
+  CHESS_CUDA(ctx, cudaStreamSynchronize(stream));  // pr lives on this stack frame
+  chess_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.min_bins = 0; p.keep_unmappable = 1; p.abs_window = 3; p.compute_sn = 1;
+  p.rel_window = 1.0; p.mappability_cutoff = 0.0; p.default_value = 1.0; p.kernel = 1;
+  double *d_ssim = reinterpret_cast<double *>(ctx->d_results);
+  int32_t *d_status = reinterpret_cast<int32_t *>(d_ssim + 1);
+  return chess_launch_compare_generic(ctx, m1, m2, reinterpret_cast<const chess_pair *>(ctx->d_pairs), 1, n, p,
+                                      d_ssim, out, d_status, stream);
+}

@@ -1,0 +1,82 @@
+// Shared declarations for the chess_b200 CUDA translation units (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/chess_b200.h"
+
+struct chess_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  std::string err;
+  int64_t launches = 0;
+  // staging for the *_host entry points (grown on demand, freed in destroy)
+  void *d_pairs = nullptr;
+  size_t d_pairs_bytes = 0;
+  void *d_results = nullptr;
+  size_t d_results_bytes = 0;
+  void *h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+};
+
+#define CHESS_CUDA(ctx, call)                                                          \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+      return CHESS_ERR_CUDA;                                                           \
+    }                                                                                  \
+  } while (0)
+
+// Internal launchers (one per translation unit).
+int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                                 const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                                 const chess_params &p, double *ssim, double *sn, int32_t *status,
+                                 cudaStream_t stream);
+int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                              const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                              const chess_params &p, double *ssim, double *sn, int32_t *status,
+                              cudaStream_t stream, bool *handled);
+
+// ---- small device helpers -------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Source index of output index o for an order-0 resize n_in -> n_out: the
+// sampling rule of scipy.ndimage.zoom(order=0, grid_mode=True), which is what
+// skimage.transform.resize(order=0) calls (chess/sim.py:323-329).  Plain
+// round-to-nearest double operations, no FMA contraction, so the index agrees
+// with the CPU for every o.
+__device__ __forceinline__ int resize_src_index(int o, int n_in, int n_out) {
+  double zoom = __ddiv_rn((double)n_in, (double)n_out);
+  double cc = __dsub_rn(__dmul_rn(__dadd_rn((double)o, 0.5), zoom), 0.5);
+  int idx = (int)floor(__dadd_rn(cc, 0.5));
+  return min(max(idx, 0), n_in - 1);
+}
+
+// Window rule of chess/sim.py:356-365.
+__host__ __device__ __forceinline__ int window_rule(int n, int abs_window, double rel_window) {
+  int w = abs_window ? abs_window : (int)((double)n * rel_window);
+  if ((w & 1) == 0) w -= 1;
+  return w < 3 ? 3 : w;
+}

@@ -1,0 +1,474 @@
+// Generic (any n <= 1024, any odd window) per-pair comparison kernel.
+//
+// One CTA per region pair.  It follows compare_matrix_pair (chess/sim.py:306-380)
+// step by step, reading the two submatrices straight from their storage (the
+// symmetric O/E band or packed dense matrices, see chess_pair in
+// include/chess_b200.h) -- the gather of sub_matrix_from_edges_dict
+// (chess/helpers.py:286-306) is index arithmetic here, never a copy:
+//
+//   0. not found / < min_bins                         sim.py:198-200, 319-320
+//   1. index maps: order-0 resize of the smaller side, 180-degree flip of the
+//      query when the strands differ                  sim.py:323-333
+//   2. column sums in row order (bit-identical to np.sum(m, 0)), masked
+//      columns, cutoff test                           sim.py:74-87, 336-347
+//   3. union of masked columns removed from both      sim.py:350-353
+//   4. window rule, data range                        sim.py:356-370
+//   5. SSIM: running sums of x, y, xx, yy, xy down the columns, block scan
+//      across a row, skimage's formula on every valid window, mean
+//   6. SN: direct (subtraction-free) 7x7 sums of d and d*d with the
+//      NaN-padded border of filter_uniform_filter (sim.py:33-71); windows whose
+//      one-pass variance suffers cancellation are recomputed two-pass in
+//      numpy's own summation order from a 7-row ring in shared memory.
+//
+// This kernel is the exact, shape-agnostic path; compare_fast.cu holds the
+// tuned kernels and falls back to this one.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRed = 192;  // doubles of reduction / scan scratch
+
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < BLOCK / 32 ? red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) red[32] = v;
+  }
+  __syncthreads();
+  v = red[32];
+  __syncthreads();
+  return v;
+}
+template <int BLOCK>
+__device__ __forceinline__ double block_max(double v, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < BLOCK / 32 ? red[lane] : -CUDART_INF;
+    v = warp_max(v);
+    if (lane == 0) red[32] = v;
+  }
+  __syncthreads();
+  v = red[32];
+  __syncthreads();
+  return v;
+}
+
+// In-place inclusive scan of five arrays buf[k*stride + 0..len) across the block.
+template <int BLOCK>
+__device__ __forceinline__ void block_scan5(double *buf, int stride, int len, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = BLOCK / 32;
+  double carry[5] = {0, 0, 0, 0, 0};
+  for (int base = 0; base < len; base += BLOCK) {
+    const int idx = base + threadIdx.x;
+    double v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = idx < len ? buf[k * stride + idx] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        double t = __shfl_up_sync(0xffffffffu, v[k], o);
+        if (lane >= o) v[k] += t;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) red[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        double t = lane < NW ? red[k * 32 + lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          double u = __shfl_up_sync(0xffffffffu, t, o);
+          if (lane >= o) t += u;
+        }
+        red[k * 32 + lane] = t;  // inclusive prefix of warp totals
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double off = carry[k] + (warp ? red[k * 32 + warp - 1] : 0.0);
+      v[k] += off;
+      if (idx < len) buf[k * stride + idx] = v[k];
+      carry[k] += red[k * 32 + NW - 1];
+    }
+    __syncthreads();
+  }
+}
+
+// numpy's pairwise summation for n = 49 contiguous doubles (n < 128: eight
+// running accumulators over blocks of eight, combined as a tree, then the tail).
+__device__ __forceinline__ double numpy_sum49(const double *a) {
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+#pragma unroll
+  for (int i = 8; i < 48; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  return __dadd_rn(res, a[48]);
+}
+
+// |nanmean| / nanvar of one NaN-padded 7x7 window, evaluated the way numpy
+// does it (two passes, np.nanmean / np.nanvar on the 49-slot axis).
+__device__ __noinline__ double sn_window_twopass(const double *ring, int stride, int rc, int c,
+                                                 int np_, double cnt) {
+  double val[49];
+  bool ok[49];
+#pragma unroll
+  for (int wi = 0; wi < 7; ++wi) {
+    const int rr = rc - 3 + wi;
+    const bool rok = rr >= 0 && rr < np_;
+    const int slot = ((rr % 7) + 7) % 7;
+#pragma unroll
+    for (int wj = 0; wj < 7; ++wj) {
+      const int cc = c - 3 + wj;
+      const bool v = rok && cc >= 0 && cc < np_;
+      ok[wi * 7 + wj] = v;
+      val[wi * 7 + wj] = v ? ring[slot * stride + cc] : 0.0;
+    }
+  }
+  const double avg = __ddiv_rn(numpy_sum49(val), cnt);
+#pragma unroll
+  for (int s = 0; s < 49; ++s) {
+    const double dv = ok[s] ? __dsub_rn(val[s], avg) : 0.0;
+    val[s] = __dmul_rn(dv, dv);
+  }
+  const double var = __ddiv_rn(numpy_sum49(val), cnt);
+  return __ddiv_rn(fabs(avg), var);
+}
+
+template <int BLOCK, int CPT>
+__global__ void __launch_bounds__(BLOCK)
+compare_generic_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
+                       const chess_pair *__restrict__ pairs, long long n_pairs, int ncap,
+                       chess_params p, double *__restrict__ ssim_out, double *__restrict__ sn_out,
+                       int *__restrict__ status_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *red = reinterpret_cast<double *>(smem_raw);
+  double *buf = red + kRed;                       // max(5*ncap, 9*ncap+12) doubles
+  int *mr = reinterpret_cast<int *>(buf + 9 * (size_t)ncap + 12);
+  int *mq = mr + ncap;                            // pre-compaction source indices
+  int *kr = mq + ncap;
+  int *kq = kr + ncap;                            // compacted source indices
+  int *iscratch = kq + ncap;                      // 64 ints
+  unsigned char *flag = reinterpret_cast<unsigned char *>(iscratch + 64);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double qnan = CUDART_NAN;
+
+  for (long long pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+    const chess_pair d = pairs[pi];
+    int status = CHESS_PAIR_OK;
+    if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
+    else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
+    if (status != CHESS_PAIR_OK) {
+      if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = status; }
+      continue;
+    }
+    const int n = max(d.ref_n, d.qry_n);
+    const double *R = ref_base + d.ref_off;
+    const double *Q = qry_base + d.qry_off;
+    const size_t rp = (size_t)d.ref_pitch, qp = (size_t)d.qry_pitch;
+
+    // ---- 1. index maps (resize + flip)
+    for (int k = tid; k < n; k += BLOCK) {
+      mr[k] = d.ref_n < n ? resize_src_index(k, d.ref_n, n) : k;
+      const int t = d.flip ? n - 1 - k : k;
+      mq[k] = d.qry_n < n ? resize_src_index(t, d.qry_n, n) : t;
+    }
+    __syncthreads();
+
+    // ---- 2. column sums in row order, min / max of the uncompacted pair
+    const bool use_masks = p.mappability_cutoff > 0;
+    const double masked_sum = (double)n * p.default_value;
+    double vmax = -CUDART_INF, vmin = CUDART_INF;
+    int cnt_r = 0, cnt_q = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int c = tid + j * BLOCK;
+      if (c < n) {
+        const int cr = mr[c], cq = mq[c];
+        double sr = 0.0, sq = 0.0;
+        for (int r = 0; r < n; ++r) {
+          const double x = __ldg(R + (size_t)mr[r] * rp + cr);
+          const double y = __ldg(Q + (size_t)mq[r] * qp + cq);
+          sr += x;
+          sq += y;
+          vmax = fmax(vmax, fmax(x, y));
+          vmin = fmin(vmin, fmin(x, y));
+        }
+        const bool fr = use_masks && sr == masked_sum;
+        const bool fq = use_masks && sq == masked_sum;
+        flag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+        cnt_r += fr;
+        cnt_q += fq;
+      }
+    }
+    const int tot_r = (int)block_sum<BLOCK>((double)cnt_r, red);
+    const int tot_q = (int)block_sum<BLOCK>((double)cnt_q, red);
+    if (use_masks && ((double)tot_r / (double)n > p.mappability_cutoff ||
+                      (double)tot_q / (double)n > p.mappability_cutoff)) {
+      if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = CHESS_PAIR_UNMAPPABLE; }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- 3. remove the union of masked columns from rows and columns of both
+    int np_ = n;
+    const bool remove = use_masks && !p.keep_unmappable && (tot_r + tot_q) > 0;
+    if (remove) {
+      int carry = 0;
+      for (int base = 0; base < n; base += BLOCK) {
+        const int c = base + tid;
+        const bool keep = c < n && flag[c] == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) iscratch[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < BLOCK / 32; ++w) {
+          const int v = iscratch[w];
+          if (w < warp) woff += v;
+          total += v;
+        }
+        if (keep) {
+          const int pos = carry + woff + __popc(bal & ((1u << lane) - 1u));
+          kr[pos] = mr[c];
+          kq[pos] = mq[c];
+        }
+        carry += total;
+        __syncthreads();
+      }
+      np_ = carry;
+    } else {
+      for (int k = tid; k < n; k += BLOCK) { kr[k] = mr[k]; kq[k] = mq[k]; }
+    }
+    __syncthreads();
+
+    // ---- 4. window rule and data range
+    const int win = window_rule(np_, p.abs_window, p.rel_window);
+    if (win > np_) {
+      if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      __syncthreads();
+      continue;
+    }
+    if (remove) {  // min / max over the compacted pair only
+      vmax = -CUDART_INF;
+      vmin = CUDART_INF;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = tid + j * BLOCK;
+        if (c < np_) {
+          const int cr = kr[c], cq = kq[c];
+          for (int r = 0; r < np_; ++r) {
+            const double x = __ldg(R + (size_t)kr[r] * rp + cr);
+            const double y = __ldg(Q + (size_t)kq[r] * qp + cq);
+            vmax = fmax(vmax, fmax(x, y));
+            vmin = fmin(vmin, fmin(x, y));
+          }
+        }
+      }
+    }
+    const double dmax = block_max<BLOCK>(vmax, red);
+    const double dmin = -block_max<BLOCK>(-vmin, red);
+    const double drange = dmax - dmin;
+
+    // ---- 5. SSIM over every valid window
+    const int m = np_ - win + 1;
+    const double NP = (double)win * (double)win;
+    const double cov_norm = NP / (NP - 1.0);
+    const double C1 = (0.01 * drange) * (0.01 * drange);
+    const double C2 = (0.03 * drange) * (0.03 * drange);
+    double acc = 0.0;
+    {
+      double V[CPT][5];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) V[j][k] = 0.0;
+      for (int r = 0; r < np_; ++r) {
+        const size_t ro = (size_t)kr[r] * rp, qo = (size_t)kq[r] * qp;
+        const bool sub = r >= win;
+        const size_t ro2 = sub ? (size_t)kr[r - win] * rp : 0, qo2 = sub ? (size_t)kq[r - win] * qp : 0;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int c = tid + j * BLOCK;
+          if (c < np_) {
+            const double x = __ldg(R + ro + kr[c]), y = __ldg(Q + qo + kq[c]);
+            V[j][0] += x; V[j][1] += y; V[j][2] += x * x; V[j][3] += y * y; V[j][4] += x * y;
+            if (sub) {
+              const double xo = __ldg(R + ro2 + kr[c]), yo = __ldg(Q + qo2 + kq[c]);
+              V[j][0] -= xo; V[j][1] -= yo; V[j][2] -= xo * xo; V[j][3] -= yo * yo; V[j][4] -= xo * yo;
+            }
+          }
+        }
+        if (r >= win - 1) {
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const int c = tid + j * BLOCK;
+            if (c < np_) {
+#pragma unroll
+              for (int k = 0; k < 5; ++k) buf[k * ncap + c] = V[j][k];
+            }
+          }
+          __syncthreads();
+          block_scan5<BLOCK>(buf, ncap, np_, red);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const int c = tid + j * BLOCK;
+            if (c < m) {
+              double h[5];
+#pragma unroll
+              for (int k = 0; k < 5; ++k)
+                h[k] = buf[k * ncap + c + win - 1] - (c ? buf[k * ncap + c - 1] : 0.0);
+              const double ux = h[0] / NP, uy = h[1] / NP;
+              const double uxx = h[2] / NP, uyy = h[3] / NP, uxy = h[4] / NP;
+              const double vx = cov_norm * (uxx - ux * ux);
+              const double vy = cov_norm * (uyy - uy * uy);
+              const double vxy = cov_norm * (uxy - ux * uy);
+              const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2;
+              const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+              acc += (A1 * A2) / (B1 * B2);
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    const double ssim = block_sum<BLOCK>(acc, red) / ((double)m * (double)m);
+
+    // ---- 6. SN
+    double sn = qnan;
+    if (p.compute_sn) {
+      double *ring = buf;                 // 7 * ncap
+      double *a1 = buf + 7 * (size_t)ncap; // np_+6, shifted by 3
+      double *a2 = a1 + ncap + 6;
+      for (int k = tid; k < 3; k += BLOCK) {
+        a1[k] = 0.0; a2[k] = 0.0; a1[np_ + 3 + k] = 0.0; a2[np_ + 3 + k] = 0.0;
+      }
+      double dreg[CPT][7];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) dreg[j][k] = 0.0;
+      double sacc = 0.0, scnt = 0.0;
+      for (int r = 0; r < np_ + 3; ++r) {
+        const bool live = r < np_;
+        const size_t ro = live ? (size_t)kr[r] * rp : 0, qo = live ? (size_t)kq[r] * qp : 0;
+        const int slot = r % 7;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int c = tid + j * BLOCK;
+          if (c < np_) {
+            const double dv = live ? __ldg(R + ro + kr[c]) - __ldg(Q + qo + kq[c]) : 0.0;
+#pragma unroll
+            for (int k = 6; k > 0; --k) dreg[j][k] = dreg[j][k - 1];
+            dreg[j][0] = dv;
+            ring[slot * ncap + c] = dv;
+            double s1 = dreg[j][0], s2 = dreg[j][0] * dreg[j][0];
+#pragma unroll
+            for (int k = 1; k < 7; ++k) { s1 += dreg[j][k]; s2 += dreg[j][k] * dreg[j][k]; }
+            a1[3 + c] = s1;
+            a2[3 + c] = s2;
+          }
+        }
+        __syncthreads();
+        if (r >= 3) {
+          const int rc = r - 3;
+          const int rcnt = min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const int c = tid + j * BLOCK;
+            if (c < np_) {
+              double w1 = 0.0, w2 = 0.0;
+#pragma unroll
+              for (int t = 0; t < 7; ++t) { w1 += a1[c + t]; w2 += a2[c + t]; }
+              if (w2 != 0.0) {  // w2 == 0 <=> every d in the window is 0 <=> 0/0 -> NaN, skipped
+                const int ccnt = min(c + 3, np_ - 1) - max(c - 3, 0) + 1;
+                const double cnt = (double)(rcnt * ccnt);
+                const double mean = w1 / cnt, ms = w2 / cnt;
+                const double var = ms - mean * mean;
+                double g;
+                if (var > 1e-6 * ms) g = fabs(mean) / var;
+                else g = sn_window_twopass(ring, ncap, rc, c, np_, cnt);
+                if (g == g) { sacc += g; scnt += 1.0; }
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      const double tot = block_sum<BLOCK>(sacc, red);
+      const double cnt = block_sum<BLOCK>(scnt, red);
+      sn = tot / cnt;  // 0/0 -> NaN, like np.nanmean of an all-NaN map
+    }
+    if (tid == 0) { ssim_out[pi] = ssim; sn_out[pi] = sn; status_out[pi] = CHESS_PAIR_OK; }
+    __syncthreads();
+  }
+}
+
+size_t generic_smem_bytes(int ncap) {
+  size_t doubles = kRed + 9 * (size_t)ncap + 12;
+  size_t ints = 4 * (size_t)ncap + 64;
+  size_t bytes = doubles * 8 + ints * 4 + (size_t)ncap;
+  return (bytes + 15) & ~size_t(15);
+}
+
+template <int BLOCK, int CPT>
+int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
+           int64_t n_pairs, int ncap, const chess_params &p, double *ssim, double *sn,
+           int32_t *status, cudaStream_t stream) {
+  auto kern = compare_generic_kernel<BLOCK, CPT>;
+  const size_t smem = generic_smem_bytes(ncap);
+  if ((int)smem > ctx->max_smem_optin) {
+    ctx->err = "compare_generic: shared memory demand exceeds the device limit";
+    return CHESS_ERR_UNSUPPORTED;
+  }
+  CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > n_pairs) grid = n_pairs;
+  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(ref_base, qry_base, pairs, (long long)n_pairs, ncap, p,
+                                                ssim, sn, status);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+}  // namespace
+
+int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                                 const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                                 const chess_params &p, double *ssim, double *sn, int32_t *status,
+                                 cudaStream_t stream) {
+  if (n_pairs <= 0) return CHESS_OK;
+  if (max_n > 1024) {
+    ctx->err = "compare: submatrices larger than 1024 bins are not supported";
+    return CHESS_ERR_UNSUPPORTED;
+  }
+  const int ncap = max_n < 32 ? 32 : max_n;
+  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
+  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
+  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
+  return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
+}

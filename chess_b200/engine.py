@@ -1,0 +1,351 @@
+"""Device-side state and the batched comparison engine.
+
+PyTorch is used for device memory, streams and (in bench.py) torch.distributed
+only; all arithmetic runs in the hand-written kernels behind the C ABI
+(include/chess_b200.h).  Nothing here falls back to the CPU.
+
+Data layout in HBM (one per sample, per GPU)
+    COO      src int32[nnz], sink int32[nnz], value float64[nnz]   (src <= sink)
+    band     float64[n_bins, 2W-1], band[i, (j-i)+W-1] = value(i, j) for |j-i| < W,
+             absent cells = default value (1 for O/E).  Row r of the submatrix
+             that starts at bin i0 is the contiguous run
+             band.flat[i0*(2W-1) + (W-1) + r*(2W-2) : ... + n], i.e. every
+             submatrix is a rectangular 2-D view with pitch 2W-2 -- rows load
+             coalesced and no per-pair copy is ever made.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import PAIR_DTYPE, lib, check
+
+_contexts = {}
+
+
+def get_context(device=0):
+    """The (cached) library context of one GPU."""
+    device = int(device)
+    if device not in _contexts:
+        _contexts[device] = _native.Context(device)
+    return _contexts[device]
+
+
+def visible_devices():
+    """GPU indices to use: $CHESS_B200_DEVICES ("0,1,2") or every visible GPU."""
+    env = os.environ.get("CHESS_B200_DEVICES")
+    if env:
+        return [int(v) for v in env.split(",") if v.strip() != ""]
+    if not torch.cuda.is_available():
+        raise _native.ChessNativeError("chess_b200 needs a CUDA device (B200); none is visible "
+                                       "and there is no CPU fallback")
+    return list(range(torch.cuda.device_count()))
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class DeviceContacts(object):
+    """The edges store of one sample: COO triples plus the HBM-resident band.
+
+    Replaces the ``{source: {sink: weight}}`` dict built by
+    chess/helpers.py:342-391.  ``store[source][sink]`` still works (host-side
+    CSR view) so code written against the dict keeps running; the comparison
+    kernels read the band.
+    """
+
+    def __init__(self, src, sink, value, n_bins=None, fill=1.0):
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        sink = np.ascontiguousarray(sink, dtype=np.int64)
+        self.value = np.ascontiguousarray(value, dtype=np.float64)
+        swap = src > sink
+        if swap.any():
+            src, sink = np.where(swap, sink, src), np.where(swap, src, sink)
+        self.src, self.sink = src, sink
+        hi = int(sink.max()) + 1 if len(sink) else 0
+        self.n_bins = int(n_bins) if n_bins is not None else hi
+        if self.n_bins < hi:
+            raise ValueError("contact indices exceed the number of regions")
+        self.fill = float(fill)
+        self._bands = {}   # device -> (W, fill, tensor)
+        self._coo = {}     # device -> (src32, sink32, value) tensors
+        self._csr = None
+
+    # -- dict-like view (compatibility with code indexing the reference's dict)
+    def _rows(self):
+        if self._csr is None:
+            order = np.lexsort((self.sink, self.src))
+            s, t, w = self.src[order], self.sink[order], self.value[order]
+            starts = np.searchsorted(s, np.arange(self.n_bins + 1))
+            self._csr = (starts, t, w)
+        return self._csr
+
+    def __getitem__(self, source):
+        starts, t, w = self._rows()
+        if source < 0 or source >= self.n_bins or starts[source] == starts[source + 1]:
+            raise KeyError(source)
+        lo, hi = starts[source], starts[source + 1]
+        return dict(zip(t[lo:hi].tolist(), w[lo:hi].tolist()))
+
+    def __contains__(self, source):
+        starts, _, _ = self._rows()
+        return 0 <= source < self.n_bins and starts[source] != starts[source + 1]
+
+    def __len__(self):
+        starts, _, _ = self._rows()
+        return int(np.count_nonzero(np.diff(starts)))
+
+    def triples(self):
+        return self.src, self.sink, self.value
+
+    # -- device residency
+    def coo_on(self, device):
+        device = int(device)
+        if device not in self._coo:
+            dev = torch.device("cuda", device)
+            self._coo[device] = (
+                torch.from_numpy(self.src.astype(np.int32)).to(dev),
+                torch.from_numpy(self.sink.astype(np.int32)).to(dev),
+                torch.from_numpy(self.value).to(dev))
+        return self._coo[device]
+
+    def band_on(self, device, min_w, fill=None):
+        """The band on ``device`` with half-width >= min_w (rebuilt if too narrow)."""
+        device = int(device)
+        fill = self.fill if fill is None else float(fill)
+        have = self._bands.get(device)
+        if have is not None and have[0] >= min_w and have[1] == fill:
+            return have[0], have[2]
+        W = max(int(min_w), 1)
+        W = min(((W + 15) // 16) * 16, max(self.n_bins, 1))
+        W = max(W, int(min_w))
+        ctx = get_context(device)
+        dev = torch.device("cuda", device)
+        if have is not None:
+            del self._bands[device]
+            del have
+        band = torch.empty(self.n_bins * (2 * W - 1), dtype=torch.float64, device=dev)
+        s, t, v = self.coo_on(device)
+        with torch.cuda.device(dev):
+            check(lib.chess_band_build(ctx.handle, _ptr(s), _ptr(t), _ptr(v), len(self.value),
+                                       self.n_bins, W, fill, _ptr(band), _stream_ptr(dev)),
+                  ctx.handle, "chess_band_build")
+        self._bands[device] = (W, fill, band)
+        return W, band
+
+    def drop_device_copies(self):
+        self._bands.clear()
+        self._coo.clear()
+
+    def submatrix(self, start_ix, n, default_weight=None, device=None):
+        """Dense n x n numpy tile starting at bin ``start_ix`` (device gather + D2H)."""
+        device = visible_devices()[0] if device is None else int(device)
+        W, band = self.band_on(device, n, default_weight)
+        ctx = get_context(device)
+        dev = torch.device("cuda", device)
+        out = torch.empty((n, n), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.chess_gather_submatrix(ctx.handle, _ptr(band), int(start_ix) * (2 * W - 1) + W - 1,
+                                             2 * W - 2, int(n), _ptr(out), _stream_ptr(dev)),
+                  ctx.handle, "chess_gather_submatrix")
+        return out.cpu().numpy()
+
+
+def as_device_contacts(edges):
+    """Accept a DeviceContacts or a ``{src: {sink: w}}`` mapping (uploaded as is)."""
+    if isinstance(edges, DeviceContacts):
+        return edges
+    cached = getattr(edges, "_chess_b200_contacts", None)
+    if cached is not None:
+        return cached
+    src, sink, val = [], [], []
+    for a, row in edges.items():
+        for b, w in row.items():
+            src.append(a)
+            sink.append(b)
+            val.append(w)
+    contacts = DeviceContacts(np.asarray(src, dtype=np.int64), np.asarray(sink, dtype=np.int64),
+                              np.asarray(val, dtype=np.float64))
+    try:
+        edges._chess_b200_contacts = contacts
+    except AttributeError:
+        pass
+    return contacts
+
+
+def region_spans(region_index, regions):
+    """(first_bin, n_bins) arrays for a list of regions; n = 0 where not found.
+
+    Batched form of the lookup in sub_regions (chess/helpers.py:233-242).  A
+    chromosome missing from the index raises KeyError like the reference.
+    """
+    n = len(regions)
+    first = np.full(n, -1, dtype=np.int64)
+    count = np.zeros(n, dtype=np.int64)
+    by_chrom = {}
+    for k, r in enumerate(regions):
+        by_chrom.setdefault(r.chromosome, []).append(k)
+    for chrom, ks in by_chrom.items():
+        index = region_index[chrom]
+        ks = np.asarray(ks)
+        qb = np.array([regions[k].start - 1 for k in ks], dtype=np.int64)
+        qe = np.array([regions[k].end for k in ks], dtype=np.int64)
+        lo, hi = index.span(qb, qe)
+        ok = lo >= 0
+        first[ks[ok]] = lo[ok]
+        count[ks[ok]] = hi[ok] - lo[ok] + 1
+    return first, count
+
+
+def build_pair_table(ref_first, ref_n, ref_w, qry_first, qry_n, qry_w, flip):
+    """chess_pair records for band-resident samples."""
+    n = len(ref_first)
+    tab = np.zeros(n, dtype=PAIR_DTYPE)
+    tab["ref_off"] = np.where(ref_n > 0, ref_first * (2 * ref_w - 1) + ref_w - 1, 0)
+    tab["qry_off"] = np.where(qry_n > 0, qry_first * (2 * qry_w - 1) + qry_w - 1, 0)
+    tab["ref_pitch"] = 2 * ref_w - 2
+    tab["qry_pitch"] = 2 * qry_w - 2
+    tab["ref_n"] = ref_n
+    tab["qry_n"] = qry_n
+    tab["flip"] = flip
+    return tab
+
+
+class CompareEngine(object):
+    """Batched replacement for the worker pool of bin/chess:189-225.
+
+    Holds the two samples resident on one or more GPUs and compares arbitrary
+    lists of (ID, reference_region, query_region) pairs.  Pairs are sharded in
+    contiguous ranges over the GPUs (no collective; results are concatenated
+    on the host in input order).
+    """
+
+    def __init__(self, reference_edges, reference_regions, query_edges, query_regions, devices=None):
+        self.ref = as_device_contacts(reference_edges)
+        self.qry = as_device_contacts(query_edges)
+        self.ref_index = reference_regions
+        self.qry_index = query_regions
+        self.devices = list(devices) if devices is not None else visible_devices()[:1]
+        if not self.devices:
+            raise _native.ChessNativeError("no CUDA device selected")
+
+    def compare_spans(self, ref_first, ref_n, qry_first, qry_n, flip, default_value=1, **params):
+        """Compare pairs given as bin spans -> (ssim, sn, status) numpy arrays."""
+        ref_first = np.asarray(ref_first, dtype=np.int64)
+        ref_n = np.asarray(ref_n, dtype=np.int64)
+        qry_first = np.asarray(qry_first, dtype=np.int64)
+        qry_n = np.asarray(qry_n, dtype=np.int64)
+        flip = np.asarray(flip, dtype=np.int32)
+        total = len(ref_first)
+        ssim = np.full(total, np.nan)
+        sn = np.full(total, np.nan)
+        status = np.zeros(total, dtype=np.int32)
+        if total == 0:
+            return ssim, sn, status
+        max_n = int(max(ref_n.max(), qry_n.max(), 1))
+        p = _native.make_params(default_value=default_value, **params)
+        ndev = min(len(self.devices), total)
+        bounds = np.linspace(0, total, ndev + 1).astype(np.int64)
+        pending = []
+        for k in range(ndev):
+            device = self.devices[k]
+            lo, hi = int(bounds[k]), int(bounds[k + 1])
+            if hi == lo:
+                continue
+            ctx = get_context(device)
+            dev = torch.device("cuda", device)
+            with torch.cuda.device(dev):
+                rw, rband = self.ref.band_on(device, max_n, default_value)
+                qw, qband = self.qry.band_on(device, max_n, default_value)
+                tab = build_pair_table(ref_first[lo:hi], ref_n[lo:hi], rw, qry_first[lo:hi], qry_n[lo:hi], qw,
+                                       flip[lo:hi])
+                h_tab = torch.from_numpy(tab.view(np.uint8)).pin_memory()
+                d_tab = h_tab.to(dev, non_blocking=True)
+                d_ssim = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+                d_sn = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+                d_status = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+                check(lib.chess_compare_batch(ctx.handle, _ptr(rband), _ptr(qband), _ptr(d_tab), hi - lo, max_n,
+                                              C.byref(p), _ptr(d_ssim), _ptr(d_sn), _ptr(d_status),
+                                              _stream_ptr(dev)), ctx.handle, "chess_compare_batch")
+                h_ssim = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+                h_sn = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+                h_status = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+                h_ssim.copy_(d_ssim, non_blocking=True)
+                h_sn.copy_(d_sn, non_blocking=True)
+                h_status.copy_(d_status, non_blocking=True)
+            pending.append((dev, lo, hi, h_ssim, h_sn, h_status, (h_tab, d_tab, d_ssim, d_sn, d_status)))
+        for dev, lo, hi, h_ssim, h_sn, h_status, _keep in pending:
+            torch.cuda.synchronize(dev)
+            ssim[lo:hi] = h_ssim.numpy()
+            sn[lo:hi] = h_sn.numpy()
+            status[lo:hi] = h_status.numpy()
+        return ssim, sn, status
+
+    def compare(self, pairs, compute_sn=True, default_value=1, **params):
+        """Compare (ID, reference_region, query_region) tuples.
+
+        Returns (ids, ssim, sn, status).  Where the reference yields
+        ``(nan, nan)`` the arrays hold NaN and ``status`` says why
+        (``_native.PAIR_*``).  A window larger than a compacted matrix raises
+        ValueError -- in the reference skimage raises it and the run aborts
+        (chess/sim.py:217-220, bin/chess:220-221).
+        """
+        pairs = list(pairs)
+        ids = [p[0] for p in pairs]
+        if params.get("mappability_cutoff", 0.1) <= 0 and not params.get("keep_unmappable_bins", False):
+            # np.union1d(*[]) in chess/sim.py:351
+            raise TypeError("union1d() missing 2 required positional arguments: 'ar1' and 'ar2'")
+        rf, rn = region_spans(self.ref_index, [p[1] for p in pairs])
+        qf, qn = region_spans(self.qry_index, [p[2] for p in pairs])
+        flip = np.array([1 if p[1].strand != p[2].strand else 0 for p in pairs], dtype=np.int32)
+        ssim, sn, status = self.compare_spans(rf, rn, qf, qn, flip, default_value=default_value,
+                                              compute_sn=compute_sn, **params)
+        if (status == _native.PAIR_WINDOW_EXCEEDS).any():
+            raise ValueError("win_size exceeds image extent. Either ensure that your images are "
+                             "at least 7x7; or pass win_size explicitly in the function call, "
+                             "with an odd value less than or equal to the smaller side of your images.")
+        return ids, ssim, sn, status
+
+
+def compare_dense_pairs(references, queries, flips, device=None, default_value=1, **params):
+    """Compare already-dense matrix pairs (lists of square float64 arrays).
+
+    The matrices are packed back to back in one device buffer per side and
+    described to the kernel as pitch-n views (the dense branch of chess_pair).
+    """
+    device = visible_devices()[0] if device is None else int(device)
+    ctx = get_context(device)
+    dev = torch.device("cuda", device)
+    n_pairs = len(references)
+    tab = np.zeros(n_pairs, dtype=PAIR_DTYPE)
+    r_off = q_off = 0
+    for k, (r, q) in enumerate(zip(references, queries)):
+        if r.ndim != 2 or q.ndim != 2 or r.shape[0] != r.shape[1] or q.shape[0] != q.shape[1]:
+            raise ValueError("compare_dense_pairs expects square matrices")
+        tab[k] = (r_off, q_off, r.shape[0], q.shape[0], r.shape[0], q.shape[0], 1 if flips[k] else 0, 0)
+        r_off += r.size
+        q_off += q.size
+    max_n = int(max([r.shape[0] for r in references] + [q.shape[0] for q in queries] + [1]))
+    h_ref = np.concatenate([np.ascontiguousarray(r, dtype=np.float64).ravel() for r in references]) \
+        if n_pairs else np.zeros(1)
+    h_qry = np.concatenate([np.ascontiguousarray(q, dtype=np.float64).ravel() for q in queries]) \
+        if n_pairs else np.zeros(1)
+    p = _native.make_params(default_value=default_value, **params)
+    ssim = np.empty(n_pairs)
+    sn = np.empty(n_pairs)
+    status = np.empty(n_pairs, dtype=np.int32)
+    with torch.cuda.device(dev):
+        d_ref = torch.from_numpy(h_ref).to(dev)
+        d_qry = torch.from_numpy(h_qry).to(dev)
+        check(lib.chess_compare_batch_host(ctx.handle, _ptr(d_ref), _ptr(d_qry), tab.ctypes.data_as(C.c_void_p),
+                                           n_pairs, max_n, C.byref(p), ssim.ctypes.data_as(C.c_void_p),
+                                           sn.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                           _stream_ptr(dev)), ctx.handle, "chess_compare_batch_host")
+    return ssim, sn, status

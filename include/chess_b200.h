@@ -1,0 +1,171 @@
+/* chess_b200.h -- C ABI of the B200-native `chess sim` comparison hot path.
+ *
+ * The reference (vaquerizaslab/chess 0.3.8) is pure Python and has no FFI: the
+ * boundary of its hot path is a set of Python call signatures.  Every entry
+ * point below names the reference interface it stands behind (paths relative
+ * to the reference checkout).  The Python package `chess_b200` binds this
+ * library with ctypes and keeps the reference's names and signatures
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain C, opaque context, `int` status (0 = ok, <0 = error; message via
+ *    chess_last_error()).
+ *  - The caller owns every buffer.  Pointers marked DEVICE are device
+ *    pointers of the context's GPU (e.g. torch.Tensor.data_ptr()); the
+ *    library never frees caller memory.  The `_host` entry points take HOST
+ *    pointers and perform the host<->device copies themselves through
+ *    context-owned staging buffers.
+ *  - All launches go to the caller-supplied stream (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream).  Device entry points do not
+ *    synchronise; `_host` entry points return after the results are in host
+ *    memory.
+ *  - One context per GPU; a context is not thread-safe.
+ *  - There is no CPU fallback: without a CUDA device every compute entry
+ *    point fails.
+ */
+#ifndef CHESS_B200_H
+#define CHESS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHESS_B200_ABI_VERSION 1
+
+typedef struct chess_ctx chess_ctx;
+
+/* ---- status codes of the API calls ------------------------------------ */
+#define CHESS_OK 0
+#define CHESS_ERR_CUDA (-1)     /* a CUDA runtime call failed                */
+#define CHESS_ERR_ARG (-2)      /* invalid argument                          */
+#define CHESS_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover   */
+#define CHESS_ERR_NOMEM (-4)
+
+/* ---- per-pair status written by the compare kernels -------------------- */
+#define CHESS_PAIR_OK 0
+#define CHESS_PAIR_NOT_FOUND 1   /* region has no bins: ValueError in the gather
+                                    -> (nan, nan), chess/sim.py:198-200        */
+#define CHESS_PAIR_TOO_SMALL 2   /* < min_bins, chess/sim.py:319-320           */
+#define CHESS_PAIR_UNMAPPABLE 3  /* masked fraction > cutoff, sim.py:344-347   */
+#define CHESS_PAIR_WINDOW_EXCEEDS 4 /* window larger than the compacted matrix:
+                                    skimage raises ValueError, which aborts the
+                                    reference run (sim.py:217-220)             */
+
+/* One comparison.  A submatrix is the square [0,n) x [0,n) of the 2-D view
+ *     element(r, c) = base[off + r * pitch + c]
+ * which covers both storages the path uses:
+ *   - symmetric band (chess_oe_band_build): off = first_bin*(2W-1) + (W-1),
+ *     pitch = 2W-2;
+ *   - packed dense matrices (chess/sim.py:306 compare_matrix_pair callers):
+ *     off = offset of the matrix, pitch = n.
+ * Stands behind the (pair_ix, reference_region, query_region) tuple consumed
+ * by chunk_comparison_worker, chess/sim.py:147-222, after the region -> bin
+ * lookup of chess/helpers.py:222-268.                                        */
+typedef struct chess_pair {
+  int64_t ref_off;   /* element offset of (0,0) of the reference submatrix    */
+  int64_t qry_off;
+  int32_t ref_pitch; /* row pitch in elements                                  */
+  int32_t qry_pitch;
+  int32_t ref_n;     /* bins; 0 or negative = region not found                */
+  int32_t qry_n;
+  int32_t flip;      /* 1 if the strands differ (sim.py:332-333)               */
+  int32_t reserved;
+} chess_pair;
+
+/* Keyword arguments of compare_matrix_pair, chess/sim.py:306-317.            */
+typedef struct chess_params {
+  int32_t min_bins;          /* 20 from the CLI (bin/chess:204)                */
+  int32_t keep_unmappable;   /* --keep-unmappable-bins                         */
+  int32_t abs_window;        /* -a; 0 = None                                   */
+  int32_t compute_sn;        /* False for background comparisons (bin/chess:306) */
+  double rel_window;         /* -r                                             */
+  double mappability_cutoff; /* --mappability-cutoff                           */
+  double default_value;      /* fill / masking value, 1 from the CLI           */
+  int32_t kernel;            /* 0 = auto, 1 = force the generic kernel         */
+  int32_t reserved;
+} chess_params;
+
+/* ---- context ------------------------------------------------------------ */
+int chess_abi_version(void);
+int chess_ctx_create(int device, chess_ctx **out);
+void chess_ctx_destroy(chess_ctx *ctx);
+const char *chess_last_error(const chess_ctx *ctx); /* ctx may be NULL */
+/* Number of kernels this context has launched (bench.py's gpu_launches).     */
+int64_t chess_launch_count(const chess_ctx *ctx);
+
+/* ---- K1: per-chromosome per-diagonal expected values -------------------- *
+ * Replaces expected_values + possible_contacts, chess/oe.py:17-146.
+ * COO triples are canonical (src <= sink), non-finite weights already dropped
+ * (chess/helpers.py:328-335).  bin_chrom[i] is the chromosome id of bin i,
+ * chrom_start[c] the first bin of chromosome c (n_chrom+1 entries, bins of a
+ * chromosome contiguous).  Outputs (DEVICE):
+ *   expected[chrom_start[c] + d]  expected value of chromosome c at distance d
+ *   inter_expected[0]             inter-chromosomal expected value
+ *   mappable[i]                   1 if the marginal of bin i is > 0
+ *   possible[chrom_start[c] + d]  #(i, i+d) pairs with both bins mappable
+ *   diag_sum[chrom_start[c] + d]  (optional, may be NULL) the diagonal sums
+ * Sums are accumulated in 128-bit fixed point, so the result does not depend
+ * on the order of the atomics (bit-identical across runs and GPU counts).
+ * `workspace` (DEVICE) must hold chess_expected_workspace_bytes(n_bins).      */
+size_t chess_expected_workspace_bytes(int64_t n_bins);
+int chess_expected_from_coo(chess_ctx *ctx, const int32_t *src, const int32_t *sink,
+                            const double *weight, int64_t nnz, const int32_t *bin_chrom,
+                            const int64_t *chrom_start, int32_t n_chrom, int64_t n_bins,
+                            double *expected, double *inter_expected, uint8_t *mappable,
+                            int64_t *possible, double *diag_sum, void *workspace,
+                            size_t workspace_bytes, void *stream);
+/* possible_contacts alone, chess/oe.py:17-75 (intra-chromosomal counts).      */
+int chess_possible_contacts(chess_ctx *ctx, const uint8_t *mappable, const int64_t *chrom_start,
+                            int32_t n_chrom, int64_t n_bins, int64_t *possible, void *stream);
+
+/* ---- K2: O/E values and the symmetric band ------------------------------ *
+ * chess_oe_values replaces _oe_generator, chess/oe.py:149-166: out[k] =
+ * weight[k] / expected (1 when the expected value is exactly 0); apply_log2
+ * is the optional fused transform (default off: `chess sim` applies none).   */
+int chess_oe_values(chess_ctx *ctx, const int32_t *src, const int32_t *sink, const double *weight,
+                    int64_t nnz, const int32_t *bin_chrom, const int64_t *chrom_start,
+                    const double *expected, const double *inter_expected, int32_t apply_log2,
+                    double *out, void *stream);
+/* chess_band_build replaces the dict-of-dict edges store (helpers.py:342-356)
+ * and the per-cell fill of sub_matrix_from_edges_dict (helpers.py:296-304):
+ * band[i*(2W-1) + (j-i) + W-1] for |j-i| < W, pre-filled with `fill`, then
+ * both mirror cells of every triple are written.  band holds
+ * n_bins*(2W-1) doubles (DEVICE).                                            */
+int chess_band_build(chess_ctx *ctx, const int32_t *src, const int32_t *sink, const double *value,
+                     int64_t nnz, int64_t n_bins, int32_t W, double fill, double *band,
+                     void *stream);
+
+/* Dense copy of one submatrix view, out[r*n + c] = base[off + r*pitch + c]:
+ * the return value of sub_matrix_from_edges_dict, chess/helpers.py:286-306.   */
+int chess_gather_submatrix(chess_ctx *ctx, const double *base, int64_t off, int32_t pitch,
+                           int32_t n, double *out, void *stream);
+
+/* ---- K3-K5: gather + masks + SSIM + SN ---------------------------------- *
+ * Replaces, per pair, sub_matrix_from_edges_dict (helpers.py:286-306) and
+ * compare_matrix_pair (sim.py:306-380) including skimage's
+ * structural_similarity and SN (sim.py:15-71).  All pointers DEVICE.
+ * ssim/sn are NaN and status != 0 where the reference returns (nan, nan);
+ * sn is NaN when compute_sn == 0 (the reference returns None).
+ * max_n = largest ref_n/qry_n in the batch (sizes shared memory).            */
+int chess_compare_batch(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                        const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                        const chess_params *params, double *ssim, double *sn, int32_t *status,
+                        void *stream);
+/* Same with HOST pair descriptors and HOST result arrays; the copies are part
+ * of the call (this is the entry point bench.py times as `e2e`).             */
+int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                             const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
+                             const chess_params *params, double *ssim_host, double *sn_host,
+                             int32_t *status_host, void *stream);
+
+/* SN(M1, M2, size=7), chess/sim.py:15-30, on n x n DEVICE matrices.          */
+int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n, double *out,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHESS_B200_H */

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+and against the golden vectors produced by the reference's own code.
+
+Tolerances (BASELINE.json north_star, fp64 mode): SSIM, SN and z within 1e-6
+relative; masks, NaN pattern, pair order and every integer quantity exact.
+"""
+import os
+import queue
+
+import numpy as np
+import pytest
+
+from oracle import chess_oracle as O
+from tests.conftest import unhex, unhex_arr, close
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import chess_b200
+    return chess_b200
+
+
+def _oe_input_contacts(cb, toy, tag):
+    """Contacts from the reference's own O/E output (bit-identical inputs)."""
+    regions, conv, _ = cb.load_regions(toy(tag + ".bed"))
+    edges, trees, regions = cb.load_oe_contacts(toy(tag + ".oe.sparse"), toy(tag + ".bed"))
+    return edges, trees, regions
+
+
+# ------------------------------------------------------------------ K1 / K2
+@pytest.mark.parametrize("tag", ["ref", "qry", "named"])
+def test_expected_values_and_oe(cb, golden, toy, tag):
+    g = golden["oe"][tag]
+    regions, conv, _ = cb.load_regions(toy(tag + ".bed"))
+    triples = cb.helpers._parse_sparse(toy(tag + ".sparse"), conv)
+    intra, chrom, inter = cb.expected_values(regions, triples)
+    np.testing.assert_allclose(intra, unhex_arr(g["intra_expected"]), rtol=1e-12, atol=0)
+    for c, v in g["chrom_expected"].items():
+        np.testing.assert_allclose(chrom[c], unhex_arr(v), rtol=1e-12, atol=0, err_msg=c)
+    assert close(inter, unhex(g["inter_expected"]), 1e-12)
+    tot, ctot, itot = cb.possible_contacts(regions, g["mappable"])
+    assert tot == g["possible_intra"] and ctot == g["possible_chrom"] and itot == g["possible_inter"]
+    _, oe = cb.observed_expected(toy(tag + ".bed"), toy(tag + ".sparse"))
+    if g["oe"] is not None:
+        want = [(a, b, unhex(w)) for a, b, w in g["oe"]]
+    else:
+        want = list(O.iter_sparse(toy(tag + ".oe.sparse")))
+    assert len(oe) == len(want)
+    assert [(a, b) for a, b, _ in oe] == [(a, b) for a, b, _ in want]
+    np.testing.assert_allclose([w for _, _, w in oe], [w for _, _, w in want], rtol=1e-12, atol=0)
+
+
+def test_expected_values_order_independent(cb, toy):
+    """128-bit fixed-point accumulation: shuffling the triples changes nothing."""
+    regions, conv, _ = cb.load_regions(toy("ref.bed"))
+    a, b, w = cb.helpers._parse_sparse(toy("ref.sparse"), conv)
+    base = cb.expected_values(regions, (a, b, w))
+    perm = np.random.default_rng(3).permutation(len(w))
+    again = cb.expected_values(regions, (a[perm], b[perm], w[perm]))
+    assert base[0] == again[0] and base[1] == again[1] and base[2] == again[2]
+
+
+def test_expected_values_against_exact_sums(cb):
+    """Weights spanning 30 orders of magnitude: result within 1 ulp of math.fsum."""
+    import math
+    from chess_b200.helpers import GenomicRegion
+    rng = np.random.default_rng(9)
+    n = 40
+    regions = [GenomicRegion(chromosome="c", start=i * 10, end=i * 10 + 10, ix=i) for i in range(n)]
+    a, b, w = [], [], []
+    for i in range(n):
+        for j in range(i, n):
+            for _ in range(3):
+                a.append(i); b.append(j); w.append(float(rng.lognormal(0, 8)))
+    a, b, w = np.array(a), np.array(b), np.array(w)
+    _, chrom, _ = cb.expected_values(regions, (a, b, w))
+    for d in range(n):
+        sel = (b - a) == d
+        exact = math.fsum(w[sel]) / (n - d)
+        assert abs(chrom["c"][d] - exact) <= 4e-16 * exact, d
+
+
+# ------------------------------------------------------------------ gather
+def test_gather_bit_exact(cb, golden, toy):
+    edges, trees, _ = _oe_input_contacts(cb, toy, "ref")
+    for case in golden["gather"]["cases"]:
+        reg = cb.GenomicRegion(chromosome=case["chrom"], start=case["start"], end=case["end"])
+        m, hits = cb.sub_matrix_from_edges_dict(edges, trees, reg, default_weight=1)
+        assert m.shape == (case["n"], case["n"])
+        assert min(h.ix for h in hits) == case["first_ix"]
+        assert np.array_equal(m.ravel(), unhex_arr(case["m"]))
+    with pytest.raises(ValueError):
+        cb.sub_matrix_from_edges_dict(edges, trees, cb.GenomicRegion(chromosome="chrA", start=90001, end=120000), 1)
+    # a plain dict of dicts is accepted too (uploaded on first use)
+    oregions, oconv, _ = O.load_regions(toy("ref.bed"))
+    plain = dict(O.edges_dict(O.iter_sparse(toy("ref.oe.sparse"))))
+    case = golden["gather"]["cases"][0]
+    m, _ = cb.sub_matrix_from_edges_dict(plain, trees, cb.GenomicRegion(chromosome="chrA", start=1, end=24000), 1)
+    assert np.array_equal(m.ravel(), unhex_arr(case["m"]))
+    assert edges[0][0] == plain[0][0]
+
+
+# ------------------------------------------------------------------ compare
+def _check_rows(rows, want, tag):
+    assert len(rows) == len(want)
+    for (pid, s, sn), (gpid, gs, gsn) in zip(rows, want):
+        gs, gsn = unhex(gs), unhex(gsn)
+        assert pid == gpid
+        assert close(s, gs, RTOL), (tag, pid, s, gs)
+        assert close(sn, gsn, RTOL), (tag, pid, sn, gsn)
+
+
+@pytest.mark.parametrize("source", ["oe_input", "device_oe"])
+def test_worker_matches_reference_rows(cb, golden, toy, source):
+    if source == "oe_input":
+        re_, rt, _ = _oe_input_contacts(cb, toy, "ref")
+        qe, qt, _ = _oe_input_contacts(cb, toy, "qry")
+    else:
+        re_, rt, _ = cb.load_contacts(toy("ref.sparse"), toy("ref.bed"))
+        qe, qt, _ = cb.load_contacts(toy("qry.sparse"), toy("qry.bed"))
+    pairs, _ = cb.load_pairs_for_chroms(toy("pairs.bedpe"), set(rt) | set(qt))
+    for tag, g in golden["worker"].items():
+        kw = g["params"]
+        qi, qo = queue.Queue(), queue.Queue()
+        qi.put([pairs, True])
+        qi.put(None)
+        cb.chunk_comparison_worker(qi, qo, re_, rt, qe, qt, 20, kw.get("keep_unmappable_bins", False),
+                                   kw.get("absolute_window_size"), kw.get("relative_window_size", 1.),
+                                   kw.get("mappability_cutoff", 0.1))
+        res = qo.get()
+        assert not isinstance(res, Exception), res
+        _check_rows(res, g["rows"], tag)
+
+
+def test_compare_pair_and_structures(cb, golden, toy):
+    re_, rt, _ = _oe_input_contacts(cb, toy, "ref")
+    qe, qt, _ = _oe_input_contacts(cb, toy, "qry")
+    pairs, _ = cb.load_pairs_for_chroms(toy("pairs.bedpe"), set(rt) | set(qt))
+    for pair, (gpid, gs, gsn) in zip(pairs[:4], golden["compare_pair_nosn"]):
+        pid, s, sn = cb.compare_pair(pair, re_, rt, qe, qt, compute_sn=False)
+        assert pid == gpid and close(s, unhex(gs), RTOL)
+        assert (sn is None) if gsn is None else np.isnan(sn)
+    res = cb.compare_structures(re_, rt, qe, qt, pairs[:6], "w0", absolute_window_size=7)
+    assert set(res) == set(golden["compare_structures_abs7"])
+    for pid, (gs, gsn) in golden["compare_structures_abs7"].items():
+        assert close(res[pid][0], unhex(gs), RTOL) and close(res[pid][1], unhex(gsn), RTOL)
+
+
+def test_window_larger_than_matrix_raises(cb, toy):
+    re_, rt, _ = _oe_input_contacts(cb, toy, "ref")
+    qe, qt, _ = _oe_input_contacts(cb, toy, "qry")
+    pairs, _ = cb.load_pairs_for_chroms(toy("pairs.bedpe"), set(rt) | set(qt))
+    with pytest.raises(ValueError):
+        cb.compare_pair(pairs[0], re_, rt, qe, qt, absolute_window_size=101)
+    with pytest.raises(TypeError):  # np.union1d(*[]) in the reference
+        cb.compare_pair(pairs[0], re_, rt, qe, qt, mappability_cutoff=0)
+
+
+def _table(path):
+    rows = [l.rstrip("\n").split("\t") for l in open(path)]
+    return rows[0], rows[1:]
+
+
+@pytest.mark.parametrize("tag,extra", [
+    ("cli_default", []),
+    ("cli_abs7_bg", ["-a", "7", "--background-regions", "background.bed"]),
+    ("cli_oe_input", ["--oe-input", "-r", "0.4", "--keep-unmappable-bins"]),
+])
+def test_cli_table(cb, toy, tmp_path, tag, extra):
+    from chess_b200.cli import Chess
+    out = str(tmp_path / (tag + ".tsv"))
+    extra = [toy(a) if a.endswith(".bed") else a for a in extra]
+    sfx = ".oe.sparse" if "--oe-input" in extra else ".sparse"
+    Chess(["chess", "sim", toy("ref" + sfx), toy("qry" + sfx), toy("pairs.bedpe"), out,
+           "--reference-regions", toy("ref.bed"), "--query-regions", toy("qry.bed")] + extra)
+    head, rows = _table(out)
+    ghead, grows = _table(toy(tag + ".tsv"))
+    assert head == ghead and len(rows) == len(grows)
+    for r, g in zip(rows, grows):
+        assert r[0] == g[0]
+        for a, b in zip(r[1:], g[1:]):
+            assert close(float(a), float(b), RTOL) or abs(float(a) - float(b)) < 1e-9, (tag, r, g)
+
+
+# ------------------------------------------------------------------ dense pairs vs oracle
+class _R:
+    def __init__(self, strand):
+        self.strand = strand
+
+
+def _sym(rng, n, sigma=0.5):
+    a = rng.lognormal(0, sigma, (n, n))
+    return (a + a.T) / 2
+
+
+@pytest.mark.parametrize("n,kw", [
+    (20, dict()), (21, dict()), (33, dict(absolute_window_size=3)), (40, dict(absolute_window_size=7)),
+    (64, dict(absolute_window_size=11)), (81, dict()), (81, dict(absolute_window_size=7)),
+    (120, dict(relative_window_size=0.5)), (129, dict(absolute_window_size=9)),
+    (200, dict(absolute_window_size=7)), (200, dict()), (257, dict(relative_window_size=0.1)),
+    (400, dict(absolute_window_size=5)), (600, dict(relative_window_size=0.9)),
+])
+def test_dense_pairs_against_oracle(cb, n, kw):
+    rng = np.random.default_rng(n)
+    a = _sym(rng, n)
+    b = (a * _sym(rng, n, 0.3))
+    b = (b + b.T) / 2
+    for k in rng.choice(n, max(1, n // 25), replace=False):   # unmappable bins in either matrix
+        m = a if rng.random() < 0.5 else b
+        m[k, :] = 1.0
+        m[:, k] = 1.0
+    for strands in (("+", "+"), ("+", "-")):
+        _, s, sn = cb.compare_matrix_pair(a, _R(strands[0]), b, _R(strands[1]), pair_ix=7, **kw)
+        _, os_, osn = O.compare_matrix_pair(a, strands[0], b, strands[1], pair_ix=7, **kw)
+        assert close(s, os_, RTOL), (n, kw, strands, s, os_)
+        assert close(sn, osn, RTOL), (n, kw, strands, sn, osn)
+
+
+def test_dense_unequal_sizes_resize(cb):
+    rng = np.random.default_rng(1)
+    for n1, n2 in ((24, 31), (41, 26), (50, 51), (30, 90)):
+        a, b = _sym(rng, n1), _sym(rng, n2)
+        for strands in (("+", "+"), ("-", "+")):
+            _, s, sn = cb.compare_matrix_pair(a, _R(strands[0]), b, _R(strands[1]), absolute_window_size=5)
+            _, os_, osn = O.compare_matrix_pair(a, strands[0], b, strands[1], absolute_window_size=5)
+            assert close(s, os_, RTOL) and close(sn, osn, RTOL), (n1, n2, strands)
+
+
+def test_small_and_unmappable_return_nan(cb):
+    rng = np.random.default_rng(2)
+    a, b = _sym(rng, 19), _sym(rng, 19)
+    assert np.isnan(cb.compare_matrix_pair(a, _R("+"), b, _R("+"))[1])
+    a, b = _sym(rng, 40), _sym(rng, 40)
+    for k in range(5):  # 12.5 % masked > 10 %
+        a[k, :] = 1.0
+        a[:, k] = 1.0
+    pid, s, sn = cb.compare_matrix_pair(a, _R("+"), b, _R("+"), pair_ix="x")
+    assert pid == "x" and np.isnan(s) and np.isnan(sn)
+    _, s, sn = cb.compare_matrix_pair(a, _R("+"), b, _R("+"), mappability_cutoff=0.2)
+    _, os_, osn = O.compare_matrix_pair(a, "+", b, "+", mappability_cutoff=0.2)
+    assert close(s, os_, RTOL) and close(sn, osn, RTOL)
+    assert cb.compare_matrix_pair(a, _R("+"), b, _R("+"), mappability_cutoff=0.2, compute_sn=False)[2] is None
+
+
+def test_mask_detection_is_bit_exact(cb):
+    """Columns that sum to n by coincidence (or miss it by one ulp) must be
+    classified exactly like np.sum(m, 0) == n does (chess/sim.py:82-85)."""
+    rng = np.random.default_rng(4)
+    n = 32
+    hits = 0
+    for trial in range(40):
+        a = _sym(rng, n)
+        # column/row k: values that sum to n up to rounding
+        k = int(rng.integers(0, n))
+        v = rng.uniform(0.5, 1.5, n)
+        v[-1] = n - v[:-1].sum()
+        a[k, :] = v
+        a[:, k] = v
+        b = _sym(rng, n)
+        want = O.compare_matrix_pair(a, "+", b, "+", absolute_window_size=5, mappability_cutoff=0.5)
+        got = cb.compare_matrix_pair(a, _R("+"), b, _R("+"), absolute_window_size=5, mappability_cutoff=0.5)
+        hits += len(O.find_masked_rows(a, 1))
+        assert close(got[1], want[1], RTOL) and close(got[2], want[2], RTOL), trial
+    assert hits > 0  # the construction does produce exact coincidences
+
+
+def test_sn_function_and_degenerate_windows(cb, golden):
+    for case in golden["SN"]:
+        n = case["n"]
+        a, b = unhex_arr(case["a"], (n, n)), unhex_arr(case["b"], (n, n))
+        assert close(cb.SN(a, b), unhex(case["sn"]), RTOL), n
+    rng = np.random.default_rng(6)
+    a = _sym(rng, 30)
+    assert np.isnan(cb.SN(a, a.copy()))                      # all windows 0/0 -> nanmean of nothing
+    b = a.copy()
+    b[10:25, 10:25] += 0.25                                  # constant offset block: zero-variance windows
+    got, want = cb.SN(a, b), O.signal_to_noise(a, b)
+    assert np.isfinite(got) == np.isfinite(want)
+    if np.isfinite(want):
+        # the block interior is ill-conditioned by construction (|mean| / ~0); same order of magnitude
+        assert 0.1 < got / want < 10
+    c = a * rng.lognormal(0, 0.2, a.shape)
+    c[:12, :12] = a[:12, :12]                                # partly identical: NaN windows are skipped
+    assert close(cb.SN(a, c), O.signal_to_noise(a, c), RTOL)
+
+
+# ------------------------------------------------------------------ size-independent properties
+@pytest.fixture(scope="module")
+def chr2_like(cb):
+    from chess_b200 import synth
+    genome = synth.Genome([("chr2", 2400)], 25000)
+    ref = synth.synthetic_sample(genome, 100, seed=1, structure_seed=7)
+    qry = synth.synthetic_sample(genome, 100, seed=2, structure_seed=7, perturb=0.1)
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    re_ = cb.observed_expected_arrays(regions, ref)
+    qe = cb.observed_expected_arrays(regions, qry)
+    pairs = synth.sliding_pairs(genome, 2000000, 100000)
+    return genome, regions, trees, re_, qe, pairs, ref, qry
+
+
+def test_identity_and_sharding_invariance(cb, chr2_like):
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    eng = cb.CompareEngine(re_, trees, re_, trees)
+    ids, s, sn, st = eng.compare(pairs)
+    ok = st == 0
+    assert ok.sum() > 100
+    assert np.all(s[ok] == 1.0)            # a matrix against itself
+    assert np.all(np.isnan(sn[ok]))        # difference is 0 everywhere: every window is 0/0
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    ids, s, sn, st = eng.compare(pairs, absolute_window_size=7)
+    parts = [eng.compare(pairs[lo:lo + 97], absolute_window_size=7) for lo in range(0, len(pairs), 97)]
+    s2 = np.concatenate([p[1] for p in parts])
+    sn2 = np.concatenate([p[2] for p in parts])
+    assert np.array_equal(s, s2, equal_nan=True) and np.array_equal(sn, sn2, equal_nan=True)
+    assert ids == [p[0] for p in pairs]
+
+
+def test_sample_against_oracle_at_chr2_scale(cb, chr2_like):
+    genome, regions, trees, re_, qe, pairs, ref, qry = chr2_like
+    oregions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in regions]
+    otrees = O.region_trees(oregions)
+    ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
+    oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    pick = pairs[::37]
+    for kw in (dict(), dict(absolute_window_size=7)):
+        ids, s, sn, st = eng.compare(pick, **kw)
+        for k, (pid, rr, qr) in enumerate(pick):
+            op = (pid, O.Region(rr.start, rr.end, rr.chromosome, strand=rr.strand),
+                  O.Region(qr.start, qr.end, qr.chromosome, strand=qr.strand))
+            _, os_, osn = O.compare_pair(op, ore, otrees, oqe, otrees, **kw)
+            assert close(s[k], os_, RTOL), (kw, pid, s[k], os_)
+            assert close(sn[k], osn, RTOL), (kw, pid, sn[k], osn)
+
+
+def test_multi_gpu_sharding_identical(cb, chr2_like):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    one = cb.CompareEngine(re_, trees, qe, trees, devices=[0]).compare(pairs)
+    two = cb.CompareEngine(re_, trees, qe, trees, devices=[0, 1]).compare(pairs)
+    assert np.array_equal(one[1], two[1], equal_nan=True) and np.array_equal(one[2], two[2], equal_nan=True)
