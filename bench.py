@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""Benchmark of the `chess sim` comparison hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over the whole pair list of the workload:
+for every region pair gather both submatrices from the resident O/E band,
+mask / compact, SSIM, SN, then the run-level z-score.  Workload = BASELINE.json
+configs[1]: human chr2 at 25 kb (9 688 bins), 2 Mb windows sliding by 100 kb
+(2 402 pairs, 81 bins each with the reference's BED lookup), default
+`chess sim` parameters (-r 1, SN on); synthetic, seeded.
+
+Numbers on the JSON line
+  value      pairs/s, whole job, samples and pair table already resident in HBM,
+             CUDA-event time of K steps (L2 flushed before every step).
+  e2e        same work through the host-buffer C-ABI call
+             (chess_compare_batch_host): pair table from host memory, results
+             back to host memory and z-scores, every step.
+  roofline   compare kernel only: algorithmic bytes (2*n*n*8 + 24 per pair,
+             SURVEY 8d) / its CUDA-event duration, against the measured HBM
+             copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (reference algorithm restated, oracle/) with a
+             multiprocessing pool on this box's cores, on a bounded sample.
+
+Under torchrun (N > 1) every rank owns one GPU and an independent chr2-sized
+sample pair (weak scaling, no data-path collective); rank 0 prints the line
+with the max-over-ranks time.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHR2_BP = 242193529
+BIN = 25000
+WINDOW_BP = 2000000
+STEP_BP = 100000
+METRIC = "region pairs/sec (SSIM+SN+z)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--window", default="r1", choices=["r1", "a7"],
+                    help="r1 = default `chess sim` (-r 1); a7 = -a 7")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 force the generic kernel")
+    return ap.parse_args()
+
+
+def window_params(tag):
+    return dict(absolute_window_size=7) if tag == "a7" else dict()
+
+
+def make_workload(rank):
+    """Synthetic chr2 @ 25 kb sample pair (seeded by rank) and the sliding pair list."""
+    from chess_b200 import synth
+    genome = synth.Genome(synth.chromosome_bins([("chr2", CHR2_BP)], BIN), BIN, [("chr2", CHR2_BP)])
+    ref = synth.synthetic_sample(genome, 100, seed=100 + 2 * rank, structure_seed=7 + rank)
+    qry = synth.synthetic_sample(genome, 100, seed=101 + 2 * rank, structure_seed=7 + rank, perturb=0.1)
+    pairs = synth.sliding_pairs(genome, WINDOW_BP, STEP_BP)
+    return genome, ref, qry, pairs
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(window):
+    """DRAM bytes per launch of the compare kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(window)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------- CPU arms
+_G = {}
+
+
+def _cpu_chunk(idx):
+    from oracle import chess_oracle as O
+    chunk = [_G["pairs"][i] for i in idx]
+    return O.compare_chunk(chunk, _G["re"], _G["rt"], _G["qe"], _G["qt"], True, **_G["kw"])
+
+
+def cpu_setup(genome, ref, qry, pairs, window, oe=None):
+    """Oracle-side state: O/E edges as dict of dicts (the reference's own layout)."""
+    from oracle import chess_oracle as O
+    regions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in genome.regions()]
+    trees = O.region_trees(regions)
+    if oe is None:
+        oe = []
+        for s in (ref, qry):
+            triples = list(zip(s[0].tolist(), s[1].tolist(), s[2].tolist()))
+            oe.append(O.observed_expected(regions, triples))
+    _G.update(re=O.edges_dict(oe[0]), qe=O.edges_dict(oe[1]), rt=trees, qt=trees, kw=window_params(window),
+              pairs=[(pid, O.Region(r.start, r.end, r.chromosome, strand=r.strand),
+                      O.Region(q.start, q.end, q.chromosome, strand=q.strand)) for pid, r, q in pairs])
+
+
+def cpu_run(sample_idx, pool, cores):
+    """One pass over `sample_idx` with the reference's parallel structure:
+    ceil(P / p)-sized chunks, one per worker (bin/chess:196-214)."""
+    size = int(math.ceil(len(sample_idx) / cores))
+    chunks = [sample_idx[i:i + size] for i in range(0, len(sample_idx), size)]
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_chunk, chunks)
+    dt = time.perf_counter() - t0
+    return dt, [row for part in out for row in part]
+
+
+def cpu_sample(n_pairs, target):
+    target = max(1, min(n_pairs, target))
+    return [int(v) for v in np.linspace(0, n_pairs - 1, target).round().astype(int)]
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU oracle port, all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    genome, ref, qry, pairs = make_workload(0)
+    cpu_setup(genome, ref, qry, pairs, args.window)
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        probe = cpu_sample(len(pairs), cores)
+        dt, _ = cpu_run(probe, pool, cores)
+        per_pair_core = dt  # one pair per core
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        target = int(max(cores, min(len(pairs), cores * budget / max(per_pair_core, 1e-3))))
+        idx = cpu_sample(len(pairs), target)
+        for _ in range(args.warmup):
+            cpu_run(idx, pool, cores)
+        times = [cpu_run(idx, pool, cores)[0] for _ in range(args.steps)]
+    total = float(np.sum(times))
+    value = len(idx) * args.steps / total
+    n_bins = len(genome.regions())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, len(pairs), n_bins, sample=len(idx)),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d pairs per step, evenly spaced; oracle/chess_oracle.py (reference "
+                                   "algorithm restated: dict-of-dict gather, restated skimage SSIM, reference SN) "
+                                   "under a %d-process fork pool with ceil(P/p) chunks" % (len(idx), len(pairs), cores)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_pairs, n_bins, sample=None):
+    cfg = {"workload": "configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb, chess sim %s, SN on"
+                       % (n_bins, "-r 1 (default)" if args.window == "r1" else "-a 7"),
+           "pairs_per_gpu": n_pairs, "bins_per_pair": 81, "window": args.window,
+           "l2": "flushed before every step (512 MiB write)",
+           "parallelism": "pairs sharded, one process per GPU, no collective"}
+    if sample is not None:
+        cfg["pairs_per_step_cpu_sample"] = sample
+    return cfg
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import chess_b200 as cb
+    from chess_b200 import _native
+    from chess_b200._native import lib, check
+    from chess_b200.engine import get_context, region_spans, build_pair_table
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    genome, ref, qry, pairs = make_workload(rank)
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    params = window_params(args.window)
+    p = _native.make_params(compute_sn=True, kernel=args.kernel, **params)
+    ctx = get_context(local_rank)
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    # ---- cold end-to-end once: host COO -> H2D -> O/E -> band -> compare -> D2H (also the setup)
+    rf, rn = region_spans(trees, [q[1] for q in pairs])
+    qf, qn = region_spans(trees, [q[2] for q in pairs])
+    flip = np.array([1 if a.strand != b.strand else 0 for _, a, b in pairs], dtype=np.int32)
+    max_n = int(max(rn.max(), qn.max()))
+    n_pairs = len(pairs)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    re_ = cb.observed_expected_arrays(regions, ref, device=local_rank)
+    qe = cb.observed_expected_arrays(regions, qry, device=local_rank)
+    rw, rband = re_.band_on(local_rank, max_n)
+    qw, qband = qe.band_on(local_rank, max_n)
+    table = build_pair_table(rf, rn, rw, qf, qn, qw, flip)
+    h_ssim, h_sn = np.empty(n_pairs), np.empty(n_pairs)
+    h_status = np.empty(n_pairs, dtype=np.int32)
+
+    def host_step():
+        check(lib.chess_compare_batch_host(ctx.handle, ptr(rband), ptr(qband), table.ctypes.data_as(C.c_void_p),
+                                           n_pairs, max_n, C.byref(p), h_ssim.ctypes.data_as(C.c_void_p),
+                                           h_sn.ctypes.data_as(C.c_void_p), h_status.ctypes.data_as(C.c_void_p), sp),
+              ctx.handle, "chess_compare_batch_host")
+        valid = h_ssim[~np.isnan(h_ssim)]
+        return (h_ssim - valid.mean()) / valid.std()
+
+    host_step()
+    cold_s = time.perf_counter() - t0
+    coo_bytes = int(sum(len(s[2]) * 16 for s in (ref, qry)))
+
+    # ---- resident buffers for the device-timed steps
+    d_table = torch.from_numpy(table.view(np.uint8)).to(dev)
+    d_ssim = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    d_sn = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    d_z = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    d_status = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def device_step(e0=None, e1=None, e2=None):
+        if e0 is not None:
+            e0.record()
+        check(lib.chess_compare_batch(ctx.handle, ptr(rband), ptr(qband), ptr(d_table), n_pairs, max_n,
+                                      C.byref(p), ptr(d_ssim), ptr(d_sn), ptr(d_status), sp),
+              ctx.handle, "chess_compare_batch")
+        if e1 is not None:
+            e1.record()
+        check(lib.chess_zscore(ctx.handle, ptr(d_ssim), n_pairs, ptr(d_z), sp), ctx.handle, "chess_zscore")
+        if e2 is not None:
+            e2.record()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        device_step()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        device_step(*ev[k])
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launches() - launches0
+    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
+    kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    total_ms = float(np.sum(step_ms))
+
+    # ---- end to end through the host-buffer C-ABI call
+    for _ in range(3):
+        host_step()
+    barrier()
+    e2e_t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        host_step()
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    # the flush is not part of the step: time it alone and subtract
+    torch.cuda.synchronize(dev)
+    f0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+    e2e_s -= time.perf_counter() - f0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ok = int((h_status == 0).sum())
+    z_dev = d_z.cpu().numpy()
+    z_host = host_step()
+    z_dev_ok = bool(np.allclose(z_dev, z_host, rtol=1e-9, atol=1e-12, equal_nan=True))
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        cnt = torch.tensor([n_pairs], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        all_pairs = int(cnt[0])
+    else:
+        all_pairs = n_pairs
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = all_pairs * args.steps / (total_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    alg_bytes = float(np.sum(2.0 * np.maximum(rn, qn).astype(np.float64) ** 2 * 8 + 24))
+    kavg_ms = float(np.mean(kern_ms))
+    achieved = alg_bytes / (kavg_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, n_pairs, len(regions)),
+                       pairs_ok=ok, wall_s_timed_region=wall, zscore_device_matches_host=z_dev_ok,
+                       e2e_cold={"seconds": cold_s, "pairs_per_s": n_pairs / cold_s,
+                                 "h2d_bytes": coo_bytes + table.nbytes,
+                                 "what": "host COO -> H2D -> expected+O/E -> band -> compare -> D2H, first call "
+                                         "(includes CUDA context/module load)"}),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": recorded_traffic(args.window),
+                     "kernel": "compare (gather+mask+SSIM+SN), %.1f us per launch, %d pairs" % (kavg_ms * 1e3, n_pairs),
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+        "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pairs/s",
+                "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_pairs * 20),
+                "call": "chess_compare_batch_host + host z-score"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(genome, ref, qry, pairs, args, re_, qe, h_ssim, h_sn)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(genome, ref, qry, pairs, args, re_, qe, gpu_ssim, gpu_sn):
+    """Oracle on the host cores, bounded sample (~10-30 s), same inputs as the GPU run."""
+    import multiprocessing as mp
+    oe = [list(zip(*[x.tolist() for x in s.triples()])) for s in (re_, qe)]  # the very O/E the GPU used
+    cpu_setup(genome, ref, qry, pairs, args.window, oe=oe)
+    cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        probe = cpu_sample(len(pairs), cores)
+        dt, _ = cpu_run(probe, pool, cores)
+        target = int(max(cores, min(len(pairs), cores * 15.0 / max(dt, 1e-3))))
+        idx = cpu_sample(len(pairs), target)
+        dt, rows = cpu_run(idx, pool, cores)
+    worst = 0.0
+    for i, (_, s, sn) in zip(idx, rows):
+        for got, want in ((gpu_ssim[i], s), (gpu_sn[i], sn)):
+            if not (np.isnan(want) and np.isnan(got)):
+                worst = max(worst, abs(got - want) / max(abs(want), 1e-300))
+    return {"value": len(idx) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d pairs, evenly spaced, one pass; oracle/chess_oracle.py under a %d-process fork "
+                      "pool with ceil(P/p) chunks (reference algorithm restated, not skimage itself)"
+                      % (len(idx), len(pairs), cores),
+            "seconds": dt, "max_rel_dev_gpu_vs_cpu": worst}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

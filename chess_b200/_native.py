@@ -18,12 +18,13 @@ class ChessNativeError(RuntimeError):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        # build on first use when a compiler is around; never fall back to CPU code
-        try:
-            from . import build as _build
-            _build.build()
-        except Exception as exc:  # pragma: no cover - depends on the toolchain
+    # (Re)build when the sources changed since the library was made; the stamp
+    # check is a hash of the few .cu files.  Never fall back to CPU code.
+    try:
+        from . import build as _build
+        _build.build()
+    except Exception as exc:  # pragma: no cover - depends on the toolchain
+        if not os.path.exists(LIB_PATH):
             raise ImportError(
                 "chess_b200: native library {} is missing and could not be built ({}). "
                 "Run `python -m chess_b200.build`; there is no CPU fallback.".format(LIB_PATH, exc))
@@ -74,6 +75,7 @@ SIGNATURES = {
     "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library disagree

@@ -147,6 +147,61 @@ extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
   return CHESS_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(1024) zscore_kernel(const double *__restrict__ s, long long n,
+                                                      double *__restrict__ z) {
+  __shared__ double red[33];
+  __shared__ double red2[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double sum = 0.0, cnt = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double v = s[i];
+    if (v == v) { sum += v; cnt += 1.0; }
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  if (lane == 0) { red[warp] = sum; red2[warp] = cnt; }
+  __syncthreads();
+  if (warp == 0) {
+    sum = warp_sum(red[lane]); cnt = warp_sum(red2[lane]);
+    if (lane == 0) { red[32] = sum; red2[32] = cnt; }
+  }
+  __syncthreads();
+  cnt = red2[32];
+  const double mean = red[32] / cnt;
+  __syncthreads();
+  double ss = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double v = s[i];
+    if (v == v) ss += (v - mean) * (v - mean);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    ss = warp_sum(red[lane]);
+    if (lane == 0) red[32] = ss;
+  }
+  __syncthreads();
+  const double sd = sqrt(red[32] / cnt);
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double v = s[i];
+    z[i] = isfinite(v) ? (v - mean) / sd : CUDART_NAN;
+  }
+}
+}  // namespace
+
+extern "C" int chess_zscore(chess_ctx *ctx, const double *ssim, int64_t n, double *z, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!ssim || !z))) { ctx->err = "chess_zscore: bad arguments"; return CHESS_ERR_ARG; }
+  if (n == 0) return CHESS_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  zscore_kernel<<<1, 1024, 0, stream>>>(ssim, (long long)n, z);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
 extern "C" int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n,
                               double *out, void *stream_) {
   if (!ctx) return CHESS_ERR_ARG;

@@ -161,6 +161,11 @@ int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base, const doubl
                              const chess_params *params, double *ssim_host, double *sn_host,
                              int32_t *status_host, void *stream);
 
+/* K6: run-level z-score, bin/chess:216-233: z = (ssim - nanmean) / nanstd
+ * (ddof 0) over the non-NaN entries; entries that are not finite keep NaN.
+ * Fixed-order reduction in one CTA, so the result is deterministic. DEVICE.   */
+int chess_zscore(chess_ctx *ctx, const double *ssim, int64_t n, double *z, void *stream);
+
 /* SN(M1, M2, size=7), chess/sim.py:15-30, on n x n DEVICE matrices.          */
 int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n, double *out,
                    void *stream);
