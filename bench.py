@@ -250,7 +250,8 @@ def run_ours(args, rank, world, local_rank):
     regions = genome.regions()
     trees = cb.region_interval_trees(regions)
     params = window_params(args.window)
-    p = _native.make_params(compute_sn=True, kernel=args.kernel, **params)
+    p = _native.make_params(compute_sn=True, kernel=args.kernel,
+                            flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES, **params)
     ctx = get_context(local_rank)
     sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731

@@ -45,7 +45,7 @@ class chess_params(C.Structure):
     _fields_ = [("min_bins", C.c_int32), ("keep_unmappable", C.c_int32),
                 ("abs_window", C.c_int32), ("compute_sn", C.c_int32),
                 ("rel_window", C.c_double), ("mappability_cutoff", C.c_double),
-                ("default_value", C.c_double), ("kernel", C.c_int32), ("reserved", C.c_int32)]
+                ("default_value", C.c_double), ("kernel", C.c_int32), ("flags", C.c_int32)]
 
 
 PAIR_DTYPE = np.dtype([("ref_off", "<i8"), ("qry_off", "<i8"), ("ref_pitch", "<i4"),
@@ -54,6 +54,7 @@ PAIR_DTYPE = np.dtype([("ref_off", "<i8"), ("qry_off", "<i8"), ("ref_pitch", "<i
 assert PAIR_DTYPE.itemsize == C.sizeof(chess_pair) == 40
 
 PAIR_OK, PAIR_NOT_FOUND, PAIR_TOO_SMALL, PAIR_UNMAPPABLE, PAIR_WINDOW_EXCEEDS = range(5)
+FLAG_SYMMETRIC, FLAG_EQUAL_SIZES = 1, 2
 
 _vp, _i32, _i64, _dbl, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_size_t
 _PP = C.POINTER(chess_params)
@@ -122,7 +123,7 @@ class Context(object):
 
 def make_params(min_bins=20, keep_unmappable_bins=False, absolute_window_size=None,
                 relative_window_size=1.0, mappability_cutoff=0.1, default_value=1,
-                compute_sn=True, kernel=0):
+                compute_sn=True, kernel=0, flags=0):
     p = chess_params()
     p.min_bins = int(min_bins)
     p.keep_unmappable = 1 if keep_unmappable_bins else 0
@@ -132,5 +133,5 @@ def make_params(min_bins=20, keep_unmappable_bins=False, absolute_window_size=No
     p.mappability_cutoff = float(mappability_cutoff)
     p.default_value = float(default_value)
     p.kernel = int(kernel)
-    p.reserved = 0
+    p.flags = int(flags)
     return p

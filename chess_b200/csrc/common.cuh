@@ -30,11 +30,15 @@ struct chess_ctx {
     }                                                                                  \
   } while (0)
 
+// Internal per-pair status: the tuned kernel could not take this pair, the
+// generic kernel must (never visible to callers).
+#define CHESS_PAIR_RETRY 100
+
 // Internal launchers (one per translation unit).
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                                  const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                  const chess_params &p, double *ssim, double *sn, int32_t *status,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, bool retry_only = false);
 int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                               const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                               const chess_params &p, double *ssim, double *sn, int32_t *status,

@@ -1,10 +1,528 @@
-// Tuned compare kernels (dispatch stub: nothing specialised yet, the generic
-// kernel handles every batch).
+// Tuned compare kernels for sm_100a.
+//
+// compare_r1_kernel -- the default `chess sim` regime (-r 1: the SSIM window is
+// the whole compacted matrix or one less, so the SSIM map is 1x1 or 2x2,
+// chess/sim.py:356-365) on symmetric band data with equal-sized sides.
+//
+// Work decomposition (B200: 148 SMs, FP64 64 FMA/clk/SM, L2 ~70 B/clk/SM for
+// 8-byte loads; the samples stay L2-resident, so the kernel is bound by issue
+// slots and the FP64 pipe, not by HBM):
+//   * one CTA per pair, NW warps; warp w owns a band of rows, lane l owns the
+//     G adjacent columns G*l .. G*l+G-1 in registers (row loads are contiguous
+//     across the warp: coalesced 8-byte loads straight from the band);
+//   * pass 1 (masks): per-band partial column sums + an "any non-default"
+//     bit per column; columns are classified exactly like
+//     np.sum(m, 0) == n * default (chess/sim.py:82-85): all-default columns are
+//     masked, columns whose blocked sum is not within 1e-7 of n * default are
+//     not, and the (practically never occurring) near-coincidences are
+//     re-summed sequentially in row order by one thread;
+//   * pass 2: global moments of x, y (SSIM, with min / max for the data range)
+//     and the SN map: running 7-row sums of d = x - y and d*d down each column
+//     (a 7-deep register ring supplies the outgoing row; a per-column count of
+//     non-zero d snaps all-zero windows to exactly 0, which is what makes
+//     0/0 -> NaN -> skipped come out as in np.nanmean), 7-column sums across
+//     lanes by three up / three down shuffles of strip prefix / suffix sums,
+//     then |mean| / var with a Newton-refined reciprocal.  Windows whose
+//     one-pass variance shows cancellation are recomputed two-pass in numpy's
+//     summation order straight from memory.
+//   * the 2x2 SSIM map needs only totals, the first / last row totals and four
+//     corner elements, because every moment map of a symmetric pair is
+//     symmetric (column totals = row totals).
+// Pairs this kernel cannot take (unequal sizes, n > 32*G) are marked
+// CHESS_PAIR_RETRY and handled by the generic kernel.
+#include <math_constants.h>
+
 #include "common.cuh"
 
-int chess_launch_compare_fast(chess_ctx *, const double *, const double *, const chess_pair *, int64_t,
-                              int32_t, const chess_params &, double *, double *, int32_t *, cudaStream_t,
-                              bool *handled) {
-  *handled = false;
+namespace {
+
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+__device__ __forceinline__ double np_sum49(const double *a) {
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+#pragma unroll
+  for (int i = 8; i < 48; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  return __dadd_rn(res, a[48]);
+}
+
+// Exact (numpy-order, two-pass) |nanmean| / nanvar of the 7x7 window at (rc, c),
+// read from memory through the compaction map.
+__device__ __noinline__ double sn_window_exact(const double *R, const double *Q, size_t rp, size_t qp,
+                                               const short *kmap, int n, int flip, int rc, int c,
+                                               int np_, double cnt) {
+  double val[49];
+  unsigned long long okmask = 0ull;
+  for (int wi = 0; wi < 7; ++wi) {
+    const int rr = rc - 3 + wi;
+    const bool rok = rr >= 0 && rr < np_;
+    const int kr = rok ? kmap[rr] : 0;
+    for (int wj = 0; wj < 7; ++wj) {
+      const int cc = c - 3 + wj;
+      const bool v = rok && cc >= 0 && cc < np_;
+      double dv = 0.0;
+      if (v) {
+        const int kc = kmap[cc];
+        const double x = __ldg(R + (size_t)kr * rp + kc);
+        const double y = flip ? __ldg(Q + (size_t)(n - 1 - kr) * qp + (n - 1 - kc))
+                              : __ldg(Q + (size_t)kr * qp + kc);
+        dv = __dsub_rn(x, y);
+        okmask |= 1ull << (wi * 7 + wj);
+      }
+      val[wi * 7 + wj] = dv;
+    }
+  }
+  const double avg = __ddiv_rn(np_sum49(val), cnt);
+  for (int s = 0; s < 49; ++s) {
+    const double dv = ((okmask >> s) & 1ull) ? __dsub_rn(val[s], avg) : 0.0;
+    val[s] = __dmul_rn(dv, dv);
+  }
+  const double var = __ddiv_rn(np_sum49(val), cnt);
+  return __ddiv_rn(fabs(avg), var);
+}
+
+__device__ __forceinline__ bool is_nonzero(double v) {
+  return ((unsigned long long)__double_as_longlong(v) << 1) != 0ull;  // +-0 -> false, everything else true
+}
+
+template <int G, int NW, bool WITH_SN>
+__global__ void __launch_bounds__(32 * NW, (G <= 4 ? 4 : 2))
+compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
+                  const chess_pair *__restrict__ pairs, long long n_pairs, chess_params p,
+                  double *__restrict__ ssim_out, double *__restrict__ sn_out,
+                  int *__restrict__ status_out) {
+  constexpr int NCOL = 32 * G;
+  constexpr int NT = 32 * NW;
+  __shared__ short kmap[NCOL];
+  __shared__ double cpart[NW][2][NCOL];
+  __shared__ unsigned char ndpart[NW][NCOL];
+  __shared__ unsigned char mflag[NCOL];
+  __shared__ double red[NW][12];
+  __shared__ double rowtot[2][5];
+  __shared__ int icount[4];
+  __shared__ int wcount[NW];
+  extern __shared__ __align__(16) double ringbuf[];  // NW * 7 * G * 32 doubles (SN only)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double qnan = CUDART_NAN;
+  const int c0 = G * lane;
+
+  for (long long pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+    const chess_pair d = pairs[pi];
+    int status = CHESS_PAIR_OK;
+    if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
+    else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
+    else if (d.ref_n != d.qry_n || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
+    if (status != CHESS_PAIR_OK) {
+      if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = status; }
+      continue;
+    }
+    const int n = d.ref_n;
+    const int flip = d.flip;
+    const double *R = ref_base + d.ref_off;
+    const double *Q = qry_base + d.qry_off;
+    const size_t rp = (size_t)d.ref_pitch, qp = (size_t)d.qry_pitch;
+    const bool use_masks = p.mappability_cutoff > 0;
+    int np_ = n;
+
+    if (use_masks) {
+      // ---- pass 1: blocked column sums + non-default bits, one row band per warp
+      const int B1 = (n + NW - 1) / NW;
+      const int r_lo = warp * B1, r_hi = min(n, r_lo + B1);
+      const unsigned long long defbits = (unsigned long long)__double_as_longlong(p.default_value);
+      double cs_r[G], cs_q[G];
+      unsigned long long nd_r[G], nd_q[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; nd_r[g] = 0ull; nd_q[g] = 0ull; }
+#pragma unroll 2
+      for (int r = r_lo; r < r_hi; ++r) {
+        const double *rowR = R + (size_t)r * rp;
+        const double *rowQ = Q + (size_t)(flip ? n - 1 - r : r) * qp;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int c = c0 + g;
+          if (c < n) {
+            const double x = __ldg(rowR + c);
+            const double y = __ldg(rowQ + (flip ? n - 1 - c : c));
+            cs_r[g] += x;
+            cs_q[g] += y;
+            nd_r[g] |= (unsigned long long)__double_as_longlong(x) ^ defbits;
+            nd_q[g] |= (unsigned long long)__double_as_longlong(y) ^ defbits;
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = c0 + g;
+        cpart[warp][0][c] = cs_r[g];
+        cpart[warp][1][c] = cs_q[g];
+        ndpart[warp][c] = (unsigned char)((nd_r[g] ? 1 : 0) | (nd_q[g] ? 2 : 0));
+      }
+      if (tid < 4) icount[tid] = 0;
+      __syncthreads();
+      // ---- classify columns
+      const double target = (double)n * p.default_value;
+      int cnt_r = 0, cnt_q = 0;
+      for (int c = tid; c < n; c += NT) {
+        double sr = cpart[0][0][c], sq = cpart[0][1][c];
+        unsigned nd = ndpart[0][c];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) { sr += cpart[w][0][c]; sq += cpart[w][1][c]; nd |= ndpart[w][c]; }
+        bool fr, fq;
+        if (!(nd & 1)) fr = true;  // every entry equals the default: n additions of 0 or 1 are exact
+        else if (fabs(sr - target) > 1e-7 * (fabs(sr) + fabs(target))) fr = false;
+        else {  // near-coincidence: decide with the reference's own summation order
+          double s = 0.0;
+          for (int r = 0; r < n; ++r) s += __ldg(R + (size_t)r * rp + c);
+          fr = s == target;
+        }
+        if (!(nd & 2)) fq = true;
+        else if (fabs(sq - target) > 1e-7 * (fabs(sq) + fabs(target))) fq = false;
+        else {
+          double s = 0.0;
+          const int cq = flip ? n - 1 - c : c;
+          for (int r = 0; r < n; ++r) s += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
+          fq = s == target;
+        }
+        mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+        cnt_r += fr;
+        cnt_q += fq;
+      }
+      cnt_r = warp_sum_int(cnt_r);
+      cnt_q = warp_sum_int(cnt_q);
+      if (lane == 0 && (cnt_r | cnt_q)) { atomicAdd(&icount[0], cnt_r); atomicAdd(&icount[1], cnt_q); }
+      __syncthreads();
+      const int tot_r = icount[0], tot_q = icount[1];
+      if ((double)tot_r / (double)n > p.mappability_cutoff || (double)tot_q / (double)n > p.mappability_cutoff) {
+        if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = CHESS_PAIR_UNMAPPABLE; }
+        __syncthreads();
+        continue;
+      }
+      // ---- compaction map
+      if (!p.keep_unmappable && (tot_r + tot_q) > 0) {
+        int carry = 0;
+        for (int base = 0; base < n; base += NT) {
+          const int c = base + tid;
+          const bool keep = c < n && mflag[c] == 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (lane == 0) wcount[warp] = __popc(bal);
+          __syncthreads();
+          int woff = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            const int v = wcount[w];
+            if (w < warp) woff += v;
+            total += v;
+          }
+          if (keep) kmap[carry + woff + __popc(bal & ((1u << lane) - 1u))] = (short)c;
+          carry += total;
+          __syncthreads();
+        }
+        np_ = carry;
+      } else {
+        for (int c = tid; c < n; c += NT) kmap[c] = (short)c;
+        __syncthreads();
+      }
+    } else {
+      for (int c = tid; c < n; c += NT) kmap[c] = (short)c;
+      __syncthreads();
+    }
+
+    // ---- window rule (-r 1): the whole matrix, made odd, at least 3
+    int win = (np_ & 1) ? np_ : np_ - 1;
+    if (win < 3) win = 3;
+    if (win > np_) {
+      if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      __syncthreads();
+      continue;
+    }
+    const int m = np_ - win + 1;  // 1 or 2
+
+    // ---- pass 2
+    int kc[G];
+    unsigned vmask = 0u;
+    double ccnt[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int c = c0 + g;
+      const bool v = c < np_;
+      if (v) vmask |= 1u << g;
+      kc[g] = v ? (int)kmap[c] : 0;
+      ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+    }
+
+    // first / last row totals of the five moments (needed for the 2x2 SSIM map only)
+    if (m == 2 && warp < 2) {
+      const int rr = warp == 0 ? 0 : np_ - 1;
+      const int kr = kmap[rr];
+      const double *rowR = R + (size_t)kr * rp;
+      const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+      double t[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (vmask & (1u << g)) {
+          const double x = __ldg(rowR + kc[g]), y = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
+          t[0] += x; t[1] += y; t[2] = fma(x, x, t[2]); t[3] = fma(y, y, t[3]); t[4] = fma(x, y, t[4]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        t[k] = warp_sum(t[k]);
+        if (lane == 0) rowtot[warp][k] = t[k];
+      }
+    }
+
+    const int B2 = (np_ + NW - 1) / NW;
+    const int lo = warp * B2, hi = min(np_, lo + B2);
+    double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
+    double vmax = -CUDART_INF, vmin = CUDART_INF;
+    double sn_sum = 0.0;
+    int sn_cnt = 0;
+    double Sd[G], Se[G];
+    int nz[G];
+    // 7-row ring of d for this lane's columns, [slot][g][lane] so that lanes hit distinct banks
+    double *myring = ringbuf + (size_t)warp * 7 * G * 32 + lane;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      Sd[g] = 0.0; Se[g] = 0.0; nz[g] = 0;
+      if (WITH_SN) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
+      }
+    }
+
+    if (lo < hi) {
+      const int first = WITH_SN ? lo - 3 : lo;
+      const int last = WITH_SN ? hi + 3 : hi;  // exclusive
+      int slot = 0;
+      for (int rr = first; rr < last; ++rr) {
+        const bool live = rr >= 0 && rr < np_;
+        const bool own = rr >= lo && rr < hi;
+        double x[G], y[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { x[g] = 0.0; y[g] = 0.0; }
+        if (live) {
+          const int kr = kmap[rr];
+          const double *rowR = R + (size_t)kr * rp;
+          const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (vmask & (1u << g)) {
+              x[g] = __ldg(rowR + kc[g]);
+              y[g] = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
+            }
+          }
+        }
+        if (own) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (vmask & (1u << g)) {
+              T0 += x[g]; T1 += y[g];
+              T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
+              vmax = fmax(vmax, fmax(x[g], y[g]));
+              vmin = fmin(vmin, fmin(x[g], y[g]));
+            }
+          }
+        }
+        if (WITH_SN) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const double dv = x[g] - y[g];
+            double *cell = myring + (slot * G + g) * 32;
+            const double dold = *cell;
+            *cell = dv;
+            Sd[g] += dv; Sd[g] -= dold;
+            Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+            nz[g] += (int)is_nonzero(dv) - (int)is_nonzero(dold);
+            if (nz[g] == 0) { Sd[g] = 0.0; Se[g] = 0.0; }
+          }
+          slot = slot == 6 ? 0 : slot + 1;
+          const int rc = rr - 3;
+          if (rc >= lo && rc < hi) {
+            const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+            // strip prefix sums, then three values from each neighbour lane
+            double P1[G + 1], P2[G + 1];
+            P1[0] = 0.0; P2[0] = 0.0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+            double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
+              const double s1 = P1[G] - P1[G - 1 - j], s2 = P2[G] - P2[G - 1 - j];
+              up1[j] = __shfl_up_sync(0xffffffffu, s1, 1);
+              up2[j] = __shfl_up_sync(0xffffffffu, s2, 1);
+              dn1[j] = __shfl_down_sync(0xffffffffu, P1[j + 1], 1);
+              dn2[j] = __shfl_down_sync(0xffffffffu, P2[j + 1], 1);
+              if (lane == 0) { up1[j] = 0.0; up2[j] = 0.0; }
+              if (lane == 31) { dn1[j] = 0.0; dn2[j] = 0.0; }
+            }
+            unsigned suspicious = 0u;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (vmask & (1u << g)) {
+                const int a = g - 3 < 0 ? 0 : g - 3;
+                const int b = g + 3 > G - 1 ? G - 1 : g + 3;
+                double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
+                double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+                if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+                if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+                if (w2 != 0.0) {
+                  const double cnt = rcnt * ccnt[g];
+                  const double m2 = w2 * cnt;
+                  const double den = fma(-w1, w1, m2);
+                  if (m2 > 1e-280 && den > 1e-6 * m2) {
+                    sn_sum += fabs(w1) * cnt * fast_rcp(den);
+                    sn_cnt += 1;
+                  } else {
+                    suspicious |= 1u << g;
+                  }
+                }
+              }
+            }
+            if (suspicious) {  // cold: cancellation in the one-pass variance -> numpy's own two passes
+              for (int g = 0; g < G; ++g) {
+                if (suspicious & (1u << g)) {
+                  const int c = c0 + g;
+                  const double cnt = rcnt * (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+                  const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+                  if (gq == gq) { sn_sum += gq; sn_cnt += 1; }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
+    // ---- combine the row bands (fixed order -> deterministic)
+    T0 = warp_sum(T0); T1 = warp_sum(T1); T2 = warp_sum(T2); T3 = warp_sum(T3); T4 = warp_sum(T4);
+    vmax = warp_max(vmax); vmin = warp_min(vmin);
+    sn_sum = warp_sum(sn_sum);
+    sn_cnt = warp_sum_int(sn_cnt);
+    if (lane == 0) {
+      red[warp][0] = T0; red[warp][1] = T1; red[warp][2] = T2; red[warp][3] = T3; red[warp][4] = T4;
+      red[warp][5] = vmax; red[warp][6] = vmin; red[warp][7] = sn_sum; red[warp][8] = (double)sn_cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t[5] = {0, 0, 0, 0, 0}, mx = -CUDART_INF, mn = CUDART_INF, ss = 0.0, sc = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) t[k] += red[w][k];
+        mx = fmax(mx, red[w][5]); mn = fmin(mn, red[w][6]);
+        ss += red[w][7]; sc += red[w][8];
+      }
+      const double drange = mx - mn;
+      const double NP = (double)win * (double)win;
+      const double cov_norm = NP / (NP - 1.0);
+      const double C1 = (0.01 * drange) * (0.01 * drange);
+      const double C2 = (0.03 * drange) * (0.03 * drange);
+      double acc = 0.0;
+      for (int a = 0; a < m; ++a) {
+        for (int b = 0; b < m; ++b) {
+          double h[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) h[k] = t[k];
+          if (m == 2) {
+            // window (a, b) leaves out row er and column ec; column totals = row totals (symmetry)
+            const int ia = a == 0 ? 1 : 0, ib = b == 0 ? 1 : 0;
+            const int er = ia ? np_ - 1 : 0, ec = ib ? np_ - 1 : 0;
+            const int kr = kmap[er], kcc = kmap[ec];
+            const double x = __ldg(R + (size_t)kr * rp + kcc);
+            const double y = flip ? __ldg(Q + (size_t)(n - 1 - kr) * qp + (n - 1 - kcc))
+                                  : __ldg(Q + (size_t)kr * qp + kcc);
+            const double corner[5] = {x, y, x * x, y * y, x * y};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) h[k] = h[k] - rowtot[ia][k] - rowtot[ib][k] + corner[k];
+          }
+          const double ux = h[0] / NP, uy = h[1] / NP;
+          const double uxx = h[2] / NP, uyy = h[3] / NP, uxy = h[4] / NP;
+          const double vx = cov_norm * (uxx - ux * ux);
+          const double vy = cov_norm * (uyy - uy * uy);
+          const double vxy = cov_norm * (uxy - ux * uy);
+          const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2;
+          const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+          acc += (A1 * A2) / (B1 * B2);
+        }
+      }
+      ssim_out[pi] = acc / (double)(m * m);
+      sn_out[pi] = WITH_SN ? ss / sc : qnan;
+      status_out[pi] = CHESS_PAIR_OK;
+    }
+    __syncthreads();
+  }
+}
+
+template <int G, int NW, bool WITH_SN>
+int launch_r1_sn(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
+                 int64_t n_pairs, const chess_params &p, double *ssim, double *sn, int32_t *status,
+                 cudaStream_t stream) {
+  auto kern = compare_r1_kernel<G, NW, WITH_SN>;
+  const size_t smem = WITH_SN ? (size_t)NW * 7 * G * 32 * sizeof(double) : 0;
+  static bool configured = false;  // static + dynamic shared memory can exceed the 48 KB default
+  if (!configured && smem > 0) {
+    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  long long grid = n_pairs;
+  const long long cap = (long long)ctx->sm_count * 32;
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, 32 * NW, smem, stream>>>(ref_base, qry_base, pairs, (long long)n_pairs, p, ssim, sn,
+                                                 status);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
+}
+
+template <int G, int NW>
+int launch_r1(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
+              int64_t n_pairs, const chess_params &p, double *ssim, double *sn, int32_t *status,
+              cudaStream_t stream) {
+  if (p.compute_sn)
+    return launch_r1_sn<G, NW, true>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  return launch_r1_sn<G, NW, false>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+}
+
+}  // namespace
+
+int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                              const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                              const chess_params &p, double *ssim, double *sn, int32_t *status,
+                              cudaStream_t stream, bool *handled) {
+  *handled = false;
+  const bool symmetric = (p.flags & CHESS_FLAG_SYMMETRIC) != 0;
+  const bool r1 = p.abs_window == 0 && p.rel_window == 1.0;
+  const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
+  if (!symmetric || !r1 || !plain_default || max_n > 256) return CHESS_OK;
+  int rc;
+  if (max_n <= 96) rc = launch_r1<3, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 128) rc = launch_r1<4, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 160) rc = launch_r1<5, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 192) rc = launch_r1<6, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 224) rc = launch_r1<7, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else rc = launch_r1<8, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  if (rc) return rc;
+  *handled = true;
+  if (!(p.flags & CHESS_FLAG_EQUAL_SIZES)) {
+    // some pairs may need the resize path: let the generic kernel pick up the RETRY marks
+    rc = chess_launch_compare_generic(ctx, ref_base, qry_base, pairs, n_pairs, max_n, p, ssim, sn, status,
+                                      stream, /*retry_only=*/true);
+  }
+  return rc;
 }

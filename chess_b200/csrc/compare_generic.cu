@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(BLOCK)
 compare_generic_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
                        const chess_pair *__restrict__ pairs, long long n_pairs, int ncap,
                        chess_params p, double *__restrict__ ssim_out, double *__restrict__ sn_out,
-                       int *__restrict__ status_out) {
+                       int *__restrict__ status_out, int retry_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *red = reinterpret_cast<double *>(smem_raw);
   double *buf = red + kRed;                       // max(5*ncap, 9*ncap+12) doubles
@@ -176,6 +176,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
   const double qnan = CUDART_NAN;
 
   for (long long pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+    if (retry_only && status_out[pi] != CHESS_PAIR_RETRY) continue;  // uniform per CTA
     const chess_pair d = pairs[pi];
     int status = CHESS_PAIR_OK;
     if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
@@ -435,7 +436,7 @@ size_t generic_smem_bytes(int ncap) {
 template <int BLOCK, int CPT>
 int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
            int64_t n_pairs, int ncap, const chess_params &p, double *ssim, double *sn,
-           int32_t *status, cudaStream_t stream) {
+           int32_t *status, cudaStream_t stream, bool retry_only) {
   auto kern = compare_generic_kernel<BLOCK, CPT>;
   const size_t smem = generic_smem_bytes(ncap);
   if ((int)smem > ctx->max_smem_optin) {
@@ -449,7 +450,7 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > n_pairs) grid = n_pairs;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(ref_base, qry_base, pairs, (long long)n_pairs, ncap, p,
-                                                ssim, sn, status);
+                                                ssim, sn, status, retry_only ? 1 : 0);
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
@@ -460,15 +461,15 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                                  const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                  const chess_params &p, double *ssim, double *sn, int32_t *status,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, bool retry_only) {
   if (n_pairs <= 0) return CHESS_OK;
   if (max_n > 1024) {
     ctx->err = "compare: submatrices larger than 1024 bins are not supported";
     return CHESS_ERR_UNSUPPORTED;
   }
   const int ncap = max_n < 32 ? 32 : max_n;
-  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
-  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
-  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
-  return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream);
+  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
+  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
+  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
+  return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
 }

@@ -250,7 +250,11 @@ class CompareEngine(object):
         if total == 0:
             return ssim, sn, status
         max_n = int(max(ref_n.max(), qry_n.max(), 1))
-        p = _native.make_params(default_value=default_value, **params)
+        # the band is symmetric by construction; equal sizes let the kernels skip the resize path
+        flags = _native.FLAG_SYMMETRIC
+        if bool(np.all((ref_n == qry_n) | (ref_n <= 0) | (qry_n <= 0))):
+            flags |= _native.FLAG_EQUAL_SIZES
+        p = _native.make_params(default_value=default_value, flags=flags, **params)
         ndev = min(len(self.devices), total)
         bounds = np.linspace(0, total, ndev + 1).astype(np.int64)
         pending = []
@@ -286,6 +290,8 @@ class CompareEngine(object):
             ssim[lo:hi] = h_ssim.numpy()
             sn[lo:hi] = h_sn.numpy()
             status[lo:hi] = h_status.numpy()
+        if (status >= 100).any():
+            raise _native.ChessNativeError("internal error: a pair was left unprocessed by the tuned kernel")
         return ssim, sn, status
 
     def compare(self, pairs, compute_sn=True, default_value=1, **params):

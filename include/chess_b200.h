@@ -85,8 +85,16 @@ typedef struct chess_params {
   double mappability_cutoff; /* --mappability-cutoff                           */
   double default_value;      /* fill / masking value, 1 from the CLI           */
   int32_t kernel;            /* 0 = auto, 1 = force the generic kernel         */
-  int32_t reserved;
+  int32_t flags;             /* CHESS_FLAG_* promises about the batch          */
 } chess_params;
+
+/* Promises the caller makes about a batch; they only select faster kernels and
+ * never change results.  SYMMETRIC: every submatrix view is symmetric (true for
+ * the band, chess/helpers.py:301-302 mirrors every edge).  EQUAL_SIZES: every
+ * pair whose two regions were found has ref_n == qry_n (no resize step,
+ * chess/sim.py:323-329).                                                      */
+#define CHESS_FLAG_SYMMETRIC 1
+#define CHESS_FLAG_EQUAL_SIZES 2
 
 /* ---- context ------------------------------------------------------------ */
 int chess_abi_version(void);

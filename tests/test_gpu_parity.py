@@ -346,3 +346,28 @@ def test_multi_gpu_sharding_identical(cb, chr2_like):
     one = cb.CompareEngine(re_, trees, qe, trees, devices=[0]).compare(pairs)
     two = cb.CompareEngine(re_, trees, qe, trees, devices=[0, 1]).compare(pairs)
     assert np.array_equal(one[1], two[1], equal_nan=True) and np.array_equal(one[2], two[2], equal_nan=True)
+
+
+def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
+    """The tuned kernels and the generic kernel are two implementations of the
+    same function: statuses identical, values within 1e-9."""
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    flipped = [(pid, r, cb.GenomicRegion(chromosome=q.chromosome, start=q.start, end=q.end, strand="-"))
+               for pid, r, q in pairs[::5]]
+    for kw in (dict(), dict(keep_unmappable_bins=True), dict(mappability_cutoff=0.3), dict(compute_sn=False)):
+        for plist in (pairs, flipped):
+            fast = eng.compare(plist, **kw)
+            gen = eng.compare(plist, kernel=1, **kw)
+            assert np.array_equal(fast[3], gen[3])
+            np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+            np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+    # windows of 40..200 bins exercise every column-strip width of the tuned kernel
+    from chess_b200 import synth
+    for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000):
+        plist = synth.sliding_pairs(genome, window_bp, 900000)
+        fast = eng.compare(plist)
+        gen = eng.compare(plist, kernel=1)
+        assert np.array_equal(fast[3], gen[3])
+        np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+        np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
