@@ -99,6 +99,160 @@ __device__ __forceinline__ bool is_nonzero(double v) {
   return ((unsigned long long)__double_as_longlong(v) << 1) != 0ull;  // +-0 -> false, everything else true
 }
 
+constexpr int kSuspCap = 24;
+
+struct Band2 {
+  double T0, T1, T2, T3, T4, vmax, vmin, sn_sum;
+  int sn_cnt;
+};
+
+// Pass 2 over the rows [lo, hi) of one band (plus three halo rows either side for SN).
+// COMPACT = some bins were removed: rows / columns go through kmap; otherwise the
+// lane's G columns are G consecutive doubles from one base pointer.
+template <int G, bool WITH_SN, bool COMPACT>
+__device__ __forceinline__ void pass2_rows(const double *__restrict__ R, const double *__restrict__ Q,
+                                           size_t rp, size_t qp, const short *kmap, int n, int np_,
+                                           int flip, int lo, int hi, int lane, double *myring,
+                                           int *susp, int *susp_n, Band2 &acc) {
+  const int c0 = G * lane;
+  unsigned vmask = 0u;
+  double ccnt[G];
+  int kc[COMPACT ? G : 1];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int c = c0 + g;
+    if (c < np_) vmask |= 1u << g;
+    if (COMPACT) kc[g] = c < np_ ? (int)kmap[c] : 0;
+    ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+  }
+  double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
+  double vmax = -CUDART_INF, vmin = CUDART_INF;
+  double sn_sum = 0.0;
+  int sn_cnt = 0;
+  double Sd[G], Se[G];
+  unsigned hist[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    Sd[g] = 0.0; Se[g] = 0.0; hist[g] = 0u;
+    if (WITH_SN) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
+    }
+  }
+  const int first = WITH_SN ? lo - 3 : lo;
+  const int last = WITH_SN ? hi + 3 : hi;  // exclusive
+  const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+  int slot = 0;
+  for (int rr = first; rr < last; ++rr) {
+    const bool live = rr >= 0 && rr < np_;
+    const bool own = rr >= lo && rr < hi;
+    double x[G], y[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { x[g] = 0.0; y[g] = 0.0; }
+    if (live) {
+      if (COMPACT) {
+        const int kr = kmap[rr];
+        const double *rowR = R + (size_t)kr * rp;
+        const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (vmask & (1u << g)) {
+            x[g] = __ldg(rowR + kc[g]);
+            y[g] = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
+          }
+        }
+      } else {
+        const double *xr = R + (size_t)rr * rp + c0;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (vmask & (1u << g)) x[g] = __ldg(xr + g);
+        if (!flip) {
+          const double *yr = Q + (size_t)rr * qp + c0;
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (vmask & (1u << g)) y[g] = __ldg(yr + g);
+        } else {
+          const double *yr = Q + (size_t)(n - 1 - rr) * qp + (n - 1 - c0);
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (vmask & (1u << g)) y[g] = __ldg(yr - g);
+        }
+      }
+    }
+    if (own) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        T0 += x[g]; T1 += y[g];
+        T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
+        if (vmask & (1u << g)) {  // plain compare-selects: the data are finite, no NaN handling needed
+          const double hi2 = x[g] > y[g] ? x[g] : y[g];
+          const double lo2 = x[g] > y[g] ? y[g] : x[g];
+          vmax = hi2 > vmax ? hi2 : vmax;
+          vmin = lo2 < vmin ? lo2 : vmin;
+        }
+      }
+    }
+    if (WITH_SN) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const double dv = x[g] - y[g];
+        double *cell = myring + (slot * G + g) * 32;
+        const double dold = *cell;
+        *cell = dv;
+        Sd[g] += dv; Sd[g] -= dold;
+        Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+        // 7-row history of "d != 0": an all-zero column window is snapped to exactly 0, so an
+        // all-zero 7x7 window gives w2 == 0 exactly (0/0 -> NaN -> skipped by np.nanmean)
+        hist[g] = ((hist[g] << 1) & 0x7fu) | (is_nonzero(dv) ? 1u : 0u);
+        if (hist[g] == 0u) Se[g] = 0.0;
+      }
+      slot = slot == 6 ? 0 : slot + 1;
+      const int rc = rr - 3;
+      if (rc >= lo && rc < hi) {
+        const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+        // strip prefix sums, then three partial sums from each neighbour lane (lane 31 is never
+        // valid -- the launcher guarantees n <= 31*G -- so the rotation wraps onto zeros)
+        double P1[G + 1], P2[G + 1];
+        P1[0] = 0.0; P2[0] = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+        double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
+          const double s1 = P1[G] - P1[G - 1 - j], s2 = P2[G] - P2[G - 1 - j];
+          up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+          up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+          dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+          dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int a = g - 3 < 0 ? 0 : g - 3;
+          const int b = g + 3 > G - 1 ? G - 1 : g + 3;
+          double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
+          double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+          if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+          if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+          const double cnt = rcnt * ccnt[g];
+          const double m2 = w2 * cnt;
+          const double den = fma(-w1, w1, m2);
+          const bool valid = (vmask & (1u << g)) != 0u;
+          const bool good = m2 > 1e-280 && den > 1e-6 * m2;
+          const double gq = fabs(w1) * cnt * fast_rcp(den);
+          if (valid && good) { sn_sum += gq; sn_cnt += 1; }
+          if (valid && !good && w2 != 0.0) {  // rare
+            const int e = atomicAdd(susp_n, 1);
+            if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
+          }
+        }
+      }
+    }
+  }
+  acc.T0 = T0; acc.T1 = T1; acc.T2 = T2; acc.T3 = T3; acc.T4 = T4;
+  acc.vmax = vmax; acc.vmin = vmin; acc.sn_sum = sn_sum; acc.sn_cnt = sn_cnt;
+}
+
 template <int G, int NW, bool WITH_SN>
 __global__ void __launch_bounds__(32 * NW, (G <= 4 ? 4 : 2))
 compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
@@ -115,6 +269,8 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
   __shared__ double rowtot[2][5];
   __shared__ int icount[4];
   __shared__ int wcount[NW];
+  __shared__ int susp[NW][kSuspCap];
+  __shared__ int susp_n[NW];
   extern __shared__ __align__(16) double ringbuf[];  // NW * 7 * G * 32 doubles (SN only)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,7 +282,7 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     int status = CHESS_PAIR_OK;
     if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
     else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
-    else if (d.ref_n != d.qry_n || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
+    else if (d.ref_n != d.qry_n || d.ref_n > 31 * G) status = CHESS_PAIR_RETRY;
     if (status != CHESS_PAIR_OK) {
       if (tid == 0) { ssim_out[pi] = qnan; sn_out[pi] = qnan; status_out[pi] = status; }
       continue;
@@ -150,14 +306,14 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
       for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; nd_r[g] = 0ull; nd_q[g] = 0ull; }
 #pragma unroll 2
       for (int r = r_lo; r < r_hi; ++r) {
-        const double *rowR = R + (size_t)r * rp;
-        const double *rowQ = Q + (size_t)(flip ? n - 1 - r : r) * qp;
+        const double *xr = R + (size_t)r * rp + c0;
+        const double *yr = flip ? Q + (size_t)(n - 1 - r) * qp + (n - 1 - c0) : Q + (size_t)r * qp + c0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const int c = c0 + g;
           if (c < n) {
-            const double x = __ldg(rowR + c);
-            const double y = __ldg(rowQ + (flip ? n - 1 - c : c));
+            const double x = __ldg(xr + g);
+            const double y = __ldg(flip ? yr - g : yr + g);
             cs_r[g] += x;
             cs_q[g] += y;
             nd_r[g] |= (unsigned long long)__double_as_longlong(x) ^ defbits;
@@ -253,18 +409,6 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     const int m = np_ - win + 1;  // 1 or 2
 
     // ---- pass 2
-    int kc[G];
-    unsigned vmask = 0u;
-    double ccnt[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c = c0 + g;
-      const bool v = c < np_;
-      if (v) vmask |= 1u << g;
-      kc[g] = v ? (int)kmap[c] : 0;
-      ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-    }
-
     // first / last row totals of the five moments (needed for the 2x2 SSIM map only)
     if (m == 2 && warp < 2) {
       const int rr = warp == 0 ? 0 : np_ - 1;
@@ -274,8 +418,10 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
       double t[5] = {0, 0, 0, 0, 0};
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        if (vmask & (1u << g)) {
-          const double x = __ldg(rowR + kc[g]), y = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
+        const int c = c0 + g;
+        if (c < np_) {
+          const int kcc = kmap[c];
+          const double x = __ldg(rowR + kcc), y = __ldg(rowQ + (flip ? n - 1 - kcc : kcc));
           t[0] += x; t[1] += y; t[2] = fma(x, x, t[2]); t[3] = fma(y, y, t[3]); t[4] = fma(x, y, t[4]);
         }
       }
@@ -288,126 +434,47 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
 
     const int B2 = (np_ + NW - 1) / NW;
     const int lo = warp * B2, hi = min(np_, lo + B2);
-    double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
-    double vmax = -CUDART_INF, vmin = CUDART_INF;
-    double sn_sum = 0.0;
-    int sn_cnt = 0;
-    double Sd[G], Se[G];
-    int nz[G];
-    // 7-row ring of d for this lane's columns, [slot][g][lane] so that lanes hit distinct banks
+    Band2 acc;
+    acc.T0 = acc.T1 = acc.T2 = acc.T3 = acc.T4 = 0.0;
+    acc.vmax = -CUDART_INF; acc.vmin = CUDART_INF; acc.sn_sum = 0.0; acc.sn_cnt = 0;
     double *myring = ringbuf + (size_t)warp * 7 * G * 32 + lane;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      Sd[g] = 0.0; Se[g] = 0.0; nz[g] = 0;
-      if (WITH_SN) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
-      }
-    }
-
+    if (lane == 0) susp_n[warp] = 0;
+    __syncwarp();
     if (lo < hi) {
-      const int first = WITH_SN ? lo - 3 : lo;
-      const int last = WITH_SN ? hi + 3 : hi;  // exclusive
-      int slot = 0;
-      for (int rr = first; rr < last; ++rr) {
-        const bool live = rr >= 0 && rr < np_;
-        const bool own = rr >= lo && rr < hi;
-        double x[G], y[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { x[g] = 0.0; y[g] = 0.0; }
-        if (live) {
-          const int kr = kmap[rr];
-          const double *rowR = R + (size_t)kr * rp;
-          const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (vmask & (1u << g)) {
-              x[g] = __ldg(rowR + kc[g]);
-              y[g] = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
-            }
+      if (np_ == n)
+        pass2_rows<G, WITH_SN, false>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, myring, susp[warp],
+                                      &susp_n[warp], acc);
+      else
+        pass2_rows<G, WITH_SN, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, myring, susp[warp],
+                                     &susp_n[warp], acc);
+      if (WITH_SN) {
+        // cold: windows whose one-pass variance cancelled -> numpy's own two passes, after the hot loop
+        __syncwarp();
+        const int ns = susp_n[warp];
+        if (ns > 0 && ns <= kSuspCap) {
+          for (int e = lane; e < ns; e += 32) {
+            const int rc = susp[warp][e] >> 16, c = susp[warp][e] & 0xffff;
+            const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                        (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+            const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+            if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
           }
-        }
-        if (own) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (vmask & (1u << g)) {
-              T0 += x[g]; T1 += y[g];
-              T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
-              vmax = fmax(vmax, fmax(x[g], y[g]));
-              vmin = fmin(vmin, fmin(x[g], y[g]));
-            }
-          }
-        }
-        if (WITH_SN) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const double dv = x[g] - y[g];
-            double *cell = myring + (slot * G + g) * 32;
-            const double dold = *cell;
-            *cell = dv;
-            Sd[g] += dv; Sd[g] -= dold;
-            Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
-            nz[g] += (int)is_nonzero(dv) - (int)is_nonzero(dold);
-            if (nz[g] == 0) { Sd[g] = 0.0; Se[g] = 0.0; }
-          }
-          slot = slot == 6 ? 0 : slot + 1;
-          const int rc = rr - 3;
-          if (rc >= lo && rc < hi) {
-            const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-            // strip prefix sums, then three values from each neighbour lane
-            double P1[G + 1], P2[G + 1];
-            P1[0] = 0.0; P2[0] = 0.0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
-            double up1[3], up2[3], dn1[3], dn2[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
-              const double s1 = P1[G] - P1[G - 1 - j], s2 = P2[G] - P2[G - 1 - j];
-              up1[j] = __shfl_up_sync(0xffffffffu, s1, 1);
-              up2[j] = __shfl_up_sync(0xffffffffu, s2, 1);
-              dn1[j] = __shfl_down_sync(0xffffffffu, P1[j + 1], 1);
-              dn2[j] = __shfl_down_sync(0xffffffffu, P2[j + 1], 1);
-              if (lane == 0) { up1[j] = 0.0; up2[j] = 0.0; }
-              if (lane == 31) { dn1[j] = 0.0; dn2[j] = 0.0; }
-            }
-            unsigned suspicious = 0u;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (vmask & (1u << g)) {
-                const int a = g - 3 < 0 ? 0 : g - 3;
-                const int b = g + 3 > G - 1 ? G - 1 : g + 3;
-                double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
-                double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
-                if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
-                if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
-                if (w2 != 0.0) {
-                  const double cnt = rcnt * ccnt[g];
-                  const double m2 = w2 * cnt;
-                  const double den = fma(-w1, w1, m2);
-                  if (m2 > 1e-280 && den > 1e-6 * m2) {
-                    sn_sum += fabs(w1) * cnt * fast_rcp(den);
-                    sn_cnt += 1;
-                  } else {
-                    suspicious |= 1u << g;
-                  }
-                }
-              }
-            }
-            if (suspicious) {  // cold: cancellation in the one-pass variance -> numpy's own two passes
-              for (int g = 0; g < G; ++g) {
-                if (suspicious & (1u << g)) {
-                  const int c = c0 + g;
-                  const double cnt = rcnt * (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-                  const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
-                  if (gq == gq) { sn_sum += gq; sn_cnt += 1; }
-                }
-              }
+        } else if (ns > kSuspCap) {  // list overflow: redo the whole band exactly
+          acc.sn_sum = 0.0; acc.sn_cnt = 0;
+          for (int rc = lo; rc < hi; ++rc) {
+            for (int c = lane; c < np_; c += 32) {
+              const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                          (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+              const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+              if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
             }
           }
         }
       }
     }
+    double T0 = acc.T0, T1 = acc.T1, T2 = acc.T2, T3 = acc.T3, T4 = acc.T4;
+    double vmax = acc.vmax, vmin = acc.vmin, sn_sum = acc.sn_sum;
+    int sn_cnt = acc.sn_cnt;
 
     // ---- combine the row bands (fixed order -> deterministic)
     T0 = warp_sum(T0); T1 = warp_sum(T1); T2 = warp_sum(T2); T3 = warp_sum(T3); T4 = warp_sum(T4);
@@ -509,13 +576,13 @@ int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const doub
   const bool symmetric = (p.flags & CHESS_FLAG_SYMMETRIC) != 0;
   const bool r1 = p.abs_window == 0 && p.rel_window == 1.0;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
-  if (!symmetric || !r1 || !plain_default || max_n > 256) return CHESS_OK;
+  if (!symmetric || !r1 || !plain_default || max_n > 248) return CHESS_OK;
   int rc;
-  if (max_n <= 96) rc = launch_r1<3, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
-  else if (max_n <= 128) rc = launch_r1<4, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
-  else if (max_n <= 160) rc = launch_r1<5, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
-  else if (max_n <= 192) rc = launch_r1<6, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
-  else if (max_n <= 224) rc = launch_r1<7, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  if (max_n <= 93) rc = launch_r1<3, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 124) rc = launch_r1<4, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 155) rc = launch_r1<5, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 186) rc = launch_r1<6, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
+  else if (max_n <= 217) rc = launch_r1<7, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
   else rc = launch_r1<8, 4>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
   if (rc) return rc;
   *handled = true;
