@@ -1,0 +1,68 @@
+"""Sharding of region pairs over GPUs and the host-side gather of results.
+
+The comparison path shards naturally: every pair is independent
+(chess/sim.py:306-380), so there is no data-path collective.  The reference
+splits the pair list into ceil(P/p) chunks, one per worker
+(chess/helpers.py:530-534, bin/chess:212-214) and collects (pair_ix, ssim, sn)
+through a queue; here contiguous ranges go to ranks / devices and the results
+(24 bytes per pair) are concatenated in pair order on rank 0.
+
+Two ways to use several GPUs:
+  * one process, several devices: ``CompareEngine(devices=[...])`` uses
+    :func:`shard_bounds` and copies results back itself;
+  * one process per GPU under ``torchrun``: each rank calls
+    :func:`my_shard`, compares its slice, then :func:`gather_to_rank0`.
+Works with the ``gloo`` backend on CPU tensors (tests) and ``nccl``/``gloo`` on
+a GPU box; the payload is tiny, so the backend is irrelevant for speed.
+"""
+import numpy as np
+
+
+def shard_bounds(total, world):
+    """world+1 monotone offsets: shard k is [b[k], b[k+1]); sizes differ by at most 1."""
+    world = max(int(world), 1)
+    base, extra = divmod(int(total), world)
+    sizes = [base + (1 if k < extra else 0) for k in range(world)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def my_shard(total, rank, world):
+    b = shard_bounds(total, world)
+    return int(b[rank]), int(b[rank + 1])
+
+
+def gather_to_rank0(local_arrays, total, rank, world, dist=None):
+    """Concatenate per-rank result arrays in rank (= pair) order on rank 0.
+
+    ``local_arrays`` is a tuple of 1-D numpy arrays covering this rank's shard.
+    Returns the full arrays on rank 0 and ``None`` elsewhere.
+    """
+    if world == 1 or dist is None:
+        return tuple(np.asarray(a) for a in local_arrays)
+    import torch
+    bounds = shard_bounds(total, world)
+    longest = int(np.max(np.diff(bounds)))
+    out = []
+    for arr in local_arrays:
+        arr = np.ascontiguousarray(arr)
+        pad = np.zeros(longest, dtype=arr.dtype)
+        pad[:len(arr)] = arr
+        t = torch.from_numpy(pad)
+        bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, gather_list=bucket, dst=0)
+        if rank == 0:
+            full = np.empty(total, dtype=arr.dtype)
+            for k in range(world):
+                full[bounds[k]:bounds[k + 1]] = bucket[k].numpy()[:bounds[k + 1] - bounds[k]]
+            out.append(full)
+    return tuple(out) if rank == 0 else None
+
+
+def max_over_ranks(value, world, dist=None, device=None):
+    """Max of a Python float over ranks (timings are always max-over-ranks)."""
+    if world == 1 or dist is None:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])

@@ -21,6 +21,7 @@ import torch
 
 from . import _native
 from ._native import PAIR_DTYPE, lib, check
+from .distributed import shard_bounds
 
 _contexts = {}
 
@@ -256,7 +257,7 @@ class CompareEngine(object):
             flags |= _native.FLAG_EQUAL_SIZES
         p = _native.make_params(default_value=default_value, flags=flags, **params)
         ndev = min(len(self.devices), total)
-        bounds = np.linspace(0, total, ndev + 1).astype(np.int64)
+        bounds = shard_bounds(total, ndev)
         pending = []
         for k in range(ndev):
             device = self.devices[k]
