@@ -46,11 +46,14 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return y;
 }
 
-__device__ __forceinline__ double np_sum49(const double *a) {
+// numpy's pairwise summation for n = 49 contiguous doubles (n < 128: eight running accumulators
+// over blocks of eight, combined as a tree, then the tail).  Deliberately not unrolled: this is the
+// cold path and must stay small in registers, because its frame adds to the hot kernel's.
+__device__ __noinline__ double np_sum49(const double *a) {
   double r[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = a[j];
-#pragma unroll
+#pragma unroll 1
   for (int i = 8; i < 48; i += 8) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
@@ -67,10 +70,12 @@ __device__ __noinline__ double sn_window_exact(const double *R, const double *Q,
                                                int np_, double cnt) {
   double val[49];
   unsigned long long okmask = 0ull;
+#pragma unroll 1
   for (int wi = 0; wi < 7; ++wi) {
     const int rr = rc - 3 + wi;
     const bool rok = rr >= 0 && rr < np_;
     const int kr = rok ? kmap[rr] : 0;
+#pragma unroll 1
     for (int wj = 0; wj < 7; ++wj) {
       const int cc = c - 3 + wj;
       const bool v = rok && cc >= 0 && cc < np_;
@@ -87,6 +92,7 @@ __device__ __noinline__ double sn_window_exact(const double *R, const double *Q,
     }
   }
   const double avg = __ddiv_rn(np_sum49(val), cnt);
+#pragma unroll 1
   for (int s = 0; s < 49; ++s) {
     const double dv = ((okmask >> s) & 1ull) ? __dsub_rn(val[s], avg) : 0.0;
     val[s] = __dmul_rn(dv, dv);
@@ -106,27 +112,74 @@ struct Band2 {
   int sn_cnt;
 };
 
-// Pass 2 over the rows [lo, hi) of one band (plus three halo rows either side for SN).
-// COMPACT = some bins were removed: rows / columns go through kmap; otherwise the
-// lane's G columns are G consecutive doubles from one base pointer.
-template <int G, bool WITH_SN, bool COMPACT>
-__device__ __forceinline__ void pass2_rows(const double *__restrict__ R, const double *__restrict__ Q,
-                                           size_t rp, size_t qp, const short *kmap, int n, int np_,
-                                           int flip, int lo, int hi, int lane, double *myring,
-                                           int *susp, int *susp_n, Band2 &acc) {
+// Per-lane view of the compacted pair: column offsets of the lane's G columns in both matrices.
+template <int G>
+struct LaneCols {
+  int xo[G], yo[G];   // element offsets inside a row of the reference / query view
+  bool valid[G];
+};
+
+template <int G>
+__device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, int n, int np_, int flip,
+                                          int lane) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int c = G * lane + g;
+    lc.valid[g] = c < np_;
+    const int kc = lc.valid[g] ? (int)kmap[c] : 0;
+    lc.xo[g] = kc;
+    lc.yo[g] = flip ? n - 1 - kc : kc;
+  }
+}
+
+// Loop A of pass 2: moments of x and y and min / max over the rows [lo, hi) of the band.
+template <int G>
+__device__ __forceinline__ void moments_rows(const double *__restrict__ R, const double *__restrict__ Q,
+                                             size_t rp, size_t qp, const short *kmap, int n, int flip,
+                                             int lo, int hi, const LaneCols<G> &lc, Band2 &acc) {
+  double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
+  double vmax = -CUDART_INF, vmin = CUDART_INF;
+#pragma unroll 4
+  for (int rr = lo; rr < hi; ++rr) {
+    const int kr = kmap[rr];
+    const double *rowR = R + (size_t)kr * rp;
+    const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+    double x[G], y[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      x[g] = 0.0; y[g] = 0.0;
+      if (lc.valid[g]) { x[g] = __ldg(rowR + lc.xo[g]); y[g] = __ldg(rowQ + lc.yo[g]); }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      T0 += x[g]; T1 += y[g];
+      T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
+      // branch-free compare-selects (the data are finite: no NaN handling needed)
+      const bool xgt = x[g] > y[g];
+      const double hi2 = xgt ? x[g] : y[g];
+      const double lo2 = xgt ? y[g] : x[g];
+      vmax = (lc.valid[g] & (hi2 > vmax)) ? hi2 : vmax;
+      vmin = (lc.valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+    }
+  }
+  acc.T0 = T0; acc.T1 = T1; acc.T2 = T2; acc.T3 = T3; acc.T4 = T4;
+  acc.vmax = vmax; acc.vmin = vmin;
+}
+
+// Loop B of pass 2: the SN map of the band rows [lo, hi) (three halo rows either side feed the
+// 7-row column sums).
+template <int G>
+__device__ __forceinline__ void sn_rows(const double *__restrict__ R, const double *__restrict__ Q,
+                                        size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
+                                        int lo, int hi, int lane, const LaneCols<G> &lc, double *myring,
+                                        int *susp, int *susp_n, Band2 &acc) {
   const int c0 = G * lane;
-  unsigned vmask = 0u;
   double ccnt[G];
-  int kc[COMPACT ? G : 1];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int c = c0 + g;
-    if (c < np_) vmask |= 1u << g;
-    if (COMPACT) kc[g] = c < np_ ? (int)kmap[c] : 0;
     ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
   }
-  double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
-  double vmax = -CUDART_INF, vmin = CUDART_INF;
   double sn_sum = 0.0;
   int sn_cnt = 0;
   double Sd[G], Se[G];
@@ -134,123 +187,94 @@ __device__ __forceinline__ void pass2_rows(const double *__restrict__ R, const d
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     Sd[g] = 0.0; Se[g] = 0.0; hist[g] = 0u;
-    if (WITH_SN) {
 #pragma unroll
-      for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
-    }
+    for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
   }
-  const int first = WITH_SN ? lo - 3 : lo;
-  const int last = WITH_SN ? hi + 3 : hi;  // exclusive
+  const int first = lo - 3, last = hi + 3;  // exclusive
   const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+  double *ringrow = myring;
   int slot = 0;
+  // software pipeline: the loads of row rr+1 are issued before row rr is processed
+  double xn[G], yn[G];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
+    if (row >= 0 && row < np_) {
+      const int kr = kmap[row];
+      const double *rowR = R + (size_t)kr * rp;
+      const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (lc.valid[g]) { xn[g] = __ldg(rowR + lc.xo[g]); yn[g] = __ldg(rowQ + lc.yo[g]); }
+      }
+    }
+  };
+  fetch(first);
   for (int rr = first; rr < last; ++rr) {
-    const bool live = rr >= 0 && rr < np_;
-    const bool own = rr >= lo && rr < hi;
-    double x[G], y[G];
+    double dv[G];
+    bool nzv[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) { x[g] = 0.0; y[g] = 0.0; }
-    if (live) {
-      if (COMPACT) {
-        const int kr = kmap[rr];
-        const double *rowR = R + (size_t)kr * rp;
-        const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+    for (int g = 0; g < G; ++g) { dv[g] = xn[g] - yn[g]; nzv[g] = xn[g] != yn[g]; }
+    if (rr + 1 < last) fetch(rr + 1);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (vmask & (1u << g)) {
-            x[g] = __ldg(rowR + kc[g]);
-            y[g] = __ldg(rowQ + (flip ? n - 1 - kc[g] : kc[g]));
-          }
-        }
-      } else {
-        const double *xr = R + (size_t)rr * rp + c0;
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (vmask & (1u << g)) x[g] = __ldg(xr + g);
-        if (!flip) {
-          const double *yr = Q + (size_t)rr * qp + c0;
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            if (vmask & (1u << g)) y[g] = __ldg(yr + g);
-        } else {
-          const double *yr = Q + (size_t)(n - 1 - rr) * qp + (n - 1 - c0);
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            if (vmask & (1u << g)) y[g] = __ldg(yr - g);
-        }
-      }
+    for (int g = 0; g < G; ++g) {
+      double *cell = ringrow + g * 32;
+      const double dold = *cell;
+      *cell = dv[g];
+      Sd[g] += dv[g]; Sd[g] -= dold;
+      Se[g] = fma(dv[g], dv[g], Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+      // 7-row history of "d != 0": an all-zero column window is snapped to exactly 0, so an
+      // all-zero 7x7 window gives w2 == 0 exactly (0/0 -> NaN -> skipped by np.nanmean)
+      hist[g] = ((hist[g] << 1) & 0x7fu) | (nzv[g] ? 1u : 0u);
+      Se[g] = hist[g] == 0u ? 0.0 : Se[g];
     }
-    if (own) {
+    if (slot == 6) { slot = 0; ringrow = myring; } else { slot += 1; ringrow += G * 32; }
+    const int rc = rr - 3;
+    if (rc >= lo && rc < hi) {
+      const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+      // strip prefix sums, then three partial sums from each neighbour lane (lane 31 is never
+      // valid -- the launcher guarantees n <= 31*G -- so the rotation wraps onto zeros)
+      double P1[G + 1], P2[G + 1];
+      P1[0] = 0.0; P2[0] = 0.0;
+      P1[1] = Sd[0]; P2[1] = Se[0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+      double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
+        const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
+        const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+        up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+        up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+        dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+        dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+      }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        T0 += x[g]; T1 += y[g];
-        T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
-        if (vmask & (1u << g)) {  // plain compare-selects: the data are finite, no NaN handling needed
-          const double hi2 = x[g] > y[g] ? x[g] : y[g];
-          const double lo2 = x[g] > y[g] ? y[g] : x[g];
-          vmax = hi2 > vmax ? hi2 : vmax;
-          vmin = lo2 < vmin ? lo2 : vmin;
-        }
-      }
-    }
-    if (WITH_SN) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const double dv = x[g] - y[g];
-        double *cell = myring + (slot * G + g) * 32;
-        const double dold = *cell;
-        *cell = dv;
-        Sd[g] += dv; Sd[g] -= dold;
-        Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
-        // 7-row history of "d != 0": an all-zero column window is snapped to exactly 0, so an
-        // all-zero 7x7 window gives w2 == 0 exactly (0/0 -> NaN -> skipped by np.nanmean)
-        hist[g] = ((hist[g] << 1) & 0x7fu) | (is_nonzero(dv) ? 1u : 0u);
-        if (hist[g] == 0u) Se[g] = 0.0;
-      }
-      slot = slot == 6 ? 0 : slot + 1;
-      const int rc = rr - 3;
-      if (rc >= lo && rc < hi) {
-        const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-        // strip prefix sums, then three partial sums from each neighbour lane (lane 31 is never
-        // valid -- the launcher guarantees n <= 31*G -- so the rotation wraps onto zeros)
-        double P1[G + 1], P2[G + 1];
-        P1[0] = 0.0; P2[0] = 0.0;
-#pragma unroll
-        for (int g = 0; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
-        double up1[3], up2[3], dn1[3], dn2[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
-          const double s1 = P1[G] - P1[G - 1 - j], s2 = P2[G] - P2[G - 1 - j];
-          up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
-          up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
-          dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
-          dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int a = g - 3 < 0 ? 0 : g - 3;
-          const int b = g + 3 > G - 1 ? G - 1 : g + 3;
-          double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
-          double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
-          if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
-          if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
-          const double cnt = rcnt * ccnt[g];
-          const double m2 = w2 * cnt;
-          const double den = fma(-w1, w1, m2);
-          const bool valid = (vmask & (1u << g)) != 0u;
-          const bool good = m2 > 1e-280 && den > 1e-6 * m2;
-          const double gq = fabs(w1) * cnt * fast_rcp(den);
-          if (valid && good) { sn_sum += gq; sn_cnt += 1; }
-          if (valid && !good && w2 != 0.0) {  // rare
-            const int e = atomicAdd(susp_n, 1);
-            if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
-          }
+        const int a = g - 3 < 0 ? 0 : g - 3;
+        const int b = g + 3 > G - 1 ? G - 1 : g + 3;
+        double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
+        double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+        if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+        if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+        const double cnt = rcnt * ccnt[g];
+        const double m2 = w2 * cnt;
+        const double den = fma(-w1, w1, m2);
+        // one-pass variance is trusted when var > 1e-6 * E[d^2] (and E[d^2] is not denormal-small)
+        const bool good = lc.valid[g] & (den > fma(m2, 1e-6, 1e-290));
+        const double gq = fabs(w1) * cnt * fast_rcp(den);
+        sn_sum += good ? gq : 0.0;
+        sn_cnt += good ? 1 : 0;
+        if (!good && lc.valid[g] && w2 != 0.0) {  // rare: cancellation -> exact recompute after the loop
+          const int e = atomicAdd(susp_n, 1);
+          if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
         }
       }
     }
   }
-  acc.T0 = T0; acc.T1 = T1; acc.T2 = T2; acc.T3 = T3; acc.T4 = T4;
-  acc.vmax = vmax; acc.vmin = vmin; acc.sn_sum = sn_sum; acc.sn_cnt = sn_cnt;
+  acc.sn_sum = sn_sum;
+  acc.sn_cnt = sn_cnt;
 }
 
 template <int G, int NW, bool WITH_SN>
@@ -304,20 +328,38 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
       unsigned long long nd_r[G], nd_q[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; nd_r[g] = 0ull; nd_q[g] = 0ull; }
-#pragma unroll 2
-      for (int r = r_lo; r < r_hi; ++r) {
-        const double *xr = R + (size_t)r * rp + c0;
-        const double *yr = flip ? Q + (size_t)(n - 1 - r) * qp + (n - 1 - c0) : Q + (size_t)r * qp + c0;
+      {
+        const double *xp = R + (size_t)r_lo * rp + c0;
+        const double *yp = flip ? Q + (size_t)(n - 1 - r_lo) * qp + (n - c0 - G) : Q + (size_t)r_lo * qp + c0;
+        const ptrdiff_t ystep = flip ? -(ptrdiff_t)qp : (ptrdiff_t)qp;
+        bool valid[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int c = c0 + g;
-          if (c < n) {
-            const double x = __ldg(xr + g);
-            const double y = __ldg(flip ? yr - g : yr + g);
-            cs_r[g] += x;
-            cs_q[g] += y;
-            nd_r[g] |= (unsigned long long)__double_as_longlong(x) ^ defbits;
-            nd_q[g] |= (unsigned long long)__double_as_longlong(y) ^ defbits;
+        for (int g = 0; g < G; ++g) valid[g] = c0 + g < n;
+#pragma unroll 4
+        for (int r = r_lo; r < r_hi; ++r) {
+          double x[G], y[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) { x[g] = p.default_value; y[g] = p.default_value; }
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (valid[g]) x[g] = __ldg(xp + g);
+          if (!flip) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (valid[g]) y[g] = __ldg(yp + g);
+          } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (valid[g]) y[g] = __ldg(yp + (G - 1 - g));
+          }
+          xp += rp;
+          yp += ystep;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            cs_r[g] += x[g];
+            cs_q[g] += y[g];
+            nd_r[g] |= (unsigned long long)__double_as_longlong(x[g]) ^ defbits;
+            nd_q[g] |= (unsigned long long)__double_as_longlong(y[g]) ^ defbits;
           }
         }
       }
@@ -441,12 +483,11 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     if (lane == 0) susp_n[warp] = 0;
     __syncwarp();
     if (lo < hi) {
-      if (np_ == n)
-        pass2_rows<G, WITH_SN, false>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, myring, susp[warp],
-                                      &susp_n[warp], acc);
-      else
-        pass2_rows<G, WITH_SN, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, myring, susp[warp],
-                                     &susp_n[warp], acc);
+      LaneCols<G> lc;
+      lane_cols<G>(lc, kmap, n, np_, flip, lane);
+      moments_rows<G>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc);
+      if (WITH_SN) sn_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp[warp],
+                              &susp_n[warp], acc);
       if (WITH_SN) {
         // cold: windows whose one-pass variance cancelled -> numpy's own two passes, after the hot loop
         __syncwarp();
