@@ -14,7 +14,7 @@ Numbers on the JSON line
   value      pairs/s, whole job, samples and pair table already resident in HBM,
              CUDA-event time of K steps (L2 flushed before every step).
   e2e        same work through the host-buffer C-ABI call
-             (chess_compare_batch_host): pair table from host memory, results
+             (chess_compare_band_batch_host): pair table from host memory, results
              back to host memory and z-scores, every step.
   roofline   compare kernel only: algorithmic bytes (2*n*n*8 + 24 per pair,
              SURVEY 8d) / its CUDA-event duration, against the measured HBM
@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--window", default="r1", choices=["r1", "a7"],
                     help="r1 = default `chess sim` (-r 1); a7 = -a 7")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 force the generic kernel")
+    ap.add_argument("--kernel", type=int, default=0,
+                    help="0 auto, 1 force the generic kernel, 2 the CTA-per-pair tuned kernel")
     return ap.parse_args()
 
 
@@ -266,17 +267,18 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     re_ = cb.observed_expected_arrays(regions, ref, device=local_rank)
     qe = cb.observed_expected_arrays(regions, qry, device=local_rank)
-    rw, rband = re_.band_on(local_rank, max_n)
-    qw, qband = qe.band_on(local_rank, max_n)
+    rw, rband, rsample = re_.sample_on(local_rank, max_n)
+    qw, qband, qsample = qe.sample_on(local_rank, max_n)
     table = build_pair_table(rf, rn, rw, qf, qn, qw, flip)
     h_ssim, h_sn = np.empty(n_pairs), np.empty(n_pairs)
     h_status = np.empty(n_pairs, dtype=np.int32)
 
     def host_step():
-        check(lib.chess_compare_batch_host(ctx.handle, ptr(rband), ptr(qband), table.ctypes.data_as(C.c_void_p),
-                                           n_pairs, max_n, C.byref(p), h_ssim.ctypes.data_as(C.c_void_p),
-                                           h_sn.ctypes.data_as(C.c_void_p), h_status.ctypes.data_as(C.c_void_p), sp),
-              ctx.handle, "chess_compare_batch_host")
+        check(lib.chess_compare_band_batch_host(ctx.handle, C.byref(rsample), C.byref(qsample),
+                                                table.ctypes.data_as(C.c_void_p), n_pairs, max_n, C.byref(p),
+                                                h_ssim.ctypes.data_as(C.c_void_p), h_sn.ctypes.data_as(C.c_void_p),
+                                                h_status.ctypes.data_as(C.c_void_p), sp),
+              ctx.handle, "chess_compare_band_batch_host")
         valid = h_ssim[~np.isnan(h_ssim)]
         return (h_ssim - valid.mean()) / valid.std()
 
@@ -295,9 +297,9 @@ def run_ours(args, rank, world, local_rank):
     def device_step(e0=None, e1=None, e2=None):
         if e0 is not None:
             e0.record()
-        check(lib.chess_compare_batch(ctx.handle, ptr(rband), ptr(qband), ptr(d_table), n_pairs, max_n,
-                                      C.byref(p), ptr(d_ssim), ptr(d_sn), ptr(d_status), sp),
-              ctx.handle, "chess_compare_batch")
+        check(lib.chess_compare_band_batch(ctx.handle, C.byref(rsample), C.byref(qsample), ptr(d_table), n_pairs,
+                                           max_n, C.byref(p), ptr(d_ssim), ptr(d_sn), ptr(d_status), sp),
+              ctx.handle, "chess_compare_band_batch")
         if e1 is not None:
             e1.record()
         check(lib.chess_zscore(ctx.handle, ptr(d_ssim), n_pairs, ptr(d_z), sp), ctx.handle, "chess_zscore")
@@ -390,7 +392,7 @@ def run_ours(args, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_pairs * 20),
-                "call": "chess_compare_batch_host + host z-score"},
+                "call": "chess_compare_band_batch_host + host z-score"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

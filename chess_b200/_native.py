@@ -41,6 +41,11 @@ class chess_pair(C.Structure):
                 ("flip", C.c_int32), ("reserved", C.c_int32)]
 
 
+class chess_sample(C.Structure):
+    _fields_ = [("band", C.c_void_p), ("nd_lo", C.c_void_p), ("nd_hi", C.c_void_p),
+                ("n_bins", C.c_int64), ("W", C.c_int32), ("reserved", C.c_int32)]
+
+
 class chess_params(C.Structure):
     _fields_ = [("min_bins", C.c_int32), ("keep_unmappable", C.c_int32),
                 ("abs_window", C.c_int32), ("compute_sn", C.c_int32),
@@ -58,6 +63,7 @@ FLAG_SYMMETRIC, FLAG_EQUAL_SIZES = 1, 2
 
 _vp, _i32, _i64, _dbl, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_size_t
 _PP = C.POINTER(chess_params)
+_SP = C.POINTER(chess_sample)
 
 # name -> (restype, argtypes); every symbol include/chess_b200.h declares
 SIGNATURES = {
@@ -75,6 +81,9 @@ SIGNATURES = {
     "chess_gather_submatrix": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
+    "chess_band_index_build": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp]),
+    "chess_compare_band_batch": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
+    "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }

@@ -69,6 +69,7 @@ extern "C" void chess_ctx_destroy(chess_ctx *ctx) {
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_results) cudaFree(ctx->d_results);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->d_items) cudaFree(ctx->d_items);
   delete ctx;
 }
 
@@ -109,19 +110,36 @@ extern "C" int chess_compare_batch(chess_ctx *ctx, const double *ref_base, const
                                       sn, status, stream);
 }
 
-extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
-                                        const double *qry_base, const chess_pair *pairs_host,
-                                        int64_t n_pairs, int32_t max_n, const chess_params *params,
-                                        double *ssim_host, double *sn_host, int32_t *status_host,
-                                        void *stream_) {
+extern "C" int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                                        const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                                        const chess_params *params, double *ssim, double *sn,
+                                        int32_t *status, void *stream_) {
   if (!ctx) return CHESS_ERR_ARG;
-  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
-    ctx->err = "chess_compare_batch_host: NULL buffer";
+  int rc = validate(ctx, params);
+  if (rc) return rc;
+  if (!ref || !qry || !ref->band || !qry->band ||
+      n_pairs < 0 || (n_pairs > 0 && (!pairs || !ssim || !sn || !status))) {
+    ctx->err = "chess_compare_band_batch: NULL buffer";
     return CHESS_ERR_ARG;
   }
   if (n_pairs == 0) return CHESS_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  chess_params p = *params;
+  p.flags |= CHESS_FLAG_SYMMETRIC;  // a band is symmetric by construction
+  if (p.kernel == 0) {
+    bool handled = false;
+    rc = chess_launch_compare_items(ctx, ref, qry, pairs, n_pairs, max_n, p, ssim, sn, status, stream, &handled);
+    if (rc) return rc;
+    if (handled) return CHESS_OK;
+  }
+  return chess_compare_batch(ctx, ref->band, qry->band, pairs, n_pairs, max_n, &p, ssim, sn, status, stream_);
+}
+
+// Shared body of the *_host entry points: stage the pair table, run `launch`, copy the results back.
+template <typename Launch>
+static int host_roundtrip(chess_ctx *ctx, const chess_pair *pairs_host, int64_t n_pairs, double *ssim_host,
+                          double *sn_host, int32_t *status_host, cudaStream_t stream, Launch launch) {
   const size_t pair_bytes = (size_t)n_pairs * sizeof(chess_pair);
   const size_t res_bytes = (size_t)n_pairs * (2 * sizeof(double) + sizeof(int32_t));
   int rc;
@@ -135,8 +153,7 @@ extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
   double *d_ssim = reinterpret_cast<double *>(ctx->d_results);
   double *d_sn = d_ssim + n_pairs;
   int32_t *d_status = reinterpret_cast<int32_t *>(d_sn + n_pairs);
-  rc = chess_compare_batch(ctx, ref_base, qry_base, reinterpret_cast<const chess_pair *>(ctx->d_pairs),
-                           n_pairs, max_n, params, d_ssim, d_sn, d_status, stream_);
+  rc = launch(reinterpret_cast<const chess_pair *>(ctx->d_pairs), d_ssim, d_sn, d_status);
   if (rc) return rc;
   CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_results, res_bytes, cudaMemcpyDeviceToHost, stream));
   CHESS_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -145,6 +162,44 @@ extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
   std::memcpy(sn_host, h + (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(double));
   std::memcpy(status_host, h + 2 * (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(int32_t));
   return CHESS_OK;
+}
+
+extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
+                                        const double *qry_base, const chess_pair *pairs_host,
+                                        int64_t n_pairs, int32_t max_n, const chess_params *params,
+                                        double *ssim_host, double *sn_host, int32_t *status_host,
+                                        void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
+    ctx->err = "chess_compare_batch_host: NULL buffer";
+    return CHESS_ERR_ARG;
+  }
+  if (n_pairs == 0) return CHESS_OK;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, (cudaStream_t)stream_,
+                        [&](const chess_pair *d_pairs, double *d_ssim, double *d_sn, int32_t *d_status) {
+                          return chess_compare_batch(ctx, ref_base, qry_base, d_pairs, n_pairs, max_n, params,
+                                                     d_ssim, d_sn, d_status, stream_);
+                        });
+}
+
+extern "C" int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample *ref,
+                                             const chess_sample *qry, const chess_pair *pairs_host,
+                                             int64_t n_pairs, int32_t max_n, const chess_params *params,
+                                             double *ssim_host, double *sn_host, int32_t *status_host,
+                                             void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
+    ctx->err = "chess_compare_band_batch_host: NULL buffer";
+    return CHESS_ERR_ARG;
+  }
+  if (n_pairs == 0) return CHESS_OK;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, (cudaStream_t)stream_,
+                        [&](const chess_pair *d_pairs, double *d_ssim, double *d_sn, int32_t *d_status) {
+                          return chess_compare_band_batch(ctx, ref, qry, d_pairs, n_pairs, max_n, params,
+                                                          d_ssim, d_sn, d_status, stream_);
+                        });
 }
 
 namespace {

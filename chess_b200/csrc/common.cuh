@@ -19,6 +19,11 @@ struct chess_ctx {
   size_t d_results_bytes = 0;
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
+  // workspace of the item kernel: work counters, retry flags, arrival counters, band records
+  void *d_items = nullptr;
+  size_t d_items_bytes = 0;
+  size_t items_done_cap = 0;
+  int items_parity = 0;
 };
 
 #define CHESS_CUDA(ctx, call)                                                          \
@@ -38,7 +43,12 @@ struct chess_ctx {
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                                  const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                  const chess_params &p, double *ssim, double *sn, int32_t *status,
-                                 cudaStream_t stream, bool retry_only = false);
+                                 cudaStream_t stream, bool retry_only = false,
+                                 const int *retry_flag = nullptr);
+int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                               const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                               const chess_params &p, double *ssim, double *sn, int32_t *status,
+                               cudaStream_t stream, bool *handled);
 int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                               const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                               const chess_params &p, double *ssim, double *sn, int32_t *status,

@@ -133,10 +133,13 @@ __device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, in
 }
 
 // Loop A of pass 2: moments of x and y and min / max over the rows [lo, hi) of the band.
-template <int G>
+// COLSUM additionally accumulates the lane's column sums over those rows (the item kernel uses
+// them to verify its predicted masks).
+template <int G, bool COLSUM>
 __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                              size_t rp, size_t qp, const short *kmap, int n, int flip,
-                                             int lo, int hi, const LaneCols<G> &lc, Band2 &acc) {
+                                             int lo, int hi, const LaneCols<G> &lc, Band2 &acc,
+                                             double *cs_r, double *cs_q) {
   double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
   double vmax = -CUDART_INF, vmin = CUDART_INF;
 #pragma unroll 4
@@ -154,6 +157,7 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
     for (int g = 0; g < G; ++g) {
       T0 += x[g]; T1 += y[g];
       T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
+      if (COLSUM) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
       // branch-free compare-selects (the data are finite: no NaN handling needed)
       const bool xgt = x[g] > y[g];
       const double hi2 = xgt ? x[g] : y[g];
@@ -485,7 +489,7 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     if (lo < hi) {
       LaneCols<G> lc;
       lane_cols<G>(lc, kmap, n, np_, flip, lane);
-      moments_rows<G>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc);
+      moments_rows<G, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, nullptr, nullptr);
       if (WITH_SN) sn_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp[warp],
                               &susp_n[warp], acc);
       if (WITH_SN) {
@@ -607,6 +611,383 @@ int launch_r1(chess_ctx *ctx, const double *ref_base, const double *qry_base, co
   return launch_r1_sn<G, NW, false>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
 }
 
+// =====================================================================================
+// compare_r1_items_kernel -- the same computation as compare_r1_kernel, reorganised so that
+// nothing waits on anything:
+//   * a work item is (pair, row band); warps take items from a global counter, so a launch of
+//     P pairs is 4P independent pieces and the tail of the grid costs a quarter pair, not a pair;
+//   * the masks are *predicted* in O(1) per column from a per-bin index built once per sample
+//     (nearest bin with a non-default entry on either side, chess_band_index_build): a column is
+//     all-default -- hence masked, chess/sim.py:82-85 -- iff that neighbour lies outside the
+//     window.  This removes the separate column-sum pass and every CTA barrier;
+//   * each band writes its partial results (moments, min / max, SN sum / count, first / last row
+//     totals, its share of every column sum) to a scratch record; the band that arrives last
+//     (atomic counter, no spinning) checks the prediction against the column sums -- a column
+//     that is not all-default is masked only if its sum hits n*default exactly; such a
+//     coincidence is confirmed with the reference's own sequential sum and sends the pair to the
+//     generic kernel -- and otherwise combines the bands in fixed order and writes the result.
+constexpr int kBands = 4;
+constexpr int kItemHdr = 24;
+
+struct ItemArgs {
+  const double *ref_band, *qry_band;
+  const int *ref_lo, *ref_hi, *qry_lo, *qry_hi;
+  const chess_pair *pairs;
+  long long n_pairs;
+  chess_params p;
+  double *ssim, *sn;
+  int *status;
+  double *scratch;            // n_pairs * kBands * (kItemHdr + 2*NCOL)
+  int *done;                  // n_pairs, zero on entry, zero on exit
+  unsigned long long *counter_cur, *counter_next;
+  int *retry_cur, *retry_next;
+};
+
+__device__ __forceinline__ void finish_pair(const double *t, double mx, double mn, double ss, double sc,
+                                            const double *row0, const double *rowL, int np_, int win,
+                                            int m, const short *kmap, const double *R, const double *Q,
+                                            size_t rp, size_t qp, int n, int flip, bool with_sn,
+                                            double *ssim_out, double *sn_out, int *status_out) {
+  const double drange = mx - mn;
+  const double NP = (double)win * (double)win;
+  const double cov_norm = NP / (NP - 1.0);
+  const double C1 = (0.01 * drange) * (0.01 * drange);
+  const double C2 = (0.03 * drange) * (0.03 * drange);
+  double acc = 0.0;
+  for (int a = 0; a < m; ++a) {
+    for (int b = 0; b < m; ++b) {
+      double h[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) h[k] = t[k];
+      if (m == 2) {
+        // window (a, b) leaves out one border row and one border column; column totals = row
+        // totals because every moment map of a symmetric pair is symmetric
+        const bool ra = a == 0, rb = b == 0;  // true: the last row / column is left out
+        const int er = ra ? np_ - 1 : 0, ec = rb ? np_ - 1 : 0;
+        const int kr = kmap[er], kcc = kmap[ec];
+        const double x = __ldg(R + (size_t)kr * rp + kcc);
+        const double y = flip ? __ldg(Q + (size_t)(n - 1 - kr) * qp + (n - 1 - kcc))
+                              : __ldg(Q + (size_t)kr * qp + kcc);
+        const double corner[5] = {x, y, x * x, y * y, x * y};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          h[k] = h[k] - (ra ? rowL[k] : row0[k]) - (rb ? rowL[k] : row0[k]) + corner[k];
+      }
+      const double ux = h[0] / NP, uy = h[1] / NP;
+      const double uxx = h[2] / NP, uyy = h[3] / NP, uxy = h[4] / NP;
+      const double vx = cov_norm * (uxx - ux * ux);
+      const double vy = cov_norm * (uyy - uy * uy);
+      const double vxy = cov_norm * (uxy - ux * uy);
+      const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2;
+      const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+      acc += (A1 * A2) / (B1 * B2);
+    }
+  }
+  *ssim_out = acc / (double)(m * m);
+  *sn_out = with_sn ? ss / sc : CUDART_NAN;
+  *status_out = CHESS_PAIR_OK;
+}
+
+template <int G, bool WITH_SN>
+__global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2))
+compare_r1_items_kernel(ItemArgs a) {
+  constexpr int NCOL = 32 * G;
+  constexpr int STRIDE = kItemHdr + 2 * NCOL;
+  __shared__ short s_kmap[4][NCOL];
+  __shared__ unsigned char s_mflag[4][NCOL];
+  __shared__ int s_susp[4][kSuspCap];
+  __shared__ int s_susp_n[4];
+  extern __shared__ __align__(16) double ringbuf[];  // 4 * 7 * G * 32 doubles (SN only)
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  short *kmap = s_kmap[warp];
+  unsigned char *mflag = s_mflag[warp];
+  int *susp = s_susp[warp];
+  int *susp_n = &s_susp_n[warp];
+  double *myring = ringbuf + (size_t)warp * 7 * G * 32 + lane;
+  const chess_params &p = a.p;
+  const double qnan = CUDART_NAN;
+  const bool use_masks = p.mappability_cutoff > 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
+  const long long n_items = a.n_pairs * kBands;
+
+  while (true) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(a.counter_cur, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const long long pi = item / kBands;
+    const int band = (int)(item - pi * kBands);
+    const chess_pair d = a.pairs[pi];
+    int status = CHESS_PAIR_OK;
+    if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
+    else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
+    else if (d.ref_n != d.qry_n || d.ref_n > 31 * G) status = CHESS_PAIR_RETRY;
+    if (status != CHESS_PAIR_OK) {
+      if (band == 0 && lane == 0) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = status;
+        if (status == CHESS_PAIR_RETRY) atomicOr(a.retry_cur, 1);
+      }
+      continue;
+    }
+    const int n = d.ref_n, flip = d.flip;
+    const double *R = a.ref_band + d.ref_off;
+    const double *Q = a.qry_band + d.qry_off;
+    const size_t rp = (size_t)d.ref_pitch, qp = (size_t)d.qry_pitch;
+    // first bins of the two windows, recovered from the band view (off = i0*(2W-1) + W-1, pitch = 2W-2)
+    const long long Wr = d.ref_pitch / 2 + 1, Wq = d.qry_pitch / 2 + 1;
+    const int i0r = (int)((d.ref_off - (Wr - 1)) / (2 * Wr - 1));
+    const int i0q = (int)((d.qry_off - (Wq - 1)) / (2 * Wq - 1));
+
+    // ---- predicted masks -> cutoff test -> compaction map (every band of a pair repeats this; O(n))
+    int np_ = n, tot_r = 0, tot_q = 0;
+    if (use_masks) {
+      for (int base = 0; base < n; base += 32) {
+        const int c = base + lane;
+        bool fr = false, fq = false;
+        if (c < n) {
+          const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
+          fr = __ldg(a.ref_lo + jr) < i0r && __ldg(a.ref_hi + jr) >= i0r + n;
+          fq = __ldg(a.qry_lo + jq) < i0q && __ldg(a.qry_hi + jq) >= i0q + n;
+          mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+        }
+        tot_r += __popc(__ballot_sync(0xffffffffu, fr));
+        tot_q += __popc(__ballot_sync(0xffffffffu, fq));
+      }
+      if ((double)tot_r / (double)n > p.mappability_cutoff || (double)tot_q / (double)n > p.mappability_cutoff) {
+        if (band == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_UNMAPPABLE; }
+        continue;  // NB: a coincidentally masked column could only add to the count; see verify below
+      }
+    }
+    __syncwarp();
+    if (use_masks && !p.keep_unmappable && (tot_r + tot_q) > 0) {
+      int carry = 0;
+      for (int base = 0; base < n; base += 32) {
+        const int c = base + lane;
+        const bool keep = c < n && mflag[c] == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) kmap[carry + __popc(bal & ((1u << lane) - 1u))] = (short)c;
+        carry += __popc(bal);
+      }
+      np_ = carry;
+    } else {
+      for (int c = lane; c < n; c += 32) kmap[c] = (short)c;
+    }
+    if (lane == 0) *susp_n = 0;
+    __syncwarp();
+
+    int win = (np_ & 1) ? np_ : np_ - 1;
+    if (win < 3) win = 3;
+    if (win > np_) {
+      if (band == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      continue;
+    }
+    const int m = np_ - win + 1;
+
+    // ---- this band
+    const int B2 = (np_ + kBands - 1) / kBands;
+    const int lo = band * B2, hi = min(np_, lo + B2);
+    LaneCols<G> lc;
+    lane_cols<G>(lc, kmap, n, np_, flip, lane);
+    Band2 acc;
+    acc.T0 = acc.T1 = acc.T2 = acc.T3 = acc.T4 = 0.0;
+    acc.vmax = -CUDART_INF; acc.vmin = CUDART_INF; acc.sn_sum = 0.0; acc.sn_cnt = 0;
+    double cs_r[G], cs_q[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; }
+    double rt[5] = {0, 0, 0, 0, 0};
+    if (m == 2 && (band == 0 || band == kBands - 1)) {  // first / last row totals for the 2x2 SSIM map
+      const int kr = kmap[band == 0 ? 0 : np_ - 1];
+      const double *rowR = R + (size_t)kr * rp;
+      const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (lc.valid[g]) {
+          const double x = __ldg(rowR + lc.xo[g]), y = __ldg(rowQ + lc.yo[g]);
+          rt[0] += x; rt[1] += y; rt[2] = fma(x, x, rt[2]); rt[3] = fma(y, y, rt[3]); rt[4] = fma(x, y, rt[4]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) rt[k] = warp_sum(rt[k]);
+    }
+    if (use_masks && band == 0 && np_ < n) {
+      // the column sums must cover all n rows of the uncompacted matrices: band 0 adds the few
+      // removed rows (a row removed because of the *other* matrix is not all-default in this one)
+      for (int r = 0; r < n; ++r) {
+        if (mflag[r] != 0) {
+          const double *rowR = R + (size_t)r * rp;
+          const double *rowQ = Q + (size_t)(flip ? n - 1 - r : r) * qp;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (lc.valid[g]) { cs_r[g] += __ldg(rowR + lc.xo[g]); cs_q[g] += __ldg(rowQ + lc.yo[g]); }
+          }
+        }
+      }
+    }
+    if (lo < hi) {
+      moments_rows<G, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, cs_r, cs_q);
+      if (WITH_SN) {
+        sn_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, acc);
+        __syncwarp();
+        const int ns = *susp_n;
+        if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
+          for (int e = lane; e < ns; e += 32) {
+            const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
+            const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                        (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+            const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+            if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
+          }
+        } else if (ns > kSuspCap) {  // list overflow: redo the whole band exactly
+          acc.sn_sum = 0.0; acc.sn_cnt = 0;
+          for (int rc = lo; rc < hi; ++rc) {
+            for (int c = lane; c < np_; c += 32) {
+              const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                          (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+              const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+              if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
+            }
+          }
+        }
+      }
+    }
+    // ---- partial record of this band
+    double *rec = a.scratch + ((size_t)pi * kBands + band) * STRIDE;
+    {
+      const double T0 = warp_sum(acc.T0), T1 = warp_sum(acc.T1), T2 = warp_sum(acc.T2);
+      const double T3 = warp_sum(acc.T3), T4 = warp_sum(acc.T4);
+      const double vmax = warp_max(acc.vmax), vmin = warp_min(acc.vmin);
+      const double ss = warp_sum(acc.sn_sum);
+      const int sc = warp_sum_int(acc.sn_cnt);
+      if (lane == 0) {
+        rec[0] = T0; rec[1] = T1; rec[2] = T2; rec[3] = T3; rec[4] = T4;
+        rec[5] = vmax; rec[6] = vmin; rec[7] = ss; rec[8] = (double)sc;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rec[9 + k] = rt[k];
+      }
+      if (use_masks) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          rec[kItemHdr + G * lane + g] = cs_r[g];
+          rec[kItemHdr + NCOL + G * lane + g] = cs_q[g];
+        }
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(a.done + pi, 1);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != kBands - 1) continue;
+
+    // ---- last band to arrive: verify the prediction, combine in band order, write the result
+    __threadfence();
+    const double *recs = a.scratch + (size_t)pi * kBands * STRIDE;
+    bool bad = false;
+    if (use_masks) {
+      const double target = (double)n * p.default_value;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = G * lane + g;
+        if (c < np_) {
+          double sr = 0.0, sq = 0.0;
+#pragma unroll
+          for (int b = 0; b < kBands; ++b) {
+            sr += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + c);
+            sq += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + NCOL + c);
+          }
+          const int kc = kmap[c];
+          if (!(mflag[kc] & 1) && fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
+            double s2 = 0.0;  // the reference's own order: rows 0 .. n-1 of the uncompacted matrix
+            for (int r = 0; r < n; ++r) s2 += __ldg(R + (size_t)r * rp + kc);
+            bad |= s2 == target;
+          }
+          if (!(mflag[kc] & 2) && fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
+            double s2 = 0.0;
+            const int cq = flip ? n - 1 - kc : kc;
+            for (int r = 0; r < n; ++r) s2 += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
+            bad |= s2 == target;
+          }
+        }
+      }
+      bad = __any_sync(0xffffffffu, bad);
+    }
+    if (lane == 0) {
+      if (bad) {  // a coincidentally masked column: the generic kernel redoes this pair exactly
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+        atomicOr(a.retry_cur, 1);
+      } else {
+        double t[5] = {0, 0, 0, 0, 0}, mx = -CUDART_INF, mn = CUDART_INF, ss = 0.0, sc = 0.0;
+        for (int b = 0; b < kBands; ++b) {
+          const double *rb = recs + (size_t)b * STRIDE;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) t[k] += __ldcg(rb + k);
+          mx = fmax(mx, __ldcg(rb + 5)); mn = fmin(mn, __ldcg(rb + 6));
+          ss += __ldcg(rb + 7); sc += __ldcg(rb + 8);
+        }
+        double row0[5], rowL[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          row0[k] = __ldcg(recs + 9 + k);
+          rowL[k] = __ldcg(recs + (size_t)(kBands - 1) * STRIDE + 9 + k);
+        }
+        finish_pair(t, mx, mn, ss, sc, row0, rowL, np_, win, m, kmap, R, Q, rp, qp, n, flip, WITH_SN,
+                    a.ssim + pi, a.sn + pi, a.status + pi);
+      }
+      a.done[pi] = 0;  // leave the arrival counters clean for the next launch
+    }
+  }
+}
+
+__global__ void band_index_kernel(const double *__restrict__ band, long long n_bins, int W, double dv,
+                                  int *__restrict__ nd_lo, int *__restrict__ nd_hi) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_bins) return;
+  const double *row = band + i * (2ll * W - 1) + (W - 1);  // row[k - i] = band(i, k)
+  int lo = -1, hi = 0x7fffffff;
+  for (int dist = 0; dist < W; ++dist) {
+    if (i - dist < 0) break;
+    if (row[-dist] != dv) { lo = (int)(i - dist); break; }
+  }
+  for (int dist = 0; dist < W; ++dist) {
+    if (i + dist >= n_bins) break;
+    if (row[dist] != dv) { hi = (int)(i + dist); break; }
+  }
+  nd_lo[i] = lo;
+  nd_hi[i] = hi;
+}
+
+template <int G, bool WITH_SN>
+int launch_items_sn(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
+  auto kern = compare_r1_items_kernel<G, WITH_SN>;
+  const size_t smem = WITH_SN ? (size_t)4 * 7 * G * 32 * sizeof(double) : 0;
+  static bool configured = false;
+  if (!configured && smem > 0) {
+    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)ctx->sm_count * per_sm;
+  const long long need = (a.n_pairs * kBands + 3) / 4;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+template <int G>
+int launch_items(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
+  if (a.p.compute_sn) return launch_items_sn<G, true>(ctx, a, stream);
+  return launch_items_sn<G, false>(ctx, a, stream);
+}
+
+size_t items_stride(int G) { return (size_t)kItemHdr + 2 * 32 * (size_t)G; }
+
 }  // namespace
 
 int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const double *qry_base,
@@ -633,4 +1014,94 @@ int chess_launch_compare_fast(chess_ctx *ctx, const double *ref_base, const doub
                                       stream, /*retry_only=*/true);
   }
   return rc;
+}
+
+// ---- band-sample entry points -------------------------------------------------------------------
+extern "C" int chess_band_index_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                                      double default_value, int32_t *nd_lo, int32_t *nd_hi,
+                                      void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (!band || n_bins <= 0 || W <= 0 || !nd_lo || !nd_hi) {
+    ctx->err = "chess_band_index_build: bad arguments";
+    return CHESS_ERR_ARG;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  band_index_kernel<<<(unsigned)((n_bins + 127) / 128), 128, 0, stream>>>(band, (long long)n_bins, W,
+                                                                          default_value, nd_lo, nd_hi);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                               const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                               const chess_params &p, double *ssim, double *sn, int32_t *status,
+                               cudaStream_t stream, bool *handled) {
+  *handled = false;
+  const bool r1 = p.abs_window == 0 && p.rel_window == 1.0;
+  const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
+  if (!r1 || !plain_default || max_n > 248 || !ref->nd_lo || !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
+    return CHESS_OK;
+  const int G = max_n <= 93 ? 3 : max_n <= 124 ? 4 : max_n <= 155 ? 5 : max_n <= 186 ? 6 : max_n <= 217 ? 7 : 8;
+  const size_t stride = items_stride(G);
+  const int64_t chunk = 16384;
+  const int64_t cap = n_pairs < chunk ? n_pairs : chunk;
+  // workspace: [2 counters][2 retry flags + pad][done: chunk ints][scratch: cap * kBands * stride doubles];
+  // the arrival counters sit at a fixed offset and size so that scratch records can never overlap them
+  const size_t head = 64;
+  const size_t done_bytes = (size_t)chunk * sizeof(int);
+  const size_t need = head + done_bytes + (size_t)cap * kBands * stride * sizeof(double);
+  if (ctx->d_items_bytes < need) {
+    if (ctx->d_items) cudaFree(ctx->d_items);
+    ctx->d_items = nullptr;
+    ctx->d_items_bytes = 0;
+    const size_t want = need + need / 4;
+    if (cudaMalloc(&ctx->d_items, want) != cudaSuccess) {
+      ctx->err = "allocation of the item workspace failed";
+      return CHESS_ERR_NOMEM;
+    }
+    ctx->d_items_bytes = want;
+    ctx->items_done_cap = 0;
+  }
+  char *base = reinterpret_cast<char *>(ctx->d_items);
+  if (ctx->items_done_cap == 0) {  // fresh allocation: counters, flags and arrival counters start at zero
+    CHESS_CUDA(ctx, cudaMemsetAsync(base, 0, head + done_bytes, stream));
+    ctx->items_parity = 0;
+    ctx->items_done_cap = (size_t)chunk;
+  }
+  unsigned long long *counters = reinterpret_cast<unsigned long long *>(base);
+  int *flags = reinterpret_cast<int *>(base + 16);
+  ItemArgs a;
+  a.ref_band = ref->band; a.qry_band = qry->band;
+  a.ref_lo = ref->nd_lo; a.ref_hi = ref->nd_hi; a.qry_lo = qry->nd_lo; a.qry_hi = qry->nd_hi;
+  a.p = p;
+  a.done = reinterpret_cast<int *>(base + head);
+  a.scratch = reinterpret_cast<double *>(base + head + done_bytes);
+  for (int64_t off = 0; off < n_pairs; off += chunk) {
+    const int64_t cnt = n_pairs - off < chunk ? n_pairs - off : chunk;
+    const int par = ctx->items_parity;
+    a.pairs = pairs + off; a.n_pairs = cnt;
+    a.ssim = ssim + off; a.sn = sn + off; a.status = status + off;
+    a.counter_cur = counters + par; a.counter_next = counters + (par ^ 1);
+    a.retry_cur = flags + par; a.retry_next = flags + (par ^ 1);
+    int rc;
+    switch (G) {
+      case 3: rc = launch_items<3>(ctx, a, stream); break;
+      case 4: rc = launch_items<4>(ctx, a, stream); break;
+      case 5: rc = launch_items<5>(ctx, a, stream); break;
+      case 6: rc = launch_items<6>(ctx, a, stream); break;
+      case 7: rc = launch_items<7>(ctx, a, stream); break;
+      default: rc = launch_items<8>(ctx, a, stream); break;
+    }
+    if (rc) return rc;
+    ctx->items_parity ^= 1;
+    // pairs the item kernel could not finish (unequal sizes, coincidentally masked column): the
+    // generic kernel picks them up; it returns at once when the flag is clear
+    rc = chess_launch_compare_generic(ctx, ref->band, qry->band, pairs + off, cnt, max_n, p, ssim + off,
+                                      sn + off, status + off, stream, /*retry_only=*/true, flags + par);
+    if (rc) return rc;
+  }
+  *handled = true;
+  return CHESS_OK;
 }

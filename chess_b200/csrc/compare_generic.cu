@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(BLOCK)
 compare_generic_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
                        const chess_pair *__restrict__ pairs, long long n_pairs, int ncap,
                        chess_params p, double *__restrict__ ssim_out, double *__restrict__ sn_out,
-                       int *__restrict__ status_out, int retry_only) {
+                       int *__restrict__ status_out, int retry_only, const int *retry_flag) {
+  if (retry_flag != nullptr && *retry_flag == 0) return;  // nothing was left for the generic kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *red = reinterpret_cast<double *>(smem_raw);
   double *buf = red + kRed;                       // max(5*ncap, 9*ncap+12) doubles
@@ -436,7 +437,7 @@ size_t generic_smem_bytes(int ncap) {
 template <int BLOCK, int CPT>
 int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
            int64_t n_pairs, int ncap, const chess_params &p, double *ssim, double *sn,
-           int32_t *status, cudaStream_t stream, bool retry_only) {
+           int32_t *status, cudaStream_t stream, bool retry_only, const int *retry_flag) {
   auto kern = compare_generic_kernel<BLOCK, CPT>;
   const size_t smem = generic_smem_bytes(ncap);
   if ((int)smem > ctx->max_smem_optin) {
@@ -450,7 +451,7 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > n_pairs) grid = n_pairs;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(ref_base, qry_base, pairs, (long long)n_pairs, ncap, p,
-                                                ssim, sn, status, retry_only ? 1 : 0);
+                                                ssim, sn, status, retry_only ? 1 : 0, retry_flag);
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
@@ -461,15 +462,15 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                                  const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                  const chess_params &p, double *ssim, double *sn, int32_t *status,
-                                 cudaStream_t stream, bool retry_only) {
+                                 cudaStream_t stream, bool retry_only, const int *retry_flag) {
   if (n_pairs <= 0) return CHESS_OK;
   if (max_n > 1024) {
     ctx->err = "compare: submatrices larger than 1024 bins are not supported";
     return CHESS_ERR_UNSUPPORTED;
   }
   const int ncap = max_n < 32 ? 32 : max_n;
-  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
-  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
-  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
-  return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only);
+  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
 }

@@ -76,6 +76,7 @@ class DeviceContacts(object):
             raise ValueError("contact indices exceed the number of regions")
         self.fill = float(fill)
         self._bands = {}   # device -> (W, fill, tensor)
+        self._index = {}   # device -> (nd_lo, nd_hi) tensors for the current band
         self._coo = {}     # device -> (src32, sink32, value) tensors
         self._csr = None
 
@@ -139,10 +140,32 @@ class DeviceContacts(object):
                                        self.n_bins, W, fill, _ptr(band), _stream_ptr(dev)),
                   ctx.handle, "chess_band_build")
         self._bands[device] = (W, fill, band)
+        self._index.pop(device, None)
         return W, band
+
+    def sample_on(self, device, min_w, fill=None):
+        """(W, band tensor, chess_sample) on ``device``: the band plus the per-bin index of the
+        nearest non-default entries (built once per band, lets the kernels predict masked bins)."""
+        device = int(device)
+        W, band = self.band_on(device, min_w, fill)
+        fill_v = self._bands[device][1]
+        have = self._index.get(device)
+        if have is None:
+            ctx = get_context(device)
+            dev = torch.device("cuda", device)
+            nd_lo = torch.empty(self.n_bins, dtype=torch.int32, device=dev)
+            nd_hi = torch.empty(self.n_bins, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.chess_band_index_build(ctx.handle, _ptr(band), self.n_bins, W, fill_v, _ptr(nd_lo),
+                                                 _ptr(nd_hi), _stream_ptr(dev)), ctx.handle, "chess_band_index_build")
+            have = (nd_lo, nd_hi)
+            self._index[device] = have
+        sample = _native.chess_sample(band.data_ptr(), have[0].data_ptr(), have[1].data_ptr(), self.n_bins, W, 0)
+        return W, band, sample
 
     def drop_device_copies(self):
         self._bands.clear()
+        self._index.clear()
         self._coo.clear()
 
     def submatrix(self, start_ix, n, default_weight=None, device=None):
@@ -267,8 +290,8 @@ class CompareEngine(object):
             ctx = get_context(device)
             dev = torch.device("cuda", device)
             with torch.cuda.device(dev):
-                rw, rband = self.ref.band_on(device, max_n, default_value)
-                qw, qband = self.qry.band_on(device, max_n, default_value)
+                rw, rband, rsample = self.ref.sample_on(device, max_n, default_value)
+                qw, qband, qsample = self.qry.sample_on(device, max_n, default_value)
                 tab = build_pair_table(ref_first[lo:hi], ref_n[lo:hi], rw, qry_first[lo:hi], qry_n[lo:hi], qw,
                                        flip[lo:hi])
                 h_tab = torch.from_numpy(tab.view(np.uint8)).pin_memory()
@@ -276,9 +299,10 @@ class CompareEngine(object):
                 d_ssim = torch.empty(hi - lo, dtype=torch.float64, device=dev)
                 d_sn = torch.empty(hi - lo, dtype=torch.float64, device=dev)
                 d_status = torch.empty(hi - lo, dtype=torch.int32, device=dev)
-                check(lib.chess_compare_batch(ctx.handle, _ptr(rband), _ptr(qband), _ptr(d_tab), hi - lo, max_n,
-                                              C.byref(p), _ptr(d_ssim), _ptr(d_sn), _ptr(d_status),
-                                              _stream_ptr(dev)), ctx.handle, "chess_compare_batch")
+                check(lib.chess_compare_band_batch(ctx.handle, C.byref(rsample), C.byref(qsample), _ptr(d_tab),
+                                                   hi - lo, max_n, C.byref(p), _ptr(d_ssim), _ptr(d_sn),
+                                                   _ptr(d_status), _stream_ptr(dev)),
+                      ctx.handle, "chess_compare_band_batch")
                 h_ssim = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
                 h_sn = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
                 h_status = torch.empty(hi - lo, dtype=torch.int32).pin_memory()

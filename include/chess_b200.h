@@ -84,7 +84,8 @@ typedef struct chess_params {
   double rel_window;         /* -r                                             */
   double mappability_cutoff; /* --mappability-cutoff                           */
   double default_value;      /* fill / masking value, 1 from the CLI           */
-  int32_t kernel;            /* 0 = auto, 1 = force the generic kernel         */
+  int32_t kernel;            /* 0 = auto, 1 = force the generic kernel,
+                                2 = skip the work-item kernel (A/B testing)    */
   int32_t flags;             /* CHESS_FLAG_* promises about the batch          */
 } chess_params;
 
@@ -168,6 +169,34 @@ int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base, const doubl
                              const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
                              const chess_params *params, double *ssim_host, double *sn_host,
                              int32_t *status_host, void *stream);
+
+/* ---- band-resident samples: the fastest form of the compare call ------- *
+ * A sample = its band plus a per-bin index built once by chess_band_index_build:
+ * nd_lo[i] / nd_hi[i] = nearest bin k <= i / k >= i (within the band) whose entry
+ * band(i,k) differs from the default value (-1 / INT32_MAX if none).  With it a
+ * column of a submatrix is known to be all-default -- i.e. an unmappable bin,
+ * chess/sim.py:74-87 -- without summing it, so the tuned kernels need no separate
+ * column-sum pass; the prediction is verified against the column sums the kernel
+ * accumulates anyway, and the rare mismatch is redone by the generic kernel.
+ * Pairs must be band views (off = first_bin*(2W-1)+W-1, pitch = 2W-2).          */
+typedef struct chess_sample {
+  const double *band;    /* DEVICE, n_bins*(2W-1) doubles (chess_band_build)   */
+  const int32_t *nd_lo;  /* DEVICE, n_bins, may be NULL (then no prediction)    */
+  const int32_t *nd_hi;  /* DEVICE, n_bins, may be NULL                         */
+  int64_t n_bins;
+  int32_t W;
+  int32_t reserved;
+} chess_sample;
+int chess_band_index_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                           double default_value, int32_t *nd_lo, int32_t *nd_hi, void *stream);
+int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                             const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
+                             const chess_params *params, double *ssim, double *sn, int32_t *status,
+                             void *stream);
+int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                                  const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
+                                  const chess_params *params, double *ssim_host, double *sn_host,
+                                  int32_t *status_host, void *stream);
 
 /* K6: run-level z-score, bin/chess:216-233: z = (ssim - nanmean) / nanstd
  * (ddof 0) over the non-NaN entries; entries that are not finite keep NaN.

@@ -357,17 +357,65 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
                for pid, r, q in pairs[::5]]
     for kw in (dict(), dict(keep_unmappable_bins=True), dict(mappability_cutoff=0.3), dict(compute_sn=False)):
         for plist in (pairs, flipped):
-            fast = eng.compare(plist, **kw)
             gen = eng.compare(plist, kernel=1, **kw)
-            assert np.array_equal(fast[3], gen[3])
-            np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
-            np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+            for kernel in (0, 2):   # 0: work-item kernel, 2: CTA-per-pair tuned kernel
+                fast = eng.compare(plist, kernel=kernel, **kw)
+                assert np.array_equal(fast[3], gen[3])
+                np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+                np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
     # windows of 40..200 bins exercise every column-strip width of the tuned kernel
     from chess_b200 import synth
     for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000):
         plist = synth.sliding_pairs(genome, window_bp, 900000)
-        fast = eng.compare(plist)
         gen = eng.compare(plist, kernel=1)
-        assert np.array_equal(fast[3], gen[3])
-        np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
-        np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+        for kernel in (0, 2):
+            fast = eng.compare(plist, kernel=kernel)
+            assert np.array_equal(fast[3], gen[3])
+            np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+            np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+
+
+def test_band_kernels_coincidentally_masked_bins(cb):
+    """A bin whose entries are not all default but sum to exactly n is masked by the reference
+    (np.sum(m, 0) == n, chess/sim.py:82-85).  The work-item kernel predicts masks from
+    'all entries default', must notice the coincidence and hand the pair to the generic kernel."""
+    from chess_b200 import synth
+    from chess_b200.engine import DeviceContacts
+    genome = synth.Genome([("c", 400)], 10000)
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    rng = np.random.default_rng(12)
+    src, sink, val = [], [], []
+    special = {100: (0.5, 1.5), 207: (0.25, 1.75), 300: (0.0, 2.0)}
+    for i in range(400):
+        if i in special or i - 1 in special:
+            continue   # bins next to a special bin carry no other entries, so the special column stays 'coincident'
+        for j in range(i, min(400, i + 60)):
+            if rng.random() < 0.8:
+                src.append(i); sink.append(j); val.append(float(rng.lognormal(0, 0.4)))
+    for i, (a, b) in special.items():
+        src += [i, i]; sink += [i, i + 1]; val += [a, b]       # 0.5 + 1.5 + (n-2)*1.0 == n exactly
+    def contacts(seed):
+        v = np.array(val) * np.where(np.isin(np.array(src), list(special)), 1.0,
+                                     np.random.default_rng(seed).lognormal(0, 0.1, len(val)))
+        return DeviceContacts(np.array(src), np.array(sink), v, n_bins=400)
+    re_, qe = contacts(1), contacts(2)
+    pairs = synth.sliding_pairs(genome, 500000, 30000)     # 51-bin windows
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    oregions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in regions]
+    otrees = O.region_trees(oregions)
+    ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
+    oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
+    hits = 0
+    for kernel in (0, 2, 1):
+        ids, s, sn, st = eng.compare(pairs, kernel=kernel, mappability_cutoff=0.2)
+        for k, (pid, rr, qr) in enumerate(pairs):
+            op = (pid, O.Region(rr.start, rr.end, rr.chromosome, strand=rr.strand),
+                  O.Region(qr.start, qr.end, qr.chromosome, strand=qr.strand))
+            m, _ = O.sub_matrix_from_edges_dict(ore, otrees, op[1], 1)
+            masked = O.find_masked_rows(m, 1)
+            hits += int(any(int(masked_ix) + (rr.start - 1) // 10000 in special for masked_ix in masked))
+            _, os_, osn = O.compare_pair(op, ore, otrees, oqe, otrees, mappability_cutoff=0.2)
+            assert close(s[k], os_, RTOL), (kernel, pid, s[k], os_)
+            assert close(sn[k], osn, RTOL), (kernel, pid, sn[k], osn)
+    assert hits > 0   # the construction does produce coincidentally masked bins
