@@ -115,7 +115,7 @@ struct Band2 {
 // Per-lane view of the compacted pair: column offsets of the lane's G columns in both matrices.
 template <int G>
 struct LaneCols {
-  int xo[G], yo[G];   // element offsets inside a row of the reference / query view
+  unsigned xo[G], yo[G];   // element offsets inside a row of the reference / query view
   bool valid[G];
 };
 
@@ -127,8 +127,8 @@ __device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, in
     const int c = G * lane + g;
     lc.valid[g] = c < np_;
     const int kc = lc.valid[g] ? (int)kmap[c] : 0;
-    lc.xo[g] = kc;
-    lc.yo[g] = flip ? n - 1 - kc : kc;
+    lc.xo[g] = (unsigned)kc;
+    lc.yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
   }
 }
 
@@ -144,14 +144,15 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
   double vmax = -CUDART_INF, vmin = CUDART_INF;
 #pragma unroll 4
   for (int rr = lo; rr < hi; ++rr) {
-    const int kr = kmap[rr];
-    const double *rowR = R + (size_t)kr * rp;
-    const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+    // all offsets inside one pair fit 32 bits: one IMAD per row, one add + one wide MAD per load
+    const unsigned kr = (unsigned)kmap[rr];
+    const unsigned ro = kr * (unsigned)rp;
+    const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
     double x[G], y[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       x[g] = 0.0; y[g] = 0.0;
-      if (lc.valid[g]) { x[g] = __ldg(rowR + lc.xo[g]); y[g] = __ldg(rowQ + lc.yo[g]); }
+      if (lc.valid[g]) { x[g] = __ldg(R + (ro + lc.xo[g])); y[g] = __ldg(Q + (qo + lc.yo[g])); }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -204,12 +205,12 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
 #pragma unroll
     for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
     if (row >= 0 && row < np_) {
-      const int kr = kmap[row];
-      const double *rowR = R + (size_t)kr * rp;
-      const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+      const unsigned kr = (unsigned)kmap[row];
+      const unsigned ro = kr * (unsigned)rp;
+      const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        if (lc.valid[g]) { xn[g] = __ldg(rowR + lc.xo[g]); yn[g] = __ldg(rowQ + lc.yo[g]); }
+        if (lc.valid[g]) { xn[g] = __ldg(R + (ro + lc.xo[g])); yn[g] = __ldg(Q + (qo + lc.yo[g])); }
       }
     }
   };
@@ -626,7 +627,7 @@ int launch_r1(chess_ctx *ctx, const double *ref_base, const double *qry_base, co
 //     that is not all-default is masked only if its sum hits n*default exactly; such a
 //     coincidence is confirmed with the reference's own sequential sum and sends the pair to the
 //     generic kernel -- and otherwise combines the bands in fixed order and writes the result.
-constexpr int kBands = 4;
+constexpr int kBands = 2;
 constexpr int kItemHdr = 24;
 
 struct ItemArgs {
@@ -1041,7 +1042,9 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   *handled = false;
   const bool r1 = p.abs_window == 0 && p.rel_window == 1.0;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
-  if (!r1 || !plain_default || max_n > 248 || !ref->nd_lo || !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
+  // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
+  if (!r1 || !plain_default || max_n > 248 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
+      !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
     return CHESS_OK;
   const int G = max_n <= 93 ? 3 : max_n <= 124 ? 4 : max_n <= 155 ? 5 : max_n <= 186 ? 6 : max_n <= 217 ? 7 : 8;
   const size_t stride = items_stride(G);

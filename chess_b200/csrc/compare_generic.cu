@@ -450,6 +450,9 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > n_pairs) grid = n_pairs;
+  // the retry pass after a tuned kernel normally has nothing to do (it returns on the flag) and at
+  // most a handful of pairs otherwise: a few CTAs keep its launch cost down
+  if (retry_flag != nullptr && grid > 16) grid = 16;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(ref_base, qry_base, pairs, (long long)n_pairs, ncap, p,
                                                 ssim, sn, status, retry_only ? 1 : 0, retry_flag);
   ctx->launches += 1;
