@@ -43,6 +43,7 @@ class chess_pair(C.Structure):
 
 class chess_sample(C.Structure):
     _fields_ = [("band", C.c_void_p), ("nd_lo", C.c_void_p), ("nd_hi", C.c_void_p),
+                ("pmax", C.c_void_p), ("pmin", C.c_void_p),
                 ("n_bins", C.c_int64), ("W", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -82,6 +83,7 @@ SIGNATURES = {
     "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_band_index_build": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp]),
+    "chess_band_extrema_build": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "chess_compare_band_batch": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),

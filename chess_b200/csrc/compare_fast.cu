@@ -135,7 +135,7 @@ __device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, in
 // Loop A of pass 2: moments of x and y and min / max over the rows [lo, hi) of the band.
 // COLSUM additionally accumulates the lane's column sums over those rows (the item kernel uses
 // them to verify its predicted masks).
-template <int G, bool COLSUM>
+template <int G, bool COLSUM, bool MINMAX>
 __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                              size_t rp, size_t qp, const short *kmap, int n, int flip,
                                              int lo, int hi, const LaneCols<G> &lc, Band2 &acc,
@@ -159,12 +159,14 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
       T0 += x[g]; T1 += y[g];
       T2 = fma(x[g], x[g], T2); T3 = fma(y[g], y[g], T3); T4 = fma(x[g], y[g], T4);
       if (COLSUM) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
-      // branch-free compare-selects (the data are finite: no NaN handling needed)
-      const bool xgt = x[g] > y[g];
-      const double hi2 = xgt ? x[g] : y[g];
-      const double lo2 = xgt ? y[g] : x[g];
-      vmax = (lc.valid[g] & (hi2 > vmax)) ? hi2 : vmax;
-      vmin = (lc.valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+      if (MINMAX) {
+        // branch-free compare-selects (the data are finite: no NaN handling needed)
+        const bool xgt = x[g] > y[g];
+        const double hi2 = xgt ? x[g] : y[g];
+        const double lo2 = xgt ? y[g] : x[g];
+        vmax = (lc.valid[g] & (hi2 > vmax)) ? hi2 : vmax;
+        vmin = (lc.valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+      }
     }
   }
   acc.T0 = T0; acc.T1 = T1; acc.T2 = T2; acc.T3 = T3; acc.T4 = T4;
@@ -173,11 +175,13 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
 
 // Loop B of pass 2: the SN map of the band rows [lo, hi) (three halo rows either side feed the
 // 7-row column sums).
-template <int G>
+// MOMENTS fuses loop A (without min / max) and the column sums into this loop, so the pair is read
+// once: used by the item kernel when the data range comes from the running-extrema arrays.
+template <int G, bool MOMENTS>
 __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                         size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
                                         int lo, int hi, int lane, const LaneCols<G> &lc, double *myring,
-                                        int *susp, int *susp_n, Band2 &acc) {
+                                        int *susp, int *susp_n, Band2 &acc, double *cs_r, double *cs_q) {
   const int c0 = G * lane;
   double ccnt[G];
 #pragma unroll
@@ -187,6 +191,7 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
   }
   double sn_sum = 0.0;
   int sn_cnt = 0;
+  double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
   double Sd[G], Se[G];
   unsigned hist[G];
 #pragma unroll
@@ -220,6 +225,14 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
     bool nzv[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { dv[g] = xn[g] - yn[g]; nzv[g] = xn[g] != yn[g]; }
+    if (MOMENTS && rr >= lo && rr < hi) {  // the band's own rows (halo rows belong to the neighbours)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        T0 += xn[g]; T1 += yn[g];
+        T2 = fma(xn[g], xn[g], T2); T3 = fma(yn[g], yn[g], T3); T4 = fma(xn[g], yn[g], T4);
+        cs_r[g] += xn[g]; cs_q[g] += yn[g];
+      }
+    }
     if (rr + 1 < last) fetch(rr + 1);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -280,6 +293,7 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
   }
   acc.sn_sum = sn_sum;
   acc.sn_cnt = sn_cnt;
+  if (MOMENTS) { acc.T0 = T0; acc.T1 = T1; acc.T2 = T2; acc.T3 = T3; acc.T4 = T4; }
 }
 
 template <int G, int NW, bool WITH_SN>
@@ -490,9 +504,9 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     if (lo < hi) {
       LaneCols<G> lc;
       lane_cols<G>(lc, kmap, n, np_, flip, lane);
-      moments_rows<G, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, nullptr, nullptr);
-      if (WITH_SN) sn_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp[warp],
-                              &susp_n[warp], acc);
+      moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, nullptr, nullptr);
+      if (WITH_SN) sn_rows<G, false>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp[warp],
+                                     &susp_n[warp], acc, nullptr, nullptr);
       if (WITH_SN) {
         // cold: windows whose one-pass variance cancelled -> numpy's own two passes, after the hot loop
         __syncwarp();
@@ -633,6 +647,7 @@ constexpr int kItemHdr = 24;
 struct ItemArgs {
   const double *ref_band, *qry_band;
   const int *ref_lo, *ref_hi, *qry_lo, *qry_hi;
+  const double *ref_pmax, *ref_pmin, *qry_pmax, *qry_pmin;  // running extrema, may be NULL
   const chess_pair *pairs;
   long long n_pairs;
   chess_params p;
@@ -741,7 +756,7 @@ compare_r1_items_kernel(ItemArgs a) {
     const int i0q = (int)((d.qry_off - (Wq - 1)) / (2 * Wq - 1));
 
     // ---- predicted masks -> cutoff test -> compaction map (every band of a pair repeats this; O(n))
-    int np_ = n, tot_r = 0, tot_q = 0;
+    int np_ = n, tot_r = 0, tot_q = 0, tot_one_sided = 0;
     if (use_masks) {
       for (int base = 0; base < n; base += 32) {
         const int c = base + lane;
@@ -754,6 +769,7 @@ compare_r1_items_kernel(ItemArgs a) {
         }
         tot_r += __popc(__ballot_sync(0xffffffffu, fr));
         tot_q += __popc(__ballot_sync(0xffffffffu, fq));
+        tot_one_sided += __popc(__ballot_sync(0xffffffffu, fr != fq));
       }
       if ((double)tot_r / (double)n > p.mappability_cutoff || (double)tot_q / (double)n > p.mappability_cutoff) {
         if (band == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_UNMAPPABLE; }
@@ -825,10 +841,32 @@ compare_r1_items_kernel(ItemArgs a) {
         }
       }
     }
+    // data range: n lookups in the running-extrema arrays give max / min of the uncompacted pair.
+    // They are also the extrema of the compacted pair if every removed cell holds the default value
+    // in both matrices (bins masked in one matrix only are removed from the other, where they carry
+    // data) and the default is neither the max nor the min; otherwise min / max are taken in a loop
+    bool inloop_minmax = true;
+    double xmax = -CUDART_INF, xmin = CUDART_INF;
+    if (a.ref_pmax != nullptr) {
+      for (int r = lane; r < n; r += 32) {
+        const size_t ir = (size_t)(i0r + r) * (size_t)Wr + (size_t)(n - 1 - r);
+        const size_t iq = (size_t)(i0q + r) * (size_t)Wq + (size_t)(n - 1 - r);
+        xmax = fmax(xmax, fmax(__ldg(a.ref_pmax + ir), __ldg(a.qry_pmax + iq)));
+        xmin = fmin(xmin, fmin(__ldg(a.ref_pmin + ir), __ldg(a.qry_pmin + iq)));
+      }
+      xmax = warp_max(xmax);
+      xmin = warp_min(xmin);
+      inloop_minmax = np_ < n && (tot_one_sided > 0 || !(xmax > p.default_value && xmin < p.default_value));
+    }
     if (lo < hi) {
-      moments_rows<G, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, cs_r, cs_q);
       if (WITH_SN) {
-        sn_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, acc);
+        if (inloop_minmax) {
+          Band2 mm;
+          moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, nullptr, nullptr);
+          xmax = mm.vmax; xmin = mm.vmin;
+        }
+        sn_rows<G, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, acc, cs_r,
+                         cs_q);
         __syncwarp();
         const int ns = *susp_n;
         if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
@@ -850,8 +888,18 @@ compare_r1_items_kernel(ItemArgs a) {
             }
           }
         }
+      } else {
+        Band2 mm;
+        if (inloop_minmax) {
+          moments_rows<G, true, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+          xmax = mm.vmax; xmin = mm.vmin;
+        } else {
+          moments_rows<G, true, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+        }
+        acc.T0 = mm.T0; acc.T1 = mm.T1; acc.T2 = mm.T2; acc.T3 = mm.T3; acc.T4 = mm.T4;
       }
     }
+    acc.vmax = xmax; acc.vmin = xmin;
     // ---- partial record of this band
     double *rec = a.scratch + ((size_t)pi * kBands + band) * STRIDE;
     {
@@ -958,6 +1006,21 @@ __global__ void band_index_kernel(const double *__restrict__ band, long long n_b
   nd_hi[i] = hi;
 }
 
+__global__ void band_extrema_kernel(const double *__restrict__ band, long long n_bins, int W,
+                                    double *__restrict__ pmax, double *__restrict__ pmin) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_bins) return;
+  const double *row = band + i * (2ll * W - 1) + (W - 1);  // row[d] = band(i, i+d)
+  double mx = -CUDART_INF, mn = CUDART_INF;
+  for (int d = 0; d < W; ++d) {
+    const double v = row[d];  // cells beyond the last bin hold the fill value; they are never looked up
+    mx = v > mx ? v : mx;
+    mn = v < mn ? v : mn;
+    pmax[i * W + d] = mx;
+    pmin[i * W + d] = mn;
+  }
+}
+
 template <int G, bool WITH_SN>
 int launch_items_sn(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
   auto kern = compare_r1_items_kernel<G, WITH_SN>;
@@ -1035,6 +1098,21 @@ extern "C" int chess_band_index_build(chess_ctx *ctx, const double *band, int64_
   return CHESS_OK;
 }
 
+extern "C" int chess_band_extrema_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                                        double *pmax, double *pmin, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (!band || n_bins <= 0 || W <= 0 || !pmax || !pmin) {
+    ctx->err = "chess_band_extrema_build: bad arguments";
+    return CHESS_ERR_ARG;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  band_extrema_kernel<<<(unsigned)((n_bins + 127) / 128), 128, 0, stream>>>(band, (long long)n_bins, W, pmax, pmin);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
 int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
                                const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                const chess_params &p, double *ssim, double *sn, int32_t *status,
@@ -1078,6 +1156,9 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   ItemArgs a;
   a.ref_band = ref->band; a.qry_band = qry->band;
   a.ref_lo = ref->nd_lo; a.ref_hi = ref->nd_hi; a.qry_lo = qry->nd_lo; a.qry_hi = qry->nd_hi;
+  const bool have_extrema = ref->pmax && ref->pmin && qry->pmax && qry->pmin;
+  a.ref_pmax = have_extrema ? ref->pmax : nullptr; a.ref_pmin = have_extrema ? ref->pmin : nullptr;
+  a.qry_pmax = have_extrema ? qry->pmax : nullptr; a.qry_pmin = have_extrema ? qry->pmin : nullptr;
   a.p = p;
   a.done = reinterpret_cast<int *>(base + head);
   a.scratch = reinterpret_cast<double *>(base + head + done_bytes);

@@ -76,7 +76,7 @@ class DeviceContacts(object):
             raise ValueError("contact indices exceed the number of regions")
         self.fill = float(fill)
         self._bands = {}   # device -> (W, fill, tensor)
-        self._index = {}   # device -> (nd_lo, nd_hi) tensors for the current band
+        self._index = {}   # device -> (nd_lo, nd_hi, pmax, pmin) tensors for the current band
         self._coo = {}     # device -> (src32, sink32, value) tensors
         self._csr = None
 
@@ -158,9 +158,15 @@ class DeviceContacts(object):
             with torch.cuda.device(dev):
                 check(lib.chess_band_index_build(ctx.handle, _ptr(band), self.n_bins, W, fill_v, _ptr(nd_lo),
                                                  _ptr(nd_hi), _stream_ptr(dev)), ctx.handle, "chess_band_index_build")
-            have = (nd_lo, nd_hi)
+            pmax = torch.empty(self.n_bins * W, dtype=torch.float64, device=dev)
+            pmin = torch.empty(self.n_bins * W, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.chess_band_extrema_build(ctx.handle, _ptr(band), self.n_bins, W, _ptr(pmax), _ptr(pmin),
+                                                   _stream_ptr(dev)), ctx.handle, "chess_band_extrema_build")
+            have = (nd_lo, nd_hi, pmax, pmin)
             self._index[device] = have
-        sample = _native.chess_sample(band.data_ptr(), have[0].data_ptr(), have[1].data_ptr(), self.n_bins, W, 0)
+        sample = _native.chess_sample(band.data_ptr(), have[0].data_ptr(), have[1].data_ptr(),
+                                      have[2].data_ptr(), have[3].data_ptr(), self.n_bins, W, 0)
         return W, band, sample
 
     def drop_device_copies(self):

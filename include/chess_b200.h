@@ -183,12 +183,20 @@ typedef struct chess_sample {
   const double *band;    /* DEVICE, n_bins*(2W-1) doubles (chess_band_build)   */
   const int32_t *nd_lo;  /* DEVICE, n_bins, may be NULL (then no prediction)    */
   const int32_t *nd_hi;  /* DEVICE, n_bins, may be NULL                         */
+  const double *pmax;    /* DEVICE, n_bins*W: pmax[i*W+d] = max band(i, i..i+d); may be NULL */
+  const double *pmin;    /* DEVICE, n_bins*W: running minimum likewise; may be NULL */
   int64_t n_bins;
   int32_t W;
   int32_t reserved;
 } chess_sample;
 int chess_band_index_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
                            double default_value, int32_t *nd_lo, int32_t *nd_hi, void *stream);
+/* Running extrema along every upper band row.  The data range of a submatrix
+ * (chess/sim.py:368-370) starting at bin i0 with n bins is then
+ * max_r pmax[(i0+r)*W + n-1-r] - min_r pmin[...]: n lookups instead of n*n
+ * compares (the matrix is symmetric, so its upper triangle holds every value). */
+int chess_band_extrema_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                             double *pmax, double *pmin, void *stream);
 int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
                              const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                              const chess_params *params, double *ssim, double *sn, int32_t *status,
