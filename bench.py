@@ -50,8 +50,8 @@ METRIC = "region pairs/sec (SSIM+SN+z)"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", default="r1", choices=["r1", "a7"],
                     help="r1 = default `chess sim` (-r 1); a7 = -a 7")
@@ -112,7 +112,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def summary(self):
         if not self.samples:

@@ -626,6 +626,187 @@ int launch_r1(chess_ctx *ctx, const double *ref_base, const double *qry_base, co
   return launch_r1_sn<G, NW, false>(ctx, ref_base, qry_base, pairs, n_pairs, p, ssim, sn, status, stream);
 }
 
+// Band loop of the windowed regime (-a 3 / 5 / 7 ...: SSIM window 2H+1 much smaller than the
+// matrix, chess/sim.py:356-365), one pass over the pair:
+//   * per column, running sums over the last 2H+1 rows of x, y, xx, yy, xy (the row that leaves
+//     the window comes from a ring of x and y in shared memory), and over the last 7 rows of d and
+//     d*d for SN exactly as in sn_rows (same ring: d = x - y is recomputed bit-identically);
+//   * per emitted row, sums over 2H+1 (7 for SN) columns by exchanging H (3) strip prefix / suffix
+//     sums with the two neighbour lanes, then skimage's SSIM formula on every valid window and
+//     |mean| / var on every pixel;
+//   * the band's own rows also feed the column sums that verify the predicted masks.
+// C1 / C2 need the data range before the first window: it comes from the running-extrema arrays
+// (or a min / max pre-loop when those cannot be used).
+template <int G, int H>
+__device__ __forceinline__ void win_rows(const double *__restrict__ R, const double *__restrict__ Q,
+                                         size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
+                                         int lo, int hi, int lane, const LaneCols<G> &lc, double *myring,
+                                         int *susp, int *susp_n, bool with_sn, double C1, double C2,
+                                         Band2 &acc, double &ssim_sum, double *cs_r, double *cs_q) {
+  static_assert(H >= 1 && H <= 3 && G >= 3, "neighbour exchange covers at most 3 columns per side");
+  constexpr int WIN = 2 * H + 1;
+  constexpr int D = WIN > 7 ? WIN : 7;  // ring depth in rows
+  const int c0 = G * lane;
+  const double inv_np = 1.0 / (double)(WIN * WIN);
+  const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
+  double ccnt[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int c = c0 + g;
+    ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+  }
+  double sn_sum = 0.0, ss_sum = 0.0;
+  int sn_cnt = 0;
+  double Sd[G], Se[G], Vx[G], Vy[G], Vxx[G], Vyy[G], Vxy[G];
+  unsigned hist[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    Sd[g] = Se[g] = Vx[g] = Vy[g] = Vxx[g] = Vyy[g] = Vxy[g] = 0.0;
+    hist[g] = 0u;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+  }
+  const int first = lo - 3, last = hi + 3;  // exclusive; 3 >= H
+  const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+  int slot = 0;
+  double xn[G], yn[G];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
+    if (row >= 0 && row < np_) {
+      const unsigned kr = (unsigned)kmap[row];
+      const unsigned ro = kr * (unsigned)rp;
+      const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (lc.valid[g]) { xn[g] = __ldg(R + (ro + lc.xo[g])); yn[g] = __ldg(Q + (qo + lc.yo[g])); }
+      }
+    }
+  };
+  fetch(first);
+  for (int rr = first; rr < last; ++rr) {
+    double x[G], y[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
+    if (rr >= lo && rr < hi) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
+    }
+    if (rr + 1 < last) fetch(rr + 1);
+    // ring positions of the rows that leave the 7-row and the WIN-row windows
+    const int s7 = slot + D - 7 >= D ? slot - 7 : slot + D - 7;       // row rr - 7
+    const int sw = slot + D - WIN >= D ? slot - WIN : slot + D - WIN;  // row rr - WIN
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
+      double xow = xo7, yow = yo7;
+      if (WIN != 7) { xow = myring[((sw * G + g) * 2) * 32]; yow = myring[((sw * G + g) * 2 + 1) * 32]; }
+      myring[((slot * G + g) * 2) * 32] = x[g];
+      myring[((slot * G + g) * 2 + 1) * 32] = y[g];
+      const double dv = x[g] - y[g], dold = xo7 - yo7;
+      Sd[g] += dv; Sd[g] -= dold;
+      Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+      hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
+      Se[g] = hist[g] == 0u ? 0.0 : Se[g];
+      Vx[g] += x[g]; Vx[g] -= xow;
+      Vy[g] += y[g]; Vy[g] -= yow;
+      Vxx[g] = fma(x[g], x[g], Vxx[g]); Vxx[g] = fma(-xow, xow, Vxx[g]);
+      Vyy[g] = fma(y[g], y[g], Vyy[g]); Vyy[g] = fma(-yow, yow, Vyy[g]);
+      Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
+    }
+    slot = slot == D - 1 ? 0 : slot + 1;
+
+    // ---- SSIM windows whose centre row is rr - H
+    const int rcs = rr - H;
+    if (rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H) {
+      double W5[5][G];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vxx : q == 3 ? Vyy : Vxy;
+        double P[G + 1];
+        P[0] = 0.0; P[1] = V[0];
+#pragma unroll
+        for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
+        double up[H], dn[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
+          up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
+          dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int a = g - H < 0 ? 0 : g - H;
+          const int b = g + H > G - 1 ? G - 1 : g + H;
+          double w = a == 0 ? P[b + 1] : P[b + 1] - P[a];
+          if (g - H < 0) w += up[H - 1 - g];
+          if (g + H > G - 1) w += dn[g + H - G];
+          W5[q][g] = w;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = c0 + g;
+        const double ux = W5[0][g] * inv_np, uy = W5[1][g] * inv_np;
+        const double uxx = W5[2][g] * inv_np, uyy = W5[3][g] * inv_np, uxy = W5[4][g] * inv_np;
+        const double vx = cov_norm * fma(-ux, ux, uxx);
+        const double vy = cov_norm * fma(-uy, uy, uyy);
+        const double vxy = cov_norm * fma(-ux, uy, uxy);
+        const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
+        const double B1 = fma(ux, ux, fma(uy, uy, C1)), B2 = vx + vy + C2;
+        const double den = B1 * B2;
+        double S = (A1 * A2) * fast_rcp(den);
+        if (den == 0.0) S = (A1 * A2) / den;  // zero data range: IEEE 0/0 like the reference
+        if (c >= H && c <= np_ - 1 - H) ss_sum += S;
+      }
+    }
+
+    // ---- SN pixels of row rr - 3 (identical to sn_rows)
+    const int rc = rr - 3;
+    if (with_sn && rc >= lo && rc < hi) {
+      const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+      double P1[G + 1], P2[G + 1];
+      P1[0] = 0.0; P2[0] = 0.0;
+      P1[1] = Sd[0]; P2[1] = Se[0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+      double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
+        const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+        up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+        up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+        dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+        dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int a = g - 3 < 0 ? 0 : g - 3;
+        const int b = g + 3 > G - 1 ? G - 1 : g + 3;
+        double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
+        double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+        if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+        if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+        const double cnt = rcnt * ccnt[g];
+        const double m2 = w2 * cnt;
+        const double den = fma(-w1, w1, m2);
+        const bool good = lc.valid[g] & (den > fma(m2, 1e-6, 1e-290));
+        const double gq = fabs(w1) * cnt * fast_rcp(den);
+        sn_sum += good ? gq : 0.0;
+        sn_cnt += good ? 1 : 0;
+        if (!good && lc.valid[g] && w2 != 0.0) {
+          const int e = atomicAdd(susp_n, 1);
+          if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
+        }
+      }
+    }
+  }
+  acc.sn_sum = sn_sum;
+  acc.sn_cnt = sn_cnt;
+  ssim_sum = ss_sum;
+}
+
 // =====================================================================================
 // compare_r1_items_kernel -- the same computation as compare_r1_kernel, reorganised so that
 // nothing waits on anything:
@@ -704,8 +885,10 @@ __device__ __forceinline__ void finish_pair(const double *t, double mx, double m
   *status_out = CHESS_PAIR_OK;
 }
 
-template <int G, bool WITH_SN>
-__global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2))
+// H = 0: the -r 1 regime (window = whole matrix); H = 1..3: windowed regime with window 2H+1,
+// where WITH_SN is ignored and a.p.compute_sn decides at run time.
+template <int G, bool WITH_SN, int H>
+__global__ void __launch_bounds__(128, (H == 0 && G <= 4 ? 4 : 2))
 compare_r1_items_kernel(ItemArgs a) {
   constexpr int NCOL = 32 * G;
   constexpr int STRIDE = kItemHdr + 2 * NCOL;
@@ -713,14 +896,16 @@ compare_r1_items_kernel(ItemArgs a) {
   __shared__ unsigned char s_mflag[4][NCOL];
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
-  extern __shared__ __align__(16) double ringbuf[];  // 4 * 7 * G * 32 doubles (SN only)
+  extern __shared__ __align__(16) double ringbuf[];  // per warp: 7*G*32 doubles (d), or D*2G*32 (x, y)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   short *kmap = s_kmap[warp];
   unsigned char *mflag = s_mflag[warp];
   int *susp = s_susp[warp];
   int *susp_n = &s_susp_n[warp];
-  double *myring = ringbuf + (size_t)warp * 7 * G * 32 + lane;
+  constexpr int RING = H == 0 ? 7 * G * 32 : (2 * H + 1 > 7 ? 2 * H + 1 : 7) * 2 * G * 32;
+  double *myring = ringbuf + (size_t)warp * RING + lane;
+  const bool with_sn = H == 0 ? WITH_SN : a.p.compute_sn != 0;
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
   const bool use_masks = p.mappability_cutoff > 0;
@@ -795,6 +980,7 @@ compare_r1_items_kernel(ItemArgs a) {
 
     int win = (np_ & 1) ? np_ : np_ - 1;
     if (win < 3) win = 3;
+    if (H > 0) win = 2 * H + 1;
     if (win > np_) {
       if (band == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
       continue;
@@ -813,7 +999,7 @@ compare_r1_items_kernel(ItemArgs a) {
 #pragma unroll
     for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; }
     double rt[5] = {0, 0, 0, 0, 0};
-    if (m == 2 && (band == 0 || band == kBands - 1)) {  // first / last row totals for the 2x2 SSIM map
+    if (H == 0 && m == 2 && (band == 0 || band == kBands - 1)) {  // first / last row totals for the 2x2 SSIM map
       const int kr = kmap[band == 0 ? 0 : np_ - 1];
       const double *rowR = R + (size_t)kr * rp;
       const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
@@ -858,8 +1044,19 @@ compare_r1_items_kernel(ItemArgs a) {
       xmin = warp_min(xmin);
       inloop_minmax = np_ < n && (tot_one_sided > 0 || !(xmax > p.default_value && xmin < p.default_value));
     }
+    double ssim_sum = 0.0;
     if (lo < hi) {
-      if (WITH_SN) {
+      if (H > 0) {
+        if (inloop_minmax) {  // the range must be complete before the first window: both bands scan the pair
+          Band2 mm;
+          moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, 0, np_, lc, mm, nullptr, nullptr);
+          xmax = warp_max(mm.vmax); xmin = warp_min(mm.vmin);
+        }
+        const double drange = xmax - xmin;
+        const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
+        win_rows<G, (H > 0 ? H : 1)>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n,
+                                     with_sn, C1, C2, acc, ssim_sum, cs_r, cs_q);
+      } else if (WITH_SN) {
         if (inloop_minmax) {
           Band2 mm;
           moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, nullptr, nullptr);
@@ -867,6 +1064,17 @@ compare_r1_items_kernel(ItemArgs a) {
         }
         sn_rows<G, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, acc, cs_r,
                          cs_q);
+      } else {
+        Band2 mm;
+        if (inloop_minmax) {
+          moments_rows<G, true, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+          xmax = mm.vmax; xmin = mm.vmin;
+        } else {
+          moments_rows<G, true, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+        }
+        acc.T0 = mm.T0; acc.T1 = mm.T1; acc.T2 = mm.T2; acc.T3 = mm.T3; acc.T4 = mm.T4;
+      }
+      if (with_sn) {
         __syncwarp();
         const int ns = *susp_n;
         if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
@@ -888,15 +1096,6 @@ compare_r1_items_kernel(ItemArgs a) {
             }
           }
         }
-      } else {
-        Band2 mm;
-        if (inloop_minmax) {
-          moments_rows<G, true, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
-          xmax = mm.vmax; xmin = mm.vmin;
-        } else {
-          moments_rows<G, true, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
-        }
-        acc.T0 = mm.T0; acc.T1 = mm.T1; acc.T2 = mm.T2; acc.T3 = mm.T3; acc.T4 = mm.T4;
       }
     }
     acc.vmax = xmax; acc.vmin = xmin;
@@ -913,6 +1112,10 @@ compare_r1_items_kernel(ItemArgs a) {
         rec[5] = vmax; rec[6] = vmin; rec[7] = ss; rec[8] = (double)sc;
 #pragma unroll
         for (int k = 0; k < 5; ++k) rec[9 + k] = rt[k];
+      }
+      if (H > 0) {
+        const double sw = warp_sum(ssim_sum);
+        if (lane == 0) rec[14] = sw;
       }
       if (use_masks) {
 #pragma unroll
@@ -980,8 +1183,16 @@ compare_r1_items_kernel(ItemArgs a) {
           row0[k] = __ldcg(recs + 9 + k);
           rowL[k] = __ldcg(recs + (size_t)(kBands - 1) * STRIDE + 9 + k);
         }
-        finish_pair(t, mx, mn, ss, sc, row0, rowL, np_, win, m, kmap, R, Q, rp, qp, n, flip, WITH_SN,
-                    a.ssim + pi, a.sn + pi, a.status + pi);
+        if (H == 0) {
+          finish_pair(t, mx, mn, ss, sc, row0, rowL, np_, win, m, kmap, R, Q, rp, qp, n, flip, with_sn,
+                      a.ssim + pi, a.sn + pi, a.status + pi);
+        } else {  // mean of the SSIM map: band sums in band order
+          double sm = 0.0;
+          for (int b = 0; b < kBands; ++b) sm += __ldcg(recs + (size_t)b * STRIDE + 14);
+          a.ssim[pi] = sm / ((double)m * (double)m);
+          a.sn[pi] = with_sn ? ss / sc : CUDART_NAN;
+          a.status[pi] = CHESS_PAIR_OK;
+        }
       }
       a.done[pi] = 0;  // leave the arrival counters clean for the next launch
     }
@@ -1021,10 +1232,11 @@ __global__ void band_extrema_kernel(const double *__restrict__ band, long long n
   }
 }
 
-template <int G, bool WITH_SN>
+template <int G, bool WITH_SN, int H>
 int launch_items_sn(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
-  auto kern = compare_r1_items_kernel<G, WITH_SN>;
-  const size_t smem = WITH_SN ? (size_t)4 * 7 * G * 32 * sizeof(double) : 0;
+  auto kern = compare_r1_items_kernel<G, WITH_SN, H>;
+  constexpr int RING = H == 0 ? 7 * G * 32 : (2 * H + 1 > 7 ? 2 * H + 1 : 7) * 2 * G * 32;
+  const size_t smem = (H == 0 && !WITH_SN) ? 0 : (size_t)4 * RING * sizeof(double);
   static bool configured = false;
   if (!configured && smem > 0) {
     CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1045,9 +1257,12 @@ int launch_items_sn(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
 }
 
 template <int G>
-int launch_items(chess_ctx *ctx, ItemArgs &a, cudaStream_t stream) {
-  if (a.p.compute_sn) return launch_items_sn<G, true>(ctx, a, stream);
-  return launch_items_sn<G, false>(ctx, a, stream);
+int launch_items(chess_ctx *ctx, ItemArgs &a, int H, cudaStream_t stream) {
+  if (H == 3) return launch_items_sn<G, true, 3>(ctx, a, stream);
+  if (H == 2) return launch_items_sn<G, true, 2>(ctx, a, stream);
+  if (H == 1) return launch_items_sn<G, true, 1>(ctx, a, stream);
+  if (a.p.compute_sn) return launch_items_sn<G, true, 0>(ctx, a, stream);
+  return launch_items_sn<G, false, 0>(ctx, a, stream);
 }
 
 size_t items_stride(int G) { return (size_t)kItemHdr + 2 * 32 * (size_t)G; }
@@ -1119,9 +1334,16 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
                                cudaStream_t stream, bool *handled) {
   *handled = false;
   const bool r1 = p.abs_window == 0 && p.rel_window == 1.0;
+  // windowed regime: -a 3 / 5 / 7 (an even -a is lowered by one, values below 3 become 3; sim.py:360-365)
+  int H = 0;
+  if (p.abs_window > 0) {
+    const int w = window_rule(0, p.abs_window, 1.0);
+    H = (w - 1) / 2;
+  }
+  const bool windowed = p.abs_window > 0 && H >= 1 && H <= 3 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
   // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
-  if (!r1 || !plain_default || max_n > 248 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
+  if (!(r1 || windowed) || !plain_default || max_n > 248 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
       !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
     return CHESS_OK;
   const int G = max_n <= 93 ? 3 : max_n <= 124 ? 4 : max_n <= 155 ? 5 : max_n <= 186 ? 6 : max_n <= 217 ? 7 : 8;
@@ -1171,12 +1393,12 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     a.retry_cur = flags + par; a.retry_next = flags + (par ^ 1);
     int rc;
     switch (G) {
-      case 3: rc = launch_items<3>(ctx, a, stream); break;
-      case 4: rc = launch_items<4>(ctx, a, stream); break;
-      case 5: rc = launch_items<5>(ctx, a, stream); break;
-      case 6: rc = launch_items<6>(ctx, a, stream); break;
-      case 7: rc = launch_items<7>(ctx, a, stream); break;
-      default: rc = launch_items<8>(ctx, a, stream); break;
+      case 3: rc = launch_items<3>(ctx, a, r1 ? 0 : H, stream); break;
+      case 4: rc = launch_items<4>(ctx, a, r1 ? 0 : H, stream); break;
+      case 5: rc = launch_items<5>(ctx, a, r1 ? 0 : H, stream); break;
+      case 6: rc = launch_items<6>(ctx, a, r1 ? 0 : H, stream); break;
+      case 7: rc = launch_items<7>(ctx, a, r1 ? 0 : H, stream); break;
+      default: rc = launch_items<8>(ctx, a, r1 ? 0 : H, stream); break;
     }
     if (rc) return rc;
     ctx->items_parity ^= 1;

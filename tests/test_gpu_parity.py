@@ -355,7 +355,9 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
     eng = cb.CompareEngine(re_, trees, qe, trees)
     flipped = [(pid, r, cb.GenomicRegion(chromosome=q.chromosome, start=q.start, end=q.end, strand="-"))
                for pid, r, q in pairs[::5]]
-    for kw in (dict(), dict(keep_unmappable_bins=True), dict(mappability_cutoff=0.3), dict(compute_sn=False)):
+    for kw in (dict(), dict(keep_unmappable_bins=True), dict(mappability_cutoff=0.3), dict(compute_sn=False),
+               dict(absolute_window_size=7), dict(absolute_window_size=5, mappability_cutoff=0.3),
+               dict(absolute_window_size=3, compute_sn=False), dict(absolute_window_size=8, keep_unmappable_bins=True)):
         for plist in (pairs, flipped):
             gen = eng.compare(plist, kernel=1, **kw)
             for kernel in (0, 2):   # 0: work-item kernel, 2: CTA-per-pair tuned kernel
@@ -367,12 +369,13 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
     from chess_b200 import synth
     for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000):
         plist = synth.sliding_pairs(genome, window_bp, 900000)
-        gen = eng.compare(plist, kernel=1)
-        for kernel in (0, 2):
-            fast = eng.compare(plist, kernel=kernel)
-            assert np.array_equal(fast[3], gen[3])
-            np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
-            np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+        for kw in (dict(), dict(absolute_window_size=7)):
+            gen = eng.compare(plist, kernel=1, **kw)
+            for kernel in (0, 2):
+                fast = eng.compare(plist, kernel=kernel, **kw)
+                assert np.array_equal(fast[3], gen[3])
+                np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+                np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
 
 
 def test_band_kernels_coincidentally_masked_bins(cb):
@@ -408,14 +411,15 @@ def test_band_kernels_coincidentally_masked_bins(cb):
     oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
     hits = 0
     for kernel in (0, 2, 1):
-        ids, s, sn, st = eng.compare(pairs, kernel=kernel, mappability_cutoff=0.2)
+      for extra in (dict(), dict(absolute_window_size=7)):
+        ids, s, sn, st = eng.compare(pairs, kernel=kernel, mappability_cutoff=0.2, **extra)
         for k, (pid, rr, qr) in enumerate(pairs):
             op = (pid, O.Region(rr.start, rr.end, rr.chromosome, strand=rr.strand),
                   O.Region(qr.start, qr.end, qr.chromosome, strand=qr.strand))
             m, _ = O.sub_matrix_from_edges_dict(ore, otrees, op[1], 1)
             masked = O.find_masked_rows(m, 1)
             hits += int(any(int(masked_ix) + (rr.start - 1) // 10000 in special for masked_ix in masked))
-            _, os_, osn = O.compare_pair(op, ore, otrees, oqe, otrees, mappability_cutoff=0.2)
+            _, os_, osn = O.compare_pair(op, ore, otrees, oqe, otrees, mappability_cutoff=0.2, **extra)
             assert close(s[k], os_, RTOL), (kernel, pid, s[k], os_)
             assert close(sn[k], osn, RTOL), (kernel, pid, sn[k], osn)
     assert hits > 0   # the construction does produce coincidentally masked bins
