@@ -14,10 +14,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchess_b200.so")
-SOURCES = ["api.cu", "oe.cu", "compare_generic.cu", "compare_fast.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chess_b200.h")]
+SOURCES = ["api.cu", "oe.cu", "compare_generic.cu", "compare_fast.cu",
+           "items_h0.cu", "items_h1.cu", "items_h2.cu", "items_h3.cu"]
+HEADERS = ["common.cuh", "compare_kernels.cuh", os.path.join("..", "..", "include", "chess_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["--shared", "-cudart", "static"]
 
 
 def _stamp():
@@ -25,7 +27,7 @@ def _stamp():
     for name in SOURCES + HEADERS:
         with open(os.path.join(CSRC, name), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + LINK_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -36,14 +38,31 @@ def build(force=False, verbose=False):
         if open(stamp_file).read().strip() == stamp:
             return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+    obj_dir = os.path.join(CSRC, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, proc
+
+    # one nvcc per translation unit, in parallel (the kernel instantiations dominate the build time)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = "".join(r[2].stdout + r[2].stderr for r in results)
+    if any(r[2].returncode != 0 for r in results):
+        sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libchess_b200.so")
+    proc = subprocess.run([nvcc] + NVCC_FLAGS + LINK_FLAGS + [r[1] for r in results] + ["-o", LIB],
+                          capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(log + proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed linking libchess_b200.so")
     if verbose:
-        sys.stderr.write(proc.stdout + proc.stderr)
+        sys.stderr.write(log + proc.stdout + proc.stderr)
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return LIB

@@ -39,6 +39,28 @@ struct chess_ctx {
 // generic kernel must (never visible to callers).
 #define CHESS_PAIR_RETRY 100
 
+// Arguments of the work-item kernel (compare_kernels.cuh).
+struct chess_item_args {
+  const double *ref_band, *qry_band;
+  const int *ref_lo, *ref_hi, *qry_lo, *qry_hi;
+  const double *ref_pmax, *ref_pmin, *qry_pmax, *qry_pmin;  // running extrema, may be NULL
+  const chess_pair *pairs;
+  long long n_pairs;
+  chess_params p;
+  double *ssim, *sn;
+  int *status;
+  double *scratch;            // n_pairs * kBands * (kItemHdr + 2*NCOL)
+  int *done;                  // n_pairs, zero on entry, zero on exit
+  unsigned long long *counter_cur, *counter_next;
+  int *retry_cur, *retry_next;
+};
+
+// Work-item kernel launchers, one translation unit per window half-width H (0 = -r 1 regime).
+int chess_items_launch_h0(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+int chess_items_launch_h1(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+int chess_items_launch_h2(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+
 // Internal launchers (one per translation unit).
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,
                                  const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
