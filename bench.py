@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", default="r1", choices=["r1", "a7"],
                     help="r1 = default `chess sim` (-r 1); a7 = -a 7")
+    ap.add_argument("--workload", default="chr2_25kb", choices=["chr2_25kb", "hg38_10kb"],
+                    help="chr2_25kb = BASELINE configs[1] (the contract's bench line); hg38_10kb = configs[2], "
+                         "genome-wide 10 kb, ~100k pairs of 2 Mb, pairs sharded over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 auto, 1 force the generic kernel, 2 the CTA-per-pair tuned kernel")
@@ -65,9 +68,20 @@ def window_params(tag):
     return dict(absolute_window_size=7) if tag == "a7" else dict()
 
 
-def make_workload(rank):
-    """Synthetic chr2 @ 25 kb sample pair (seeded by rank) and the sliding pair list."""
+def make_workload(rank, workload="chr2_25kb", world=1):
+    """Synthetic sample pair and the sliding pair list.
+
+    chr2_25kb: every rank gets its own chr2-sized samples (seeded by rank) and the full pair list.
+    hg38_10kb: all ranks build the same genome; rank r keeps a contiguous shard of the pair list."""
     from chess_b200 import synth
+    from chess_b200.distributed import my_shard
+    if workload == "hg38_10kb":
+        genome = synth.Genome(synth.chromosome_bins(synth.HG38_CHROM_BP, 10000), 10000, synth.HG38_CHROM_BP)
+        ref = synth.synthetic_sample(genome, 215, seed=100, structure_seed=7)
+        qry = synth.synthetic_sample(genome, 215, seed=101, structure_seed=7, perturb=0.1)
+        pairs = synth.sliding_pairs(genome, WINDOW_BP, 30000)
+        lo, hi = my_shard(len(pairs), rank, world)
+        return genome, ref, qry, pairs[lo:hi]
     genome = synth.Genome(synth.chromosome_bins([("chr2", CHR2_BP)], BIN), BIN, [("chr2", CHR2_BP)])
     ref = synth.synthetic_sample(genome, 100, seed=100 + 2 * rank, structure_seed=7 + rank)
     qry = synth.synthetic_sample(genome, 100, seed=101 + 2 * rank, structure_seed=7 + rank, perturb=0.1)
@@ -167,6 +181,20 @@ def cpu_setup(genome, ref, qry, pairs, window, oe=None):
                       O.Region(q.start, q.end, q.chromosome, strand=q.strand)) for pid, r, q in pairs])
 
 
+def cpu_subset(genome, ref, qry, pairs, max_bins=12000):
+    """The CPU oracle keeps its contacts in a dict of dicts (like the reference); for genome-wide
+    workloads only the first `max_bins` bins and the pairs inside them are handed to it."""
+    if genome.n_bins <= max_bins:
+        return genome, ref, qry, pairs
+    from chess_b200 import synth
+    limit_bp = max_bins * genome.bin_size
+    first = genome.names[0]
+    sub = synth.Genome([(first, max_bins)], genome.bin_size, [(first, limit_bp)])
+    keep = lambda s: tuple(a[(s[1] < max_bins)] for a in s)  # noqa: E731  (src <= sink)
+    pairs = [p for p in pairs if p[1].chromosome == first and p[1].end <= limit_bp and p[2].end <= limit_bp]
+    return sub, keep(ref), keep(qry), pairs
+
+
 def cpu_run(sample_idx, pool, cores):
     """One pass over `sample_idx` with the reference's parallel structure:
     ceil(P / p)-sized chunks, one per worker (bin/chess:196-214)."""
@@ -188,7 +216,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
-    genome, ref, qry, pairs = make_workload(0)
+    genome, ref, qry, pairs = make_workload(0, args.workload, 1)
+    genome, ref, qry, pairs = cpu_subset(genome, ref, qry, pairs)
     cpu_setup(genome, ref, qry, pairs, args.window)
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
@@ -222,9 +251,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_pairs, n_bins, sample=None):
-    cfg = {"workload": "configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb, chess sim %s, SN on"
-                       % (n_bins, "-r 1 (default)" if args.window == "r1" else "-a 7"),
-           "pairs_per_gpu": n_pairs, "bins_per_pair": 81, "window": args.window,
+    what = ("configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb" if args.workload == "chr2_25kb"
+            else "configs[2]: human hg38 @ 10 kb genome-wide (%d bins), 2 Mb windows step 30 kb") % n_bins
+    cfg = {"workload": "%s, chess sim %s, SN on" % (what, "-r 1 (default)" if args.window == "r1" else "-a 7"),
+           "pairs_per_gpu": n_pairs, "bins_per_pair": 81 if args.workload == "chr2_25kb" else 201,
+           "window": args.window,
            "l2": "flushed before every step (512 MiB write)",
            "parallelism": "pairs sharded, one process per GPU, no collective"}
     if sample is not None:
@@ -247,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    genome, ref, qry, pairs = make_workload(rank)
+    genome, ref, qry, pairs = make_workload(rank, args.workload, world)
     regions = genome.regions()
     trees = cb.region_interval_trees(regions)
     params = window_params(args.window)
@@ -379,7 +410,8 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak" if args.workload == "chr2_25kb" else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": dict(workload_config(args, n_pairs, len(regions)),
                        pairs_ok=ok, wall_s_timed_region=wall, zscore_device_matches_host=z_dev_ok,
                        e2e_cold={"seconds": cold_s, "pairs_per_s": n_pairs / cold_s,
@@ -406,7 +438,16 @@ def run_ours(args, rank, world, local_rank):
 def cpu_baseline(genome, ref, qry, pairs, args, re_, qe, gpu_ssim, gpu_sn):
     """Oracle on the host cores, bounded sample (~10-30 s), same inputs as the GPU run."""
     import multiprocessing as mp
-    oe = [list(zip(*[x.tolist() for x in s.triples()])) for s in (re_, qe)]  # the very O/E the GPU used
+    id_to_k = {p[0]: k for k, p in enumerate(pairs)}
+    limit = 12000
+    if genome.n_bins > limit:
+        genome, ref, qry, pairs = cpu_subset(genome, ref, qry, pairs, limit)
+    # the very O/E values the GPU used (restricted to the bins the CPU sample covers)
+    oe = []
+    for smp in (re_, qe):
+        a, b, w = smp.triples()
+        sel = b < genome.n_bins
+        oe.append(list(zip(a[sel].tolist(), b[sel].tolist(), w[sel].tolist())))
     cpu_setup(genome, ref, qry, pairs, args.window, oe=oe)
     cores = os.cpu_count() or 1
     with mp.get_context("fork").Pool(cores) as pool:
@@ -416,8 +457,9 @@ def cpu_baseline(genome, ref, qry, pairs, args, re_, qe, gpu_ssim, gpu_sn):
         idx = cpu_sample(len(pairs), target)
         dt, rows = cpu_run(idx, pool, cores)
     worst = 0.0
-    for i, (_, s, sn) in zip(idx, rows):
-        for got, want in ((gpu_ssim[i], s), (gpu_sn[i], sn)):
+    for i, (pid, s, sn) in zip(idx, rows):
+        k = id_to_k[pid]
+        for got, want in ((gpu_ssim[k], s), (gpu_sn[k], sn)):
             if not (np.isnan(want) and np.isnan(got)):
                 worst = max(worst, abs(got - want) / max(abs(want), 1e-300))
     return {"value": len(idx) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
