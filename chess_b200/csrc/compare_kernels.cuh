@@ -8,14 +8,14 @@
 
 namespace {
 
+// Reciprocal: rcp.approx.ftz.f64 (MUFU.RCP64H, measured max relative error 9.9e-7 on B200,
+// profiles/r01_microbench.txt) refined by one Newton step -> 1e-12, five orders below the 1e-6
+// parity budget, at 1 MUFU + 2 DFMA instead of the ~13 issue slots of an IEEE division.
 __device__ __forceinline__ double fast_rcp(double d) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-d, y, 1.0);
+  return fma(y, e, y);
 }
 
 // numpy's pairwise summation for n = 49 contiguous doubles (n < 128: eight running accumulators

@@ -62,6 +62,27 @@ __global__ void lds_kernel(int iters, double *sink) {
   }
   if (a == 1234.5) *sink = a;
 }
+__global__ void rcp_err_kernel(double *out) {
+  // max relative error of rcp.approx.ftz.f64 raw / after one / after two Newton steps
+  double e0 = 0, e1 = 0, e2 = 0;
+  unsigned long long st = 88172645463325252ull + threadIdx.x * 7919ull + blockIdx.x * 104729ull;
+  for (int i = 0; i < 20000; ++i) {
+    st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+    const double m = 1.0 + (double)(st >> 11) * (1.0 / 9007199254740992.0);   // [1,2)
+    const int ex = (int)((st >> 3) % 600) - 300;
+    const double d = ldexp(m, ex);
+    double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = 1.0 / d;
+    e0 = fmax(e0, fabs(y - t) / t);
+    double e = fma(-d, y, 1.0); y = fma(y, e, y);
+    e1 = fmax(e1, fabs(y - t) / t);
+    e = fma(-d, y, 1.0); y = fma(y, e, y);
+    e2 = fmax(e2, fabs(y - t) / t);
+  }
+  atomicMax((unsigned long long *)&out[0], (unsigned long long)__double_as_longlong(e0));
+  atomicMax((unsigned long long *)&out[1], (unsigned long long)__double_as_longlong(e1));
+  atomicMax((unsigned long long *)&out[2], (unsigned long long)__double_as_longlong(e2));
+}
 template <typename F> float timeit(F f, int n = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   f(); cudaDeviceSynchronize();
@@ -92,5 +113,7 @@ int main() {
     double sh = (double)iters * 8 * sms * 4 * 512; printf("SHFL.32: %.1f G lane-shuffles/s = %.1f lanes/clk/SM nominal\n", sh / ms / 1e6, sh / (ms * 1e-3) / sms / (prop.clockRate * 1e3)); }
   { int iters = 4096; float ms = timeit([&] { lds_kernel<<<sms * 4, 512>>>(iters, sink); });
     double by = (double)iters * 4 * 8 * sms * 4 * 512; printf("LDS.64: %.0f GB/s = %.1f B/clk/SM nominal\n", by / ms / 1e6, by / (ms * 1e-3) / sms / (prop.clockRate * 1e3)); }
+  { double *errbuf; CK(cudaMalloc(&errbuf, 24)); CK(cudaMemset(errbuf, 0, 24)); rcp_err_kernel<<<64, 128>>>(errbuf); double h[3]; CK(cudaMemcpy(h, errbuf, 24, cudaMemcpyDeviceToHost));
+    printf("rcp.approx.ftz.f64 max rel error: raw %.3e, +1 Newton %.3e, +2 Newton %.3e\n", h[0], h[1], h[2]); }
   return 0;
 }
