@@ -622,8 +622,25 @@ def format_table(pairs, results, bg=None):
     return "".join(lines)
 
 
+def background_regions_from_query(query_regions, query_region, limit_background=False):
+    """Every query bin start, both strands, with the span of `query_region`; kept if it ends
+    inside its chromosome, optionally only on the query region's chromosome (bin/chess:272-298)."""
+    ends = defaultdict(int)
+    for r in query_regions:
+        ends[r.chromosome] = max(ends[r.chromosome], r.end)
+    span = query_region.end - query_region.start
+    out = []
+    for r in query_regions:
+        if limit_background and r.chromosome != query_region.chromosome:
+            continue
+        for strand in ("+", "-"):
+            if r.start + span <= ends[r.chromosome]:
+                out.append(Region(r.start, r.start + span, r.chromosome, strand=strand))
+    return out
+
+
 def sim(ref_edges, ref_regions, qry_edges, qry_regions, pairs, background_regions=None,
-        **kw):
+        background_query=False, limit_background=False, **kw):
     """Serial equivalent of `Chess.sim` after loading (bin/chess:189-353).
 
     Returns (results {id: [ssim, sn, z]}, bg {id: (z_bg, p_bg)} or None).
@@ -633,10 +650,12 @@ def sim(ref_edges, ref_regions, qry_edges, qry_regions, pairs, background_region
     for pid, s, sn in compare_chunk(pairs, ref_edges, rt, qry_edges, qt, True, **kw):
         raw[pid] = [s, sn]
     results = run_zscores(raw)
-    if background_regions is None:
+    if background_regions is None and not background_query:
         return results, None
     bg = {}
-    for pid, rr, _ in pairs:
+    for pid, rr, qr in pairs:
+        if background_query:
+            background_regions = background_regions_from_query(qry_regions, qr, limit_background)
         bpairs = [(k, rr, b) for k, b in enumerate(background_regions)]
         vals = [s for _, s, _ in compare_chunk(bpairs, ref_edges, rt, qry_edges, qt, False, **kw)]
         bg[pid] = background_stats(results[pid][0], vals)

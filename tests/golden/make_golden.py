@@ -357,7 +357,9 @@ def main():
     # ---- the CLI itself  (bin/chess:80-359), two runs
     Chess = load_cli_class()
     for tag, extra in (("cli_default", []),
-                       ("cli_abs7_bg", ["-a", "7", "--background-regions", P("background.bed")])):
+                       ("cli_abs7_bg", ["-a", "7", "--background-regions", P("background.bed")]),
+                       ("cli_bgquery_limit", ["-a", "5", "--background-query", "--limit-background"]),
+                       ("cli_bgquery_all", ["--background-query", "--mappability-cutoff", "0.3"])):
         out_path = P(tag + ".tsv")
         argv = ["chess", "sim", P("ref.sparse"), P("qry.sparse"), P("pairs.bedpe"), out_path,
                 "--reference-regions", P("ref.bed"), "--query-regions", P("qry.bed"), "-p", "1"] + extra  # p=1: with p>1 the z-score sum order follows queue arrival order

@@ -169,6 +169,8 @@ def _table(path):
     ("cli_default", []),
     ("cli_abs7_bg", ["-a", "7", "--background-regions", "background.bed"]),
     ("cli_oe_input", ["--oe-input", "-r", "0.4", "--keep-unmappable-bins"]),
+    ("cli_bgquery_limit", ["-a", "5", "--background-query", "--limit-background"]),
+    ("cli_bgquery_all", ["--background-query", "--mappability-cutoff", "0.3"]),
 ])
 def test_cli_table(cb, toy, tmp_path, tag, extra):
     from chess_b200.cli import Chess
@@ -423,3 +425,89 @@ def test_band_kernels_coincidentally_masked_bins(cb):
             assert close(s[k], os_, RTOL), (kernel, pid, s[k], os_)
             assert close(sn[k], osn, RTOL), (kernel, pid, sn[k], osn)
     assert hits > 0   # the construction does produce coincidentally masked bins
+
+
+def test_band_index_and_extrema_arrays(cb):
+    """The per-bin index (nearest non-default entries) and the running extrema that the item
+    kernel uses for mask prediction and the data range, against a dense numpy reconstruction."""
+    from chess_b200.engine import DeviceContacts
+    rng = np.random.default_rng(21)
+    n, W = 300, 48
+    dense = np.ones((n, n))
+    src, sink, val = [], [], []
+    for i in range(n):
+        if i % 37 in (5, 6):
+            continue                                   # bins without any entry
+        for j in range(i, min(n, i + 40)):
+            if (j % 37 in (5, 6)) or rng.random() < 0.5:
+                continue
+            v = float(rng.lognormal(0, 0.5)) if rng.random() > 0.05 else 1.0   # some stored values equal the default
+            src.append(i); sink.append(j); val.append(v)
+            dense[i, j] = dense[j, i] = v
+    dc = DeviceContacts(np.array(src), np.array(sink), np.array(val), n_bins=n)
+    w, band, sample = dc.sample_on(0, W)
+    nd_lo, nd_hi, pmax, pmin = [t.cpu().numpy() for t in dc._index[0]]
+    pmax, pmin = pmax.reshape(n, w), pmin.reshape(n, w)
+    for i in range(n):
+        lo_c = [k for k in range(max(0, i - w + 1), i + 1) if dense[i, k] != 1.0]
+        hi_c = [k for k in range(i, min(n, i + w)) if dense[i, k] != 1.0]
+        assert nd_lo[i] == (max(lo_c) if lo_c else -1), i
+        assert nd_hi[i] == (min(hi_c) if hi_c else 0x7fffffff), i
+        row = dense[i, i:min(n, i + w)]
+        assert np.array_equal(pmax[i, :len(row)], np.maximum.accumulate(row)), i
+        assert np.array_equal(pmin[i, :len(row)], np.minimum.accumulate(row)), i
+
+
+def test_bin_masked_in_one_sample_only(cb):
+    """A bin that is unmappable in the reference only is removed from the query too, where it may
+    hold the query's largest value: the data range must come from the compacted pair."""
+    from chess_b200 import synth
+    from chess_b200.engine import DeviceContacts
+    genome = synth.Genome([("c", 300)], 10000)
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    rng = np.random.default_rng(33)
+    def sample(dead, spike):
+        src, sink, val = [], [], []
+        for i in range(300):
+            for j in range(i, min(300, i + 70)):
+                if i in dead or j in dead or rng.random() < 0.3:
+                    continue
+                v = float(rng.lognormal(0, 0.4))
+                if spike is not None and (i == spike or j == spike):
+                    v *= 40.0                       # by far the largest values of the window
+                src.append(i); sink.append(j); val.append(v)
+        return DeviceContacts(np.array(src), np.array(sink), np.array(val), n_bins=300)
+    re_ = sample(dead={120, 121}, spike=None)
+    qe = sample(dead=set(), spike=120)
+    pairs = synth.sliding_pairs(genome, 600000, 50000)     # 61-bin windows
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    oregions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in regions]
+    otrees = O.region_trees(oregions)
+    ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
+    oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
+    for kw in (dict(), dict(absolute_window_size=7), dict(keep_unmappable_bins=True)):
+        ids, s, sn, st = eng.compare(pairs, **kw)
+        for k, (pid, rr, qr) in enumerate(pairs):
+            op = (pid, O.Region(rr.start, rr.end, rr.chromosome, strand=rr.strand),
+                  O.Region(qr.start, qr.end, qr.chromosome, strand=qr.strand))
+            _, os_, osn = O.compare_pair(op, ore, otrees, oqe, otrees, **kw)
+            assert close(s[k], os_, RTOL), (kw, pid, s[k], os_)
+            assert close(sn[k], osn, RTOL), (kw, pid, sn[k], osn)
+
+
+def test_zscore_kernel(cb):
+    import ctypes as C
+    import torch
+    from chess_b200 import _native
+    from chess_b200.engine import get_context
+    rng = np.random.default_rng(3)
+    s = rng.normal(0.2, 0.1, 5000)
+    s[::13] = np.nan
+    d = torch.from_numpy(s).cuda()
+    z = torch.empty_like(d)
+    ctx = get_context(0)
+    _native.check(_native.lib.chess_zscore(ctx.handle, C.c_void_p(d.data_ptr()), len(s), C.c_void_p(z.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), ctx.handle)
+    want = (s - np.nanmean(s)) / np.nanstd(s)
+    np.testing.assert_allclose(z.cpu().numpy(), want, rtol=1e-10, equal_nan=True)

@@ -110,7 +110,7 @@ def test_compare_pair_and_structures(golden, toy):
             assert same_float(sn, unhex(gsn))
 
 
-def _cli_table(toy, background=None, oe_input=False, **kw):
+def _cli_table(toy, background=None, oe_input=False, background_query=False, limit_background=False, **kw):
     if oe_input:
         def load(tag):
             regions, conv, _ = O.load_regions(toy(tag + ".bed"))
@@ -124,7 +124,8 @@ def _cli_table(toy, background=None, oe_input=False, **kw):
     bgr = None
     if background:
         bgr, _, _ = O.load_regions(toy(background), ignore_ix=True)
-    res, bg = O.sim(re_, rr, qe, qr, pairs, background_regions=bgr, **kw)
+    res, bg = O.sim(re_, rr, qe, qr, pairs, background_regions=bgr, background_query=background_query,
+                    limit_background=limit_background, **kw)
     return O.format_table(pairs, res, bg)
 
 
@@ -134,6 +135,10 @@ def test_cli_tables_byte_identical(toy):
         open(toy("cli_abs7_bg.tsv")).read()
     assert _cli_table(toy, oe_input=True, relative_window_size=0.4, keep_unmappable_bins=True) == \
         open(toy("cli_oe_input.tsv")).read()
+    assert _cli_table(toy, background_query=True, limit_background=True, absolute_window_size=5) == \
+        open(toy("cli_bgquery_limit.tsv")).read()
+    assert _cli_table(toy, background_query=True, mappability_cutoff=0.3) == \
+        open(toy("cli_bgquery_all.tsv")).read()
 
 
 def test_ssim_restatement_equals_bruteforce():
