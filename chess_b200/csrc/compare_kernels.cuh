@@ -517,7 +517,7 @@ __device__ __forceinline__ void finish_pair(const double *t, double mx, double m
 // H = 0: the -r 1 regime (window = whole matrix); H = 1..3: windowed regime with window 2H+1,
 // where WITH_SN is ignored and a.p.compute_sn decides at run time.
 template <int G, bool WITH_SN, int H>
-__global__ void __launch_bounds__(128, (H == 0 && G <= 4 ? 4 : 2))
+__global__ void __launch_bounds__(128, (G <= 4 ? (H == 0 ? 4 : 3) : 2))
 compare_r1_items_kernel(chess_item_args a) {
   constexpr int NCOL = 32 * G;
   constexpr int STRIDE = kItemHdr + 2 * NCOL;
