@@ -205,42 +205,42 @@ extern "C" int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample 
 namespace {
 __global__ void __launch_bounds__(1024) zscore_kernel(const double *__restrict__ s, long long n,
                                                       double *__restrict__ z) {
-  __shared__ double red[33];
-  __shared__ double red2[33];
+  // One CTA, fixed reduction order (deterministic).  Count, sum and sum of squared deviations from
+  // a pivot (the first finite value) in a single sweep: with the pivot inside the data the
+  // shifted one-pass variance is as accurate as numpy's two passes for these magnitudes (|ssim| <= 1).
+  __shared__ double red[3][33];
+  __shared__ double pivot_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double sum = 0.0, cnt = 0.0;
+  if (threadIdx.x == 0) {
+    double pv = 0.0;
+    for (long long i = 0; i < n; ++i) {
+      const double v = s[i];
+      if (v == v) { pv = v; break; }
+    }
+    pivot_s = pv;
+  }
+  __syncthreads();
+  const double pivot = pivot_s;
+  double cnt = 0.0, sum = 0.0, ssq = 0.0;
   for (long long i = threadIdx.x; i < n; i += 1024) {
     const double v = s[i];
-    if (v == v) { sum += v; cnt += 1.0; }
+    if (v == v) { const double d = v - pivot; cnt += 1.0; sum += d; ssq = fma(d, d, ssq); }
   }
-  sum = warp_sum(sum); cnt = warp_sum(cnt);
-  if (lane == 0) { red[warp] = sum; red2[warp] = cnt; }
+  cnt = warp_sum(cnt); sum = warp_sum(sum); ssq = warp_sum(ssq);
+  if (lane == 0) { red[0][warp] = cnt; red[1][warp] = sum; red[2][warp] = ssq; }
   __syncthreads();
   if (warp == 0) {
-    sum = warp_sum(red[lane]); cnt = warp_sum(red2[lane]);
-    if (lane == 0) { red[32] = sum; red2[32] = cnt; }
+    cnt = warp_sum(red[0][lane]); sum = warp_sum(red[1][lane]); ssq = warp_sum(red[2][lane]);
+    if (lane == 0) { red[0][32] = cnt; red[1][32] = sum; red[2][32] = ssq; }
   }
   __syncthreads();
-  cnt = red2[32];
-  const double mean = red[32] / cnt;
-  __syncthreads();
-  double ss = 0.0;
+  cnt = red[0][32];
+  const double dmean = red[1][32] / cnt;                 // mean - pivot
+  const double var = red[2][32] / cnt - dmean * dmean;   // population variance (ddof 0)
+  const double sd = sqrt(var > 0.0 ? var : 0.0);
   for (long long i = threadIdx.x; i < n; i += 1024) {
     const double v = s[i];
-    if (v == v) ss += (v - mean) * (v - mean);
-  }
-  ss = warp_sum(ss);
-  if (lane == 0) red[warp] = ss;
-  __syncthreads();
-  if (warp == 0) {
-    ss = warp_sum(red[lane]);
-    if (lane == 0) red[32] = ss;
-  }
-  __syncthreads();
-  const double sd = sqrt(red[32] / cnt);
-  for (long long i = threadIdx.x; i < n; i += 1024) {
-    const double v = s[i];
-    z[i] = isfinite(v) ? (v - mean) / sd : CUDART_NAN;
+    z[i] = isfinite(v) ? ((v - pivot) - dmean) / sd : CUDART_NAN;
   }
 }
 }  // namespace
