@@ -49,17 +49,18 @@ struct chess_item_args {
   chess_params p;
   double *ssim, *sn;
   int *status;
-  double *scratch;            // n_pairs * kBands * (kItemHdr + 2*NCOL)
+  int ncol_pad;               // columns reserved per pair in maps and records (max n, rounded to 32)
+  double *scratch;            // n_pairs * kBands * (kItemHdr + 2*ncol_pad)
   int *done;                  // n_pairs, zero on entry, zero on exit
   unsigned long long *counter_cur, *counter_next;
   int *retry_cur, *retry_next;
 };
 
 // Work-item kernel launchers, one translation unit per window half-width H (0 = -r 1 regime).
-int chess_items_launch_h0(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
-int chess_items_launch_h1(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
-int chess_items_launch_h2(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
-int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+int chess_items_launch_h0(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
+int chess_items_launch_h1(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
+int chess_items_launch_h2(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
+int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
 
 // Internal launchers (one per translation unit).
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,

@@ -240,8 +240,8 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
     if (lane == 0) susp_n[warp] = 0;
     __syncwarp();
     if (lo < hi) {
-      LaneCols<G> lc;
-      lane_cols<G>(lc, kmap, n, np_, flip, lane);
+      LaneCols<G, false> lc;
+      lane_cols<G, false>(lc, kmap, n, np_, flip, lane, 0, 0, np_);
       moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, acc, nullptr, nullptr);
       if (WITH_SN) sn_rows<G, false>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp[warp],
                                      &susp_n[warp], acc, nullptr, nullptr);
@@ -397,7 +397,7 @@ __global__ void band_extrema_kernel(const double *__restrict__ band, long long n
   }
 }
 
-size_t items_stride(int G) { return (size_t)kItemHdr + 2 * 32 * (size_t)G; }
+size_t items_stride(int ncol_pad) { return (size_t)kItemHdr + 2 * (size_t)ncol_pad; }
 
 }  // namespace
 
@@ -475,17 +475,34 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   const bool windowed = p.abs_window > 0 && H >= 1 && H <= 3 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
   // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
-  if (!(r1 || windowed) || !plain_default || max_n > 248 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
+  if (!(r1 || windowed) || !plain_default || max_n > 1024 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
       !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
     return CHESS_OK;
-  const int G = max_n <= 93 ? 3 : max_n <= 124 ? 4 : max_n <= 155 ? 5 : max_n <= 186 ? 6 : max_n <= 217 ? 7 : 8;
-  const size_t stride = items_stride(G);
-  const int64_t chunk = 16384;
+  // column-strip width: the narrowest strip that holds the matrix in one block; wider matrices are
+  // swept in blocks of 31*G - 6 columns, with the width that wastes the fewest lane-columns
+  int G = 8;
+  if (max_n <= 248) {
+    G = max_n <= 93 ? 3 : max_n <= 124 ? 4 : max_n <= 155 ? 5 : max_n <= 186 ? 6 : max_n <= 217 ? 7 : 8;
+  } else {
+    long best = -1;
+    for (int g = 5; g <= 8; ++g) {
+      const int span = 31 * g - 6;
+      const long cost = (long)((max_n + span - 1) / span) * g;
+      if (best < 0 || cost <= best) { best = cost; G = g; }
+    }
+  }
+  const int ncol_pad = ((max_n + 31) / 32) * 32;
+  const size_t stride = items_stride(ncol_pad);
+  // pairs per launch: at most 16384 (size of the arrival-counter array) and at most ~256 MB of band records
+  const int64_t chunk_max = 16384;
+  int64_t chunk = (int64_t)((size_t)(256u << 20) / ((size_t)kBands * stride * sizeof(double)));
+  if (chunk > chunk_max) chunk = chunk_max;
+  if (chunk < 512) chunk = 512;
   const int64_t cap = n_pairs < chunk ? n_pairs : chunk;
   // workspace: [2 counters][2 retry flags + pad][done: chunk ints][scratch: cap * kBands * stride doubles];
   // the arrival counters sit at a fixed offset and size so that scratch records can never overlap them
   const size_t head = 64;
-  const size_t done_bytes = (size_t)chunk * sizeof(int);
+  const size_t done_bytes = (size_t)chunk_max * sizeof(int);
   const size_t need = head + done_bytes + (size_t)cap * kBands * stride * sizeof(double);
   if (ctx->d_items_bytes < need) {
     if (ctx->d_items) cudaFree(ctx->d_items);
@@ -503,7 +520,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   if (ctx->items_done_cap == 0) {  // fresh allocation: counters, flags and arrival counters start at zero
     CHESS_CUDA(ctx, cudaMemsetAsync(base, 0, head + done_bytes, stream));
     ctx->items_parity = 0;
-    ctx->items_done_cap = (size_t)chunk;
+    ctx->items_done_cap = (size_t)chunk_max;
   }
   unsigned long long *counters = reinterpret_cast<unsigned long long *>(base);
   int *flags = reinterpret_cast<int *>(base + 16);
@@ -514,6 +531,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   a.ref_pmax = have_extrema ? ref->pmax : nullptr; a.ref_pmin = have_extrema ? ref->pmin : nullptr;
   a.qry_pmax = have_extrema ? qry->pmax : nullptr; a.qry_pmin = have_extrema ? qry->pmin : nullptr;
   a.p = p;
+  a.ncol_pad = ncol_pad;
   a.done = reinterpret_cast<int *>(base + head);
   a.scratch = reinterpret_cast<double *>(base + head + done_bytes);
   for (int64_t off = 0; off < n_pairs; off += chunk) {
@@ -525,10 +543,11 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     a.retry_cur = flags + par; a.retry_next = flags + (par ^ 1);
     int rc;
     const int hh = r1 ? 0 : H;
-    if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, stream);
-    else if (hh == 1) rc = chess_items_launch_h1(ctx, a, G, stream);
-    else if (hh == 2) rc = chess_items_launch_h2(ctx, a, G, stream);
-    else rc = chess_items_launch_h3(ctx, a, G, stream);
+    const bool multi = max_n > 31 * G;
+    if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, multi, stream);
+    else if (hh == 1) rc = chess_items_launch_h1(ctx, a, G, multi, stream);
+    else if (hh == 2) rc = chess_items_launch_h2(ctx, a, G, multi, stream);
+    else rc = chess_items_launch_h3(ctx, a, G, multi, stream);
     if (rc) return rc;
     ctx->items_parity ^= 1;
     // pairs the item kernel could not finish (unequal sizes, coincidentally masked column): the

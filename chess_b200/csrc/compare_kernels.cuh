@@ -85,19 +85,29 @@ struct Band2 {
 };
 
 // Per-lane view of the compacted pair: column offsets of the lane's G columns in both matrices.
-template <int G>
+template <int G, bool MULTI>
 struct LaneCols {
   unsigned xo[G], yo[G];   // element offsets inside a row of the reference / query view
-  bool valid[G];
+  bool valid[G];           // column exists (0 <= c < np): it is loaded and feeds the window sums
+  bool emit[G];            // column belongs to this column block: it produces outputs / totals
+  int cbase;               // compacted index of the lane's first column (negative in a left halo)
+  // single-block kernels (MULTI = false) emit every valid column: the compiler sees one predicate
+  __device__ __forceinline__ bool em(int g) const { return MULTI ? emit[g] : valid[g]; }
 };
 
-template <int G>
-__device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, int n, int np_, int flip,
-                                          int lane) {
+// Matrices wider than one warp's 31*G columns are swept in column blocks: a block starts three
+// columns before and ends three columns after the columns it emits, so the 7-column (2H+1-column)
+// sums of its own columns see real neighbours; the halo columns are loaded and summed but emit
+// nothing.  A matrix that fits one block has cstart = 0 and emits every column.
+template <int G, bool MULTI>
+__device__ __forceinline__ void lane_cols(LaneCols<G, MULTI> &lc, const short *kmap, int n, int np_, int flip,
+                                          int lane, int cstart, int estart, int eend) {
+  lc.cbase = cstart + G * lane;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const int c = G * lane + g;
-    lc.valid[g] = c < np_;
+    const int c = lc.cbase + g;
+    lc.valid[g] = c >= 0 && c < np_;
+    lc.emit[g] = MULTI ? (lc.valid[g] && c >= estart && c < eend) : lc.valid[g];
     const int kc = lc.valid[g] ? (int)kmap[c] : 0;
     lc.xo[g] = (unsigned)kc;
     lc.yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
@@ -107,10 +117,10 @@ __device__ __forceinline__ void lane_cols(LaneCols<G> &lc, const short *kmap, in
 // Loop A of pass 2: moments of x and y and min / max over the rows [lo, hi) of the band.
 // COLSUM additionally accumulates the lane's column sums over those rows (the item kernel uses
 // them to verify its predicted masks).
-template <int G, bool COLSUM, bool MINMAX>
+template <int G, bool COLSUM, bool MINMAX, bool MULTI>
 __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                              size_t rp, size_t qp, const short *kmap, int n, int flip,
-                                             int lo, int hi, const LaneCols<G> &lc, Band2 &acc,
+                                             int lo, int hi, const LaneCols<G, MULTI> &lc, Band2 &acc,
                                              double *cs_r, double *cs_q) {
   double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
   double vmax = -CUDART_INF, vmin = CUDART_INF;
@@ -124,7 +134,7 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       x[g] = 0.0; y[g] = 0.0;
-      if (lc.valid[g]) { x[g] = __ldg(R + (ro + lc.xo[g])); y[g] = __ldg(Q + (qo + lc.yo[g])); }
+      if (lc.em(g)) { x[g] = __ldg(R + (ro + lc.xo[g])); y[g] = __ldg(Q + (qo + lc.yo[g])); }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -136,8 +146,8 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
         const bool xgt = x[g] > y[g];
         const double hi2 = xgt ? x[g] : y[g];
         const double lo2 = xgt ? y[g] : x[g];
-        vmax = (lc.valid[g] & (hi2 > vmax)) ? hi2 : vmax;
-        vmin = (lc.valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+        vmax = (lc.em(g) & (hi2 > vmax)) ? hi2 : vmax;
+        vmin = (lc.em(g) & (lo2 < vmin)) ? lo2 : vmin;
       }
     }
   }
@@ -149,12 +159,12 @@ __device__ __forceinline__ void moments_rows(const double *__restrict__ R, const
 // 7-row column sums).
 // MOMENTS fuses loop A (without min / max) and the column sums into this loop, so the pair is read
 // once: used by the item kernel when the data range comes from the running-extrema arrays.
-template <int G, bool MOMENTS>
+template <int G, bool MOMENTS, bool MULTI>
 __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                         size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
-                                        int lo, int hi, int lane, const LaneCols<G> &lc, double *myring,
+                                        int lo, int hi, int lane, const LaneCols<G, MULTI> &lc, double *myring,
                                         int *susp, int *susp_n, Band2 &acc, double *cs_r, double *cs_q) {
-  const int c0 = G * lane;
+  const int c0 = lc.cbase;
   double ccnt[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -200,9 +210,11 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
     if (MOMENTS && rr >= lo && rr < hi) {  // the band's own rows (halo rows belong to the neighbours)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        T0 += xn[g]; T1 += yn[g];
-        T2 = fma(xn[g], xn[g], T2); T3 = fma(yn[g], yn[g], T3); T4 = fma(xn[g], yn[g], T4);
-        cs_r[g] += xn[g]; cs_q[g] += yn[g];
+        if (lc.em(g)) {
+          T0 += xn[g]; T1 += yn[g];
+          T2 = fma(xn[g], xn[g], T2); T3 = fma(yn[g], yn[g], T3); T4 = fma(xn[g], yn[g], T4);
+          cs_r[g] += xn[g]; cs_q[g] += yn[g];
+        }
       }
     }
     if (rr + 1 < last) fetch(rr + 1);
@@ -252,11 +264,11 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
         const double m2 = w2 * cnt;
         const double den = fma(-w1, w1, m2);
         // one-pass variance is trusted when var > 1e-6 * E[d^2] (and E[d^2] is not denormal-small)
-        const bool good = lc.valid[g] & (den > fma(m2, 1e-6, 1e-290));
+        const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290));
         const double gq = fabs(w1) * cnt * fast_rcp(den);
         sn_sum += good ? gq : 0.0;
         sn_cnt += good ? 1 : 0;
-        if (!good && lc.valid[g] && w2 != 0.0) {  // rare: cancellation -> exact recompute after the loop
+        if (!good && lc.em(g) && w2 != 0.0) {  // rare: cancellation -> exact recompute after the loop
           const int e = atomicAdd(susp_n, 1);
           if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
         }
@@ -279,16 +291,16 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
 //   * the band's own rows also feed the column sums that verify the predicted masks.
 // C1 / C2 need the data range before the first window: it comes from the running-extrema arrays
 // (or a min / max pre-loop when those cannot be used).
-template <int G, int H>
+template <int G, int H, bool MULTI>
 __device__ __forceinline__ void win_rows(const double *__restrict__ R, const double *__restrict__ Q,
                                          size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
-                                         int lo, int hi, int lane, const LaneCols<G> &lc, double *myring,
+                                         int lo, int hi, int lane, const LaneCols<G, MULTI> &lc, double *myring,
                                          int *susp, int *susp_n, bool with_sn, double C1, double C2,
                                          Band2 &acc, double &ssim_sum, double *cs_r, double *cs_q) {
   static_assert(H >= 1 && H <= 3 && G >= 3, "neighbour exchange covers at most 3 columns per side");
   constexpr int WIN = 2 * H + 1;
   constexpr int D = WIN > 7 ? WIN : 7;  // ring depth in rows
-  const int c0 = G * lane;
+  const int c0 = lc.cbase;
   const double inv_np = 1.0 / (double)(WIN * WIN);
   const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
   double ccnt[G];
@@ -332,7 +344,9 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
     for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
     if (rr >= lo && rr < hi) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
+      for (int g = 0; g < G; ++g) {
+        if (lc.em(g)) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
+      }
     }
     if (rr + 1 < last) fetch(rr + 1);
     // ring positions of the rows that leave the 7-row and the WIN-row windows
@@ -399,7 +413,7 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
         const double den = B1 * B2;
         double S = (A1 * A2) * fast_rcp(den);
         if (den == 0.0) S = (A1 * A2) / den;  // zero data range: IEEE 0/0 like the reference
-        if (c >= H && c <= np_ - 1 - H) ss_sum += S;
+        if (lc.em(g) && c >= H && c <= np_ - 1 - H) ss_sum += S;
       }
     }
 
@@ -433,11 +447,11 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
         const double cnt = rcnt * ccnt[g];
         const double m2 = w2 * cnt;
         const double den = fma(-w1, w1, m2);
-        const bool good = lc.valid[g] & (den > fma(m2, 1e-6, 1e-290));
+        const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290));
         const double gq = fabs(w1) * cnt * fast_rcp(den);
         sn_sum += good ? gq : 0.0;
         sn_cnt += good ? 1 : 0;
-        if (!good && lc.valid[g] && w2 != 0.0) {
+        if (!good && lc.em(g) && w2 != 0.0) {
           const int e = atomicAdd(susp_n, 1);
           if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
         }
@@ -516,24 +530,25 @@ __device__ __forceinline__ void finish_pair(const double *t, double mx, double m
 
 // H = 0: the -r 1 regime (window = whole matrix); H = 1..3: windowed regime with window 2H+1,
 // where WITH_SN is ignored and a.p.compute_sn decides at run time.
-template <int G, bool WITH_SN, int H>
+// MULTI = true sweeps matrices wider than 31*G columns in column blocks (n <= 1024).
+template <int G, bool WITH_SN, int H, bool MULTI>
 __global__ void __launch_bounds__(128, (G <= 4 ? (H == 0 ? 4 : 3) : 2))
 compare_r1_items_kernel(chess_item_args a) {
-  constexpr int NCOL = 32 * G;
-  constexpr int STRIDE = kItemHdr + 2 * NCOL;
-  __shared__ short s_kmap[4][NCOL];
-  __shared__ unsigned char s_mflag[4][NCOL];
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
   extern __shared__ __align__(16) double ringbuf[];  // per warp: 7*G*32 doubles (d), or D*2G*32 (x, y)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  short *kmap = s_kmap[warp];
-  unsigned char *mflag = s_mflag[warp];
   int *susp = s_susp[warp];
   int *susp_n = &s_susp_n[warp];
   constexpr int RING = H == 0 ? 7 * G * 32 : (2 * H + 1 > 7 ? 2 * H + 1 : 7) * 2 * G * 32;
   double *myring = ringbuf + (size_t)warp * RING + lane;
+  // behind the rings: per warp, the compaction map and the mask flags of the current pair
+  const int NCOL = a.ncol_pad;
+  const size_t STRIDE = (size_t)kItemHdr + 2 * (size_t)NCOL;
+  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
+  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) +
+                                                          (size_t)4 * NCOL) + (size_t)warp * NCOL;
   const bool with_sn = H == 0 ? WITH_SN : a.p.compute_sn != 0;
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
@@ -552,7 +567,7 @@ compare_r1_items_kernel(chess_item_args a) {
     int status = CHESS_PAIR_OK;
     if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
     else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
-    else if (d.ref_n != d.qry_n || d.ref_n > 31 * G) status = CHESS_PAIR_RETRY;
+    else if (d.ref_n != d.qry_n || d.ref_n > (MULTI ? NCOL : 31 * G)) status = CHESS_PAIR_RETRY;
     if (status != CHESS_PAIR_OK) {
       if (band == 0 && lane == 0) {
         a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = status;
@@ -619,43 +634,7 @@ compare_r1_items_kernel(chess_item_args a) {
     // ---- this band
     const int B2 = (np_ + kBands - 1) / kBands;
     const int lo = band * B2, hi = min(np_, lo + B2);
-    LaneCols<G> lc;
-    lane_cols<G>(lc, kmap, n, np_, flip, lane);
-    Band2 acc;
-    acc.T0 = acc.T1 = acc.T2 = acc.T3 = acc.T4 = 0.0;
-    acc.vmax = -CUDART_INF; acc.vmin = CUDART_INF; acc.sn_sum = 0.0; acc.sn_cnt = 0;
-    double cs_r[G], cs_q[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; }
-    double rt[5] = {0, 0, 0, 0, 0};
-    if (H == 0 && m == 2 && (band == 0 || band == kBands - 1)) {  // first / last row totals for the 2x2 SSIM map
-      const int kr = kmap[band == 0 ? 0 : np_ - 1];
-      const double *rowR = R + (size_t)kr * rp;
-      const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (lc.valid[g]) {
-          const double x = __ldg(rowR + lc.xo[g]), y = __ldg(rowQ + lc.yo[g]);
-          rt[0] += x; rt[1] += y; rt[2] = fma(x, x, rt[2]); rt[3] = fma(y, y, rt[3]); rt[4] = fma(x, y, rt[4]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) rt[k] = warp_sum(rt[k]);
-    }
-    if (use_masks && band == 0 && np_ < n) {
-      // the column sums must cover all n rows of the uncompacted matrices: band 0 adds the few
-      // removed rows (a row removed because of the *other* matrix is not all-default in this one)
-      for (int r = 0; r < n; ++r) {
-        if (mflag[r] != 0) {
-          const double *rowR = R + (size_t)r * rp;
-          const double *rowQ = Q + (size_t)(flip ? n - 1 - r : r) * qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (lc.valid[g]) { cs_r[g] += __ldg(rowR + lc.xo[g]); cs_q[g] += __ldg(rowQ + lc.yo[g]); }
-          }
-        }
-      }
-    }
+    double *rec = a.scratch + ((size_t)pi * kBands + band) * STRIDE;
     // data range: n lookups in the running-extrema arrays give max / min of the uncompacted pair.
     // They are also the extrema of the compacted pair if every removed cell holds the default value
     // in both matrices (bins masked in one matrix only are removed from the other, where they carry
@@ -673,63 +652,137 @@ compare_r1_items_kernel(chess_item_args a) {
       xmin = warp_min(xmin);
       inloop_minmax = np_ < n && (tot_one_sided > 0 || !(xmax > p.default_value && xmin < p.default_value));
     }
+    // column blocks: one if the compacted matrix fits the warp (np <= 31*G), else blocks that emit
+    // 31*G - 6 columns each and carry three halo columns either side
+    constexpr int CAP = 31 * G;
+    const int SPAN = (!MULTI || np_ <= CAP) ? np_ : CAP - 6;
+    const int nblk = (!MULTI || np_ <= CAP) ? 1 : (np_ + SPAN - 1) / SPAN;
+    Band2 acc;
+    acc.T0 = acc.T1 = acc.T2 = acc.T3 = acc.T4 = 0.0;
+    acc.vmax = -CUDART_INF; acc.vmin = CUDART_INF; acc.sn_sum = 0.0; acc.sn_cnt = 0;
+    double rt[5] = {0, 0, 0, 0, 0};
     double ssim_sum = 0.0;
-    if (lo < hi) {
-      if (H > 0) {
-        if (inloop_minmax) {  // the range must be complete before the first window: both bands scan the pair
-          Band2 mm;
-          moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, 0, np_, lc, mm, nullptr, nullptr);
-          xmax = warp_max(mm.vmax); xmin = warp_min(mm.vmin);
-        }
-        const double drange = xmax - xmin;
-        const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
-        win_rows<G, (H > 0 ? H : 1)>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n,
-                                     with_sn, C1, C2, acc, ssim_sum, cs_r, cs_q);
-      } else if (WITH_SN) {
-        if (inloop_minmax) {
-          Band2 mm;
-          moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, nullptr, nullptr);
-          xmax = mm.vmax; xmin = mm.vmin;
-        }
-        sn_rows<G, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, acc, cs_r,
-                         cs_q);
-      } else {
+    if (H > 0 && inloop_minmax && lo < hi) {
+      // the range must be complete before the first window: every band scans the whole pair
+      double bmax = -CUDART_INF, bmin = CUDART_INF;
+      for (int blk = 0; blk < nblk; ++blk) {
+        LaneCols<G, MULTI> lc;
+        lane_cols<G, MULTI>(lc, kmap, n, np_, flip, lane, blk * SPAN, blk * SPAN, min(np_, (blk + 1) * SPAN));
         Band2 mm;
-        if (inloop_minmax) {
-          moments_rows<G, true, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
-          xmax = mm.vmax; xmin = mm.vmin;
-        } else {
-          moments_rows<G, true, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
-        }
-        acc.T0 = mm.T0; acc.T1 = mm.T1; acc.T2 = mm.T2; acc.T3 = mm.T3; acc.T4 = mm.T4;
+        moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, 0, np_, lc, mm, nullptr, nullptr);
+        bmax = fmax(bmax, mm.vmax); bmin = fmin(bmin, mm.vmin);
       }
-      if (with_sn) {
-        __syncwarp();
-        const int ns = *susp_n;
-        if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
-          for (int e = lane; e < ns; e += 32) {
-            const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
-            const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
-                                        (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
-            const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
-            if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
+      xmax = warp_max(bmax); xmin = warp_min(bmin);
+    } else if (inloop_minmax) {
+      xmax = -CUDART_INF; xmin = CUDART_INF;
+    }
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int estart = blk * SPAN, eend = min(np_, estart + SPAN);
+      const int cstart = nblk == 1 ? 0 : estart - 3;
+      LaneCols<G, MULTI> lc;
+      lane_cols<G, MULTI>(lc, kmap, n, np_, flip, lane, cstart, estart, eend);
+      Band2 part;
+      part.T0 = part.T1 = part.T2 = part.T3 = part.T4 = 0.0;
+      part.vmax = -CUDART_INF; part.vmin = CUDART_INF; part.sn_sum = 0.0; part.sn_cnt = 0;
+      double cs_r[G], cs_q[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) { cs_r[g] = 0.0; cs_q[g] = 0.0; }
+      if (H == 0 && m == 2 && (band == 0 || band == kBands - 1)) {  // first / last row totals (2x2 SSIM map)
+        const int kr = kmap[band == 0 ? 0 : np_ - 1];
+        const double *rowR = R + (size_t)kr * rp;
+        const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+        double t5[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (lc.em(g)) {
+            const double x = __ldg(rowR + lc.xo[g]), y = __ldg(rowQ + lc.yo[g]);
+            t5[0] += x; t5[1] += y; t5[2] = fma(x, x, t5[2]); t5[3] = fma(y, y, t5[3]); t5[4] = fma(x, y, t5[4]);
           }
-        } else if (ns > kSuspCap) {  // list overflow: redo the whole band exactly
-          acc.sn_sum = 0.0; acc.sn_cnt = 0;
-          for (int rc = lo; rc < hi; ++rc) {
-            for (int c = lane; c < np_; c += 32) {
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rt[k] += warp_sum(t5[k]);
+      }
+      if (use_masks && band == 0 && np_ < n) {
+        // the column sums must cover all n rows of the uncompacted matrices: band 0 adds the few
+        // removed rows (a row removed because of the *other* matrix is not all-default in this one)
+        for (int r = 0; r < n; ++r) {
+          if (mflag[r] != 0) {
+            const double *rowR = R + (size_t)r * rp;
+            const double *rowQ = Q + (size_t)(flip ? n - 1 - r : r) * qp;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (lc.em(g)) { cs_r[g] += __ldg(rowR + lc.xo[g]); cs_q[g] += __ldg(rowQ + lc.yo[g]); }
+            }
+          }
+        }
+      }
+      if (lo < hi) {
+        if (lane == 0) *susp_n = 0;
+        __syncwarp();
+        double ssum_blk = 0.0;
+        if (H > 0) {
+          const double drange = xmax - xmin;
+          const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
+          win_rows<G, (H > 0 ? H : 1)>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n,
+                                       with_sn, C1, C2, part, ssum_blk, cs_r, cs_q);
+          ssim_sum += ssum_blk;
+        } else if (WITH_SN) {
+          if (inloop_minmax) {
+            Band2 mm;
+            moments_rows<G, false, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, nullptr, nullptr);
+            xmax = fmax(xmax, mm.vmax); xmin = fmin(xmin, mm.vmin);
+          }
+          sn_rows<G, true>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, part, cs_r,
+                           cs_q);
+        } else {
+          Band2 mm;
+          if (inloop_minmax) {
+            moments_rows<G, true, true>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+            xmax = fmax(xmax, mm.vmax); xmin = fmin(xmin, mm.vmin);
+          } else {
+            moments_rows<G, true, false>(R, Q, rp, qp, kmap, n, flip, lo, hi, lc, mm, cs_r, cs_q);
+          }
+          part.T0 = mm.T0; part.T1 = mm.T1; part.T2 = mm.T2; part.T3 = mm.T3; part.T4 = mm.T4;
+        }
+        if (with_sn) {
+          __syncwarp();
+          const int ns = *susp_n;
+          if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
+            for (int e = lane; e < ns; e += 32) {
+              const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
               const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
                                           (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
               const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
-              if (gq == gq) { acc.sn_sum += gq; acc.sn_cnt += 1; }
+              if (gq == gq) { part.sn_sum += gq; part.sn_cnt += 1; }
             }
+          } else if (ns > kSuspCap) {  // list overflow: redo this block of the band exactly
+            part.sn_sum = 0.0; part.sn_cnt = 0;
+            for (int rc = lo; rc < hi; ++rc) {
+              for (int c = estart + lane; c < eend; c += 32) {
+                const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                            (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+                const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+                if (gq == gq) { part.sn_sum += gq; part.sn_cnt += 1; }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      acc.T0 += part.T0; acc.T1 += part.T1; acc.T2 += part.T2; acc.T3 += part.T3; acc.T4 += part.T4;
+      acc.sn_sum += part.sn_sum; acc.sn_cnt += part.sn_cnt;
+      if (use_masks) {  // this band's share of the column sums of the block's own columns
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (lc.em(g)) {
+            rec[kItemHdr + lc.cbase + g] = cs_r[g];
+            rec[kItemHdr + NCOL + lc.cbase + g] = cs_q[g];
           }
         }
       }
     }
     acc.vmax = xmax; acc.vmin = xmin;
     // ---- partial record of this band
-    double *rec = a.scratch + ((size_t)pi * kBands + band) * STRIDE;
     {
       const double T0 = warp_sum(acc.T0), T1 = warp_sum(acc.T1), T2 = warp_sum(acc.T2);
       const double T3 = warp_sum(acc.T3), T4 = warp_sum(acc.T4);
@@ -746,13 +799,6 @@ compare_r1_items_kernel(chess_item_args a) {
         const double sw = warp_sum(ssim_sum);
         if (lane == 0) rec[14] = sw;
       }
-      if (use_masks) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          rec[kItemHdr + G * lane + g] = cs_r[g];
-          rec[kItemHdr + NCOL + G * lane + g] = cs_q[g];
-        }
-      }
     }
     __threadfence();
     __syncwarp();
@@ -767,28 +813,24 @@ compare_r1_items_kernel(chess_item_args a) {
     bool bad = false;
     if (use_masks) {
       const double target = (double)n * p.default_value;
+      for (int c = lane; c < np_; c += 32) {
+        double sr = 0.0, sq = 0.0;
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int c = G * lane + g;
-        if (c < np_) {
-          double sr = 0.0, sq = 0.0;
-#pragma unroll
-          for (int b = 0; b < kBands; ++b) {
-            sr += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + c);
-            sq += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + NCOL + c);
-          }
-          const int kc = kmap[c];
-          if (!(mflag[kc] & 1) && fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
-            double s2 = 0.0;  // the reference's own order: rows 0 .. n-1 of the uncompacted matrix
-            for (int r = 0; r < n; ++r) s2 += __ldg(R + (size_t)r * rp + kc);
-            bad |= s2 == target;
-          }
-          if (!(mflag[kc] & 2) && fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
-            double s2 = 0.0;
-            const int cq = flip ? n - 1 - kc : kc;
-            for (int r = 0; r < n; ++r) s2 += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
-            bad |= s2 == target;
-          }
+        for (int b = 0; b < kBands; ++b) {
+          sr += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + c);
+          sq += __ldcg(recs + (size_t)b * STRIDE + kItemHdr + NCOL + c);
+        }
+        const int kc = kmap[c];
+        if (!(mflag[kc] & 1) && fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
+          double s2 = 0.0;  // the reference's own order: rows 0 .. n-1 of the uncompacted matrix
+          for (int r = 0; r < n; ++r) s2 += __ldg(R + (size_t)r * rp + kc);
+          bad |= s2 == target;
+        }
+        if (!(mflag[kc] & 2) && fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
+          double s2 = 0.0;
+          const int cq = flip ? n - 1 - kc : kc;
+          for (int r = 0; r < n; ++r) s2 += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
+          bad |= s2 == target;
         }
       }
       bad = __any_sync(0xffffffffu, bad);
@@ -828,20 +870,23 @@ compare_r1_items_kernel(chess_item_args a) {
   }
 }
 
-template <int G, bool WITH_SN, int H>
+template <int G, bool WITH_SN, int H, bool MULTI>
 int launch_items_sn(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  auto kern = compare_r1_items_kernel<G, WITH_SN, H>;
+  auto kern = compare_r1_items_kernel<G, WITH_SN, H, MULTI>;
   constexpr int RING = H == 0 ? 7 * G * 32 : (2 * H + 1 > 7 ? 2 * H + 1 : 7) * 2 * G * 32;
-  const size_t smem = (H == 0 && !WITH_SN) ? 0 : (size_t)4 * RING * sizeof(double);
+  // rings (always reserved: the kernel addresses the maps behind them) + per-warp map and flags
+  const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
+  const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 1024 * 3;
   static bool configured = false;
-  if (!configured && smem > 0) {
-    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!configured) {
+    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
-  static int per_sm = 0;
-  if (per_sm == 0) {
+  static int per_sm = 0, per_sm_ncol = -1;  // the occupancy query costs microseconds of host time per call
+  if (per_sm_ncol != a.ncol_pad) {
     CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
     if (per_sm < 1) per_sm = 1;
+    per_sm_ncol = a.ncol_pad;
   }
   long long grid = (long long)ctx->sm_count * per_sm;
   const long long need = (a.n_pairs * kBands + 3) / 4;

@@ -369,8 +369,9 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
                 np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
     # windows of 40..200 bins exercise every column-strip width of the tuned kernel
     from chess_b200 import synth
-    for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000):
-        plist = synth.sliding_pairs(genome, window_bp, 900000)
+    # ... and 300 / 400 / 640 bins are swept in two or three column blocks
+    for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000, 7500000, 10000000, 16000000):
+        plist = synth.sliding_pairs(genome, window_bp, 900000 if window_bp <= 5000000 else 2900000)
         for kw in (dict(), dict(absolute_window_size=7)):
             gen = eng.compare(plist, kernel=1, **kw)
             for kernel in (0, 2):
