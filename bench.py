@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--workload", default="chr2_25kb", choices=["chr2_25kb", "hg38_10kb"],
                     help="chr2_25kb = BASELINE configs[1] (the contract's bench line); hg38_10kb = configs[2], "
                          "genome-wide 10 kb, ~100k pairs of 2 Mb, pairs sharded over the ranks (strong scaling)")
+    ap.add_argument("--bin-size", type=int, default=BIN, help="chr2 workload only: bin size in bp")
+    ap.add_argument("--window-bp", type=int, default=WINDOW_BP, help="chr2 workload only: region size in bp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 auto, 1 force the generic kernel, 2 the CTA-per-pair tuned kernel")
@@ -68,7 +70,7 @@ def window_params(tag):
     return dict(absolute_window_size=7) if tag == "a7" else dict()
 
 
-def make_workload(rank, workload="chr2_25kb", world=1):
+def make_workload(rank, workload="chr2_25kb", world=1, bin_size=BIN, window_bp=WINDOW_BP):
     """Synthetic sample pair and the sliding pair list.
 
     chr2_25kb: every rank gets its own chr2-sized samples (seeded by rank) and the full pair list.
@@ -82,10 +84,11 @@ def make_workload(rank, workload="chr2_25kb", world=1):
         pairs = synth.sliding_pairs(genome, WINDOW_BP, 30000)
         lo, hi = my_shard(len(pairs), rank, world)
         return genome, ref, qry, pairs[lo:hi]
-    genome = synth.Genome(synth.chromosome_bins([("chr2", CHR2_BP)], BIN), BIN, [("chr2", CHR2_BP)])
-    ref = synth.synthetic_sample(genome, 100, seed=100 + 2 * rank, structure_seed=7 + rank)
-    qry = synth.synthetic_sample(genome, 100, seed=101 + 2 * rank, structure_seed=7 + rank, perturb=0.1)
-    pairs = synth.sliding_pairs(genome, WINDOW_BP, STEP_BP)
+    genome = synth.Genome(synth.chromosome_bins([("chr2", CHR2_BP)], bin_size), bin_size, [("chr2", CHR2_BP)])
+    band = max(100, window_bp // bin_size + 20)
+    ref = synth.synthetic_sample(genome, band, seed=100 + 2 * rank, structure_seed=7 + rank)
+    qry = synth.synthetic_sample(genome, band, seed=101 + 2 * rank, structure_seed=7 + rank, perturb=0.1)
+    pairs = synth.sliding_pairs(genome, window_bp, STEP_BP)
     return genome, ref, qry, pairs
 
 
@@ -191,7 +194,10 @@ def cpu_subset(genome, ref, qry, pairs, max_bins=12000):
     first = genome.names[0]
     sub = synth.Genome([(first, max_bins)], genome.bin_size, [(first, limit_bp)])
     keep = lambda s: tuple(a[(s[1] < max_bins)] for a in s)  # noqa: E731  (src <= sink)
-    pairs = [p for p in pairs if p[1].chromosome == first and p[1].end <= limit_bp and p[2].end <= limit_bp]
+    # strictly inside: a region ending on the last bin boundary would also touch the next bin
+    # (the BED lookup of chess/helpers.py:212-237), which the subset does not have
+    inside = limit_bp - genome.bin_size
+    pairs = [p for p in pairs if p[1].chromosome == first and p[1].end <= inside and p[2].end <= inside]
     return sub, keep(ref), keep(qry), pairs
 
 
@@ -216,7 +222,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
-    genome, ref, qry, pairs = make_workload(0, args.workload, 1)
+    genome, ref, qry, pairs = make_workload(0, args.workload, 1, args.bin_size, args.window_bp)
     genome, ref, qry, pairs = cpu_subset(genome, ref, qry, pairs)
     cpu_setup(genome, ref, qry, pairs, args.window)
     cores = os.cpu_count() or 1
@@ -251,10 +257,15 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_pairs, n_bins, sample=None):
-    what = ("configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb" if args.workload == "chr2_25kb"
-            else "configs[2]: human hg38 @ 10 kb genome-wide (%d bins), 2 Mb windows step 30 kb") % n_bins
+    if args.workload == "chr2_25kb" and (args.bin_size != BIN or args.window_bp != WINDOW_BP):
+        what = "human chr2 @ %g kb (%d bins), %g Mb windows step 100 kb" % (args.bin_size / 1e3, n_bins,
+                                                                              args.window_bp / 1e6)
+    else:
+        what = ("configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb" if args.workload == "chr2_25kb"
+                else "configs[2]: human hg38 @ 10 kb genome-wide (%d bins), 2 Mb windows step 30 kb") % n_bins
     cfg = {"workload": "%s, chess sim %s, SN on" % (what, "-r 1 (default)" if args.window == "r1" else "-a 7"),
-           "pairs_per_gpu": n_pairs, "bins_per_pair": 81 if args.workload == "chr2_25kb" else 201,
+           "pairs_per_gpu": n_pairs,
+           "bins_per_pair": args.window_bp // args.bin_size + 1 if args.workload == "chr2_25kb" else 201,
            "window": args.window,
            "l2": "flushed before every step (512 MiB write)",
            "parallelism": "pairs sharded, one process per GPU, no collective"}
@@ -278,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    genome, ref, qry, pairs = make_workload(rank, args.workload, world)
+    genome, ref, qry, pairs = make_workload(rank, args.workload, world, args.bin_size, args.window_bp)
     regions = genome.regions()
     trees = cb.region_interval_trees(regions)
     params = window_params(args.window)
