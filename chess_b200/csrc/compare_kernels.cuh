@@ -411,8 +411,9 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
         const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
         const double B1 = fma(ux, ux, fma(uy, uy, C1)), B2 = vx + vy + C2;
         const double den = B1 * B2;
-        double S = (A1 * A2) * fast_rcp(den);
-        if (den == 0.0) S = (A1 * A2) / den;  // zero data range: IEEE 0/0 like the reference
+        const double num = A1 * A2;
+        double S = num * fast_rcp(den);
+        if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
         if (lc.em(g) && c >= H && c <= np_ - 1 - H) ss_sum += S;
       }
     }
@@ -454,6 +455,157 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
         if (!good && lc.em(g) && w2 != 0.0) {
           const int e = atomicAdd(susp_n, 1);
           if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
+        }
+      }
+    }
+  }
+  acc.sn_sum = sn_sum;
+  acc.sn_cnt = sn_cnt;
+  ssim_sum = ss_sum;
+}
+
+// Window 7 (-a 7) is also the SN window, so one set of sums serves both: running 7-row column
+// sums of x, y, q = xx + yy and xy (the SSIM formula needs the two variances only as a sum), four
+// quantities through the neighbour exchange instead of seven, and
+//     sum d = Wx - Wy,   sum d*d = Wq - 2 Wxy.
+// An all-zero difference window must give exactly 0 for sum d*d (0/0 -> NaN -> skipped): a column
+// whose last seven rows all have x == y is snapped to Vy = Vx and Vq = 2 Vxy, and doubling commutes
+// with every rounding in the prefix / suffix arithmetic, so Wq - 2 Wxy cancels exactly.  Windows
+// where the subtraction loses more than ~6 digits (sum d*d < 1e-6 sum q) go to the exact recompute.
+template <int G, bool MULTI>
+__device__ __forceinline__ void win7_rows(const double *__restrict__ R, const double *__restrict__ Q,
+                                          size_t rp, size_t qp, const short *kmap, int n, int np_, int flip,
+                                          int lo, int hi, int lane, const LaneCols<G, MULTI> &lc,
+                                          double *myring, int *susp, int *susp_n, bool with_sn, double C1,
+                                          double C2, Band2 &acc, double &ssim_sum, double *cs_r,
+                                          double *cs_q) {
+  constexpr int H = 3, D = 7;
+  const int c0 = lc.cbase;
+  const double inv_np = 1.0 / 49.0;
+  const double cov_norm = 49.0 / 48.0;
+  double ccnt[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int c = c0 + g;
+    ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+  }
+  double sn_sum = 0.0, ss_sum = 0.0;
+  int sn_cnt = 0;
+  double Vx[G], Vy[G], Vq[G], Vxy[G];
+  unsigned hist[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    Vx[g] = Vy[g] = Vq[g] = Vxy[g] = 0.0;
+    hist[g] = 0u;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+  }
+  const int first = lo - 3, last = hi + 3;  // exclusive
+  const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+  int slot = 0;
+  double xn[G], yn[G];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
+    if (row >= 0 && row < np_) {
+      const unsigned kr = (unsigned)kmap[row];
+      const unsigned ro = kr * (unsigned)rp;
+      const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (lc.valid[g]) { xn[g] = __ldg(R + (ro + lc.xo[g])); yn[g] = __ldg(Q + (qo + lc.yo[g])); }
+      }
+    }
+  };
+  fetch(first);
+  for (int rr = first; rr < last; ++rr) {
+    double x[G], y[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
+    if (rr >= lo && rr < hi) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (lc.em(g)) { cs_r[g] += x[g]; cs_q[g] += y[g]; }
+      }
+    }
+    if (rr + 1 < last) fetch(rr + 1);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      double *cell = myring + ((slot * G + g) * 2) * 32;   // the slot being overwritten holds row rr - 7
+      const double xo = cell[0], yo = cell[32];
+      cell[0] = x[g];
+      cell[32] = y[g];
+      Vx[g] += x[g]; Vx[g] -= xo;
+      Vy[g] += y[g]; Vy[g] -= yo;
+      Vq[g] = fma(x[g], x[g], fma(y[g], y[g], Vq[g]));
+      Vq[g] = fma(-xo, xo, fma(-yo, yo, Vq[g]));
+      Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xo, yo, Vxy[g]);
+      hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
+      if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
+    }
+    slot = slot == D - 1 ? 0 : slot + 1;
+
+    const int rc = rr - 3;   // centre row of the SSIM window and SN pixel row
+    if (rc >= lo && rc < hi) {
+      const bool ssim_row = rc >= H && rc <= np_ - 1 - H;
+      double W4[4][G];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vq : Vxy;
+        double P[G + 1];
+        P[0] = 0.0; P[1] = V[0];
+#pragma unroll
+        for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
+        double up[3], dn[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
+          up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
+          dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int a = g - 3 < 0 ? 0 : g - 3;
+          const int b = g + 3 > G - 1 ? G - 1 : g + 3;
+          double w = a == 0 ? P[b + 1] : P[b + 1] - P[a];
+          if (g - 3 < 0) w += up[2 - g];
+          if (g + 3 > G - 1) w += dn[g + 3 - G];
+          W4[q][g] = w;
+        }
+      }
+      const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = c0 + g;
+        if (ssim_row) {
+          const double ux = W4[0][g] * inv_np, uy = W4[1][g] * inv_np;
+          const double uq = W4[2][g] * inv_np, uxy = W4[3][g] * inv_np;
+          const double m2s = fma(ux, ux, uy * uy);                  // ux^2 + uy^2
+          const double vsum = cov_norm * (uq - m2s);                // vx + vy
+          const double vxy = cov_norm * fma(-ux, uy, uxy);
+          const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
+          const double B1 = m2s + C1, B2 = vsum + C2;
+          const double den = B1 * B2;
+          const double num = A1 * A2;
+          double S = num * fast_rcp(den);
+          if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
+          if (lc.em(g) && c >= H && c <= np_ - 1 - H) ss_sum += S;
+        }
+        if (with_sn) {
+          const double w1 = W4[0][g] - W4[1][g];
+          const double w2 = fma(-2.0, W4[3][g], W4[2][g]);
+          const double cnt = rcnt * ccnt[g];
+          const double m2 = w2 * cnt;
+          const double den = fma(-w1, w1, m2);
+          // trusted: one-pass variance well conditioned AND the q - 2xy subtraction kept >= 10 digits
+          const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
+          const double gq = fabs(w1) * cnt * fast_rcp(den);
+          sn_sum += good ? gq : 0.0;
+          sn_cnt += good ? 1 : 0;
+          if (!good && lc.em(g) && w2 != 0.0) {
+            const int e = atomicAdd(susp_n, 1);
+            if (e < kSuspCap) susp[e] = (rc << 16) | (c0 + g);
+          }
         }
       }
     }
@@ -723,8 +875,12 @@ compare_r1_items_kernel(chess_item_args a) {
         if (H > 0) {
           const double drange = xmax - xmin;
           const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
-          win_rows<G, (H > 0 ? H : 1)>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n,
-                                       with_sn, C1, C2, part, ssum_blk, cs_r, cs_q);
+          if (H == 3)
+            win7_rows<G>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring, susp, susp_n, with_sn, C1,
+                         C2, part, ssum_blk, cs_r, cs_q);
+          else
+            win_rows<G, (H == 1 || H == 2 ? H : 1)>(R, Q, rp, qp, kmap, n, np_, flip, lo, hi, lane, lc, myring,
+                                                    susp, susp_n, with_sn, C1, C2, part, ssum_blk, cs_r, cs_q);
           ssim_sum += ssum_blk;
         } else if (WITH_SN) {
           if (inloop_minmax) {
