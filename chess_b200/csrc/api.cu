@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(1024) zscore_kernel(const double *__restrict__
   __shared__ double red[3][33];
   __shared__ double pivot_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cudaGridDependencySynchronize();  // launched early (programmatic serialisation): wait for the producer
   if (threadIdx.x == 0) {
     double pv = 0.0;
     for (long long i = 0; i < n; ++i) {
@@ -251,7 +252,16 @@ extern "C" int chess_zscore(chess_ctx *ctx, const double *ssim, int64_t n, doubl
   if (n == 0) return CHESS_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
-  zscore_kernel<<<1, 1024, 0, stream>>>(ssim, (long long)n, z);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CHESS_CUDA(ctx, cudaLaunchKernelEx(&cfg, zscore_kernel, ssim, (long long)n, z));
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
