@@ -1,5 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --no-cpu-baseline > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; tail -c 300 gpurun_out/bench_tmp.err
+python bench.py --no-cpu-baseline --no-genome-wide --steps 50 --warmup 5 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; tail -c 300 gpurun_out/bench_tmp.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_tmp.json").read().strip().splitlines()[-1])
