@@ -512,3 +512,37 @@ def test_zscore_kernel(cb):
                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), ctx.handle)
     want = (s - np.nanmean(s)) / np.nanstd(s)
     np.testing.assert_allclose(z.cpu().numpy(), want, rtol=1e-10, equal_nan=True)
+
+
+def test_full_size_chr2_properties(cb):
+    """BASELINE configs[1] at full size (9 688 bins, 2 402 pairs): size-independent properties."""
+    import bench
+    genome, ref, qry, pairs = bench.make_workload(0)
+    assert genome.n_bins == 9688 and len(pairs) == 2402
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    re_ = cb.observed_expected_arrays(regions, ref)
+    qe = cb.observed_expected_arrays(regions, qry)
+    fwd = cb.CompareEngine(re_, trees, qe, trees)
+    rev = cb.CompareEngine(qe, trees, re_, trees)
+    for kw in (dict(), dict(absolute_window_size=7)):
+        ids, s, sn, st = fwd.compare(pairs, **kw)
+        assert ids == [p[0] for p in pairs] and (st == 0).sum() > 2000
+        # two implementations of the same function agree on every pair
+        _, s_g, sn_g, st_g = fwd.compare(pairs, kernel=1, **kw)
+        assert np.array_equal(st, st_g)
+        np.testing.assert_allclose(s, s_g, rtol=1e-9, equal_nan=True)
+        np.testing.assert_allclose(sn, sn_g, rtol=1e-9, equal_nan=True)
+        # SSIM and SN are symmetric in (reference, query)
+        _, s_r, sn_r, st_r = rev.compare(pairs, **kw)
+        assert np.array_equal(st, st_r)
+        np.testing.assert_allclose(s, s_r, rtol=1e-10, equal_nan=True)
+        np.testing.assert_allclose(sn, sn_r, rtol=1e-10, equal_nan=True)
+        # results do not depend on how the pair list is cut into launches
+        cut = [fwd.compare(pairs[lo:lo + 517], **kw) for lo in range(0, len(pairs), 517)]
+        assert np.array_equal(np.concatenate([c[1] for c in cut]), s, equal_nan=True)
+        assert np.array_equal(np.concatenate([c[2] for c in cut]), sn, equal_nan=True)
+        # SSIM is bounded, SN non-negative, failures are NaN in both columns
+        ok = st == 0
+        assert np.all(np.abs(s[ok]) <= 1.0 + 1e-12) and np.all(sn[ok] >= 0)
+        assert np.all(np.isnan(s[~ok])) and np.all(np.isnan(sn[~ok]))
