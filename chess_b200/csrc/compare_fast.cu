@@ -250,6 +250,16 @@ compare_r1_kernel(const double *__restrict__ ref_base, const double *__restrict_
         __syncwarp();
         const int ns = susp_n[warp];
         if (ns > 0 && ns <= kSuspCap) {
+          // sort the queued codes (arrival order is not reproducible; the addition order must be)
+          if (lane == 0) {
+            for (int i2 = 1; i2 < ns; ++i2) {
+              const int key = susp[warp][i2];
+              int j2 = i2 - 1;
+              while (j2 >= 0 && susp[warp][j2] > key) { susp[warp][j2 + 1] = susp[warp][j2]; --j2; }
+              susp[warp][j2 + 1] = key;
+            }
+          }
+          __syncwarp();
           for (int e = lane; e < ns; e += 32) {
             const int rc = susp[warp][e] >> 16, c = susp[warp][e] & 0xffff;
             const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *

@@ -904,6 +904,17 @@ compare_r1_items_kernel(chess_item_args a) {
           __syncwarp();
           const int ns = *susp_n;
           if (ns > 0 && ns <= kSuspCap) {  // cold: cancelled one-pass variances -> numpy's two passes
+            // the queue was filled in arrival order: sort the (at most 24) codes first so that the
+            // lane an entry lands on, and with it the order of the additions, is reproducible
+            if (lane == 0) {
+              for (int i = 1; i < ns; ++i) {
+                const int key = susp[i];
+                int j = i - 1;
+                while (j >= 0 && susp[j] > key) { susp[j + 1] = susp[j]; --j; }
+                susp[j + 1] = key;
+              }
+            }
+            __syncwarp();
             for (int e = lane; e < ns; e += 32) {
               const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
               const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
