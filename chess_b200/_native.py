@@ -88,6 +88,8 @@ SIGNATURES = {
     "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "chess_background_batch": (C.c_int, [_vp, _SP, _SP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _PP,
+                                         _vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library disagree

@@ -16,8 +16,6 @@ from . import commands
 
 logger = logging.getLogger('')
 
-# comparisons per engine call in background mode (bounds host memory for the pair table)
-BACKGROUND_BATCH = 2_000_000
 
 
 class Chess(object):
@@ -98,7 +96,6 @@ def _background_regions_from_query(query_regions, query_region, limit_background
 
 def run_sim(args):
     """Body of `chess sim` (bin/chess:80-359) on the batched engine."""
-    import warnings
     from .engine import CompareEngine, region_spans, visible_devices
     from .helpers import load_pairs_for_chroms, load_regions, load_contacts, load_oe_contacts
 
@@ -180,64 +177,39 @@ def run_sim(args):
         z_bg = np.full(len(pairs), np.nan)
         p_bg = np.full(len(pairs), np.nan)
         rf, rn = region_spans(reference_trees, [p[1] for p in pairs])
-        cache = {}
+        # strands as integer codes: a comparison is flipped iff the codes differ (sim.py:332-333)
+        codes = {'+': 0, '-': 1, None: 2}
 
-        def bg_spans(regions, ref_strands):
-            bf, bn = region_spans(query_trees, regions)
-            return bf, bn, np.array([r.strand for r in regions], dtype=object)
+        def strand_code(strand):
+            if strand not in codes:
+                codes[strand] = len(codes)
+            return codes[strand]
 
-        k = 0
-        while k < len(pairs):
-            # one engine call for as many pairs as fit the batch budget
-            batch, spans = [], []
-            budget = BACKGROUND_BATCH
-            while k < len(pairs) and (not batch or budget > 0):
-                if background_regions is not None:
-                    key = "bed"
-                    regs = background_regions
-                else:
-                    q = pairs[k][2]
-                    key = (q.chromosome if args.limit_background else None, q.end - q.start)
-                    regs = None
-                if key not in cache:
-                    if regs is None:
-                        regs = _background_regions_from_query(query_regions, pairs[k][2], args.limit_background)
-                    cache[key] = bg_spans(regs, None)
-                bf, bn, strands = cache[key]
-                batch.append(k)
-                spans.append((bf, bn, strands))
-                budget -= len(bf)
-                k += 1
-            tot = sum(len(s[0]) for s in spans)
-            a_rf = np.empty(tot, dtype=np.int64)
-            a_rn = np.empty(tot, dtype=np.int64)
-            a_qf = np.empty(tot, dtype=np.int64)
-            a_qn = np.empty(tot, dtype=np.int64)
-            a_flip = np.empty(tot, dtype=np.int32)
-            pos = 0
-            for kk, (bf, bn, strands) in zip(batch, spans):
-                m = len(bf)
-                a_rf[pos:pos + m] = rf[kk]
-                a_rn[pos:pos + m] = rn[kk]
-                a_qf[pos:pos + m] = bf
-                a_qn[pos:pos + m] = bn
-                a_flip[pos:pos + m] = (strands != pairs[kk][1].strand)
-                pos += m
-            b_ssim, _, b_status = engine.compare_spans(a_rf, a_rn, a_qf, a_qn, a_flip, compute_sn=False, **params)
-            if (b_status == 4).any():
-                raise ValueError("win_size exceeds image extent.")
-            pos = 0
-            for kk, (bf, bn, strands) in zip(batch, spans):
-                m = len(bf)
-                vals = b_ssim[pos:pos + m]
-                pos += m
-                if np.isnan(ssim[kk]):
-                    continue
-                with warnings.catch_warnings(), np.errstate(invalid="ignore", divide="ignore"):
-                    warnings.simplefilter("ignore")
-                    mean, sd = np.nanmean(vals), np.nanstd(vals)       # bin/chess:323-324
-                    z_bg[kk] = (ssim[kk] - mean) / sd
-                    p_bg[kk] = (1 + np.sum(ssim[kk] <= vals)) / len(vals)  # bin/chess:327
+        ref_strand = np.array([strand_code(p[1].strand) for p in pairs], dtype=np.int32)
+        qry_strand = np.array([strand_code(p[2].strand) for p in pairs], dtype=np.int32)
+        qf, qn = region_spans(query_trees, [p[2] for p in pairs])
+        # pairs that share a background set (the BED, or query size [+ chromosome]) go to the device
+        # together: one chess_background_batch per set, nothing but z_bg / p_bg comes back
+        groups = {}
+        for k, pair in enumerate(pairs):
+            if background_regions is not None:
+                key = "bed"
+            else:
+                q = pair[2]
+                key = (q.chromosome if args.limit_background else None, q.end - q.start)
+            groups.setdefault(key, []).append(k)
+        for key, ks in groups.items():
+            if background_regions is not None:
+                regs = background_regions
+            else:
+                regs = _background_regions_from_query(query_regions, pairs[ks[0]][2], args.limit_background)
+            bf, bn = region_spans(query_trees, regs)
+            bstrand = np.array([strand_code(r.strand) for r in regs], dtype=np.int32)
+            ks = np.asarray(ks)
+            z, pv = engine.background(rf[ks], rn[ks], ref_strand[ks], np.asarray(ssim)[ks], bf, bn, bstrand,
+                                      own=(qf[ks], qn[ks], qry_strand[ks]), **params)
+            z_bg[ks] = z
+            p_bg[ks] = pv
 
     nan_counter = 0
     with open(output_file, 'w') as o:

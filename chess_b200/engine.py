@@ -325,6 +325,82 @@ class CompareEngine(object):
             raise _native.ChessNativeError("internal error: a pair was left unprocessed by the tuned kernel")
         return ssim, sn, status
 
+    def background(self, ref_first, ref_n, ref_strand, pair_ssim, bg_first, bg_n, bg_strand, own=None,
+                   default_value=1, **params):
+        """z_bg / p_bg of bin/chess:300-329 for pairs given as reference bin spans.
+
+        Every pair's reference region is compared with every background region
+        (bin spans of the query sample, strands as integer codes: a comparison is
+        flipped iff the codes differ).  Descriptors, SSIM values and the reductions
+        stay on the device (`chess_background_batch`); pairs are sharded over the
+        GPUs in contiguous ranges.  `own` = (first, n, strand) of every pair's own
+        query region: a background region identical to it takes the pair's ssim (the
+        reference computes the identical value twice; keeps `ssim <= bg` exact).
+        Returns (z_bg, p_bg) numpy arrays.
+        """
+        ref_first = np.ascontiguousarray(ref_first, dtype=np.int64)
+        ref_n = np.ascontiguousarray(ref_n, dtype=np.int32)
+        ref_strand = np.ascontiguousarray(ref_strand, dtype=np.int32)
+        pair_ssim = np.ascontiguousarray(pair_ssim, dtype=np.float64)
+        bg_first = np.ascontiguousarray(bg_first, dtype=np.int64)
+        bg_n = np.ascontiguousarray(bg_n, dtype=np.int32)
+        bg_strand = np.ascontiguousarray(bg_strand, dtype=np.int32)
+        if own is not None:
+            own = (np.ascontiguousarray(own[0], dtype=np.int64), np.ascontiguousarray(own[1], dtype=np.int32),
+                   np.ascontiguousarray(own[2], dtype=np.int32))
+        total = len(ref_first)
+        z_bg = np.full(total, np.nan)
+        p_bg = np.full(total, np.nan)
+        if total == 0:
+            return z_bg, p_bg
+        max_n = int(max(ref_n.max(), bg_n.max() if len(bg_n) else 1, 1))
+        flags = _native.FLAG_SYMMETRIC
+        sizes = np.unique(np.concatenate([ref_n[ref_n > 0], bg_n[bg_n > 0]]))
+        if len(sizes) <= 1:
+            flags |= _native.FLAG_EQUAL_SIZES
+        params.pop("compute_sn", None)
+        p = _native.make_params(default_value=default_value, flags=flags, compute_sn=False, **params)
+        ndev = min(len(self.devices), total)
+        bounds = shard_bounds(total, ndev)
+        pending = []
+        for k in range(ndev):
+            device = self.devices[k]
+            lo, hi = int(bounds[k]), int(bounds[k + 1])
+            if hi == lo:
+                continue
+            ctx = get_context(device)
+            dev = torch.device("cuda", device)
+            with torch.cuda.device(dev):
+                rw, rband, rsample = self.ref.sample_on(device, max_n, default_value)
+                qw, qband, qsample = self.qry.sample_on(device, max_n, default_value)
+                up = [torch.from_numpy(a).to(dev) for a in (ref_first[lo:hi], ref_n[lo:hi], ref_strand[lo:hi],
+                                                            pair_ssim[lo:hi], bg_first, bg_n, bg_strand)]
+                d_z = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+                d_p = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+                d_exc = torch.zeros(1, dtype=torch.int32, device=dev)
+                if own is not None:
+                    up += [torch.from_numpy(a[lo:hi]).to(dev) for a in own]
+                    o0, o1, o2 = _ptr(up[7]), _ptr(up[8]), _ptr(up[9])
+                else:
+                    o0 = o1 = o2 = None
+                check(lib.chess_background_batch(ctx.handle, C.byref(rsample), C.byref(qsample), _ptr(up[0]),
+                                                 _ptr(up[1]), _ptr(up[2]), o0, o1, o2, _ptr(up[3]), hi - lo, _ptr(up[4]),
+                                                 _ptr(up[5]), _ptr(up[6]), len(bg_first), max_n, C.byref(p),
+                                                 _ptr(d_z), _ptr(d_p), _ptr(d_exc), _stream_ptr(dev)),
+                      ctx.handle, "chess_background_batch")
+            pending.append((dev, lo, hi, d_z, d_p, d_exc, up))
+        exceeds = 0
+        for dev, lo, hi, d_z, d_p, d_exc, _keep in pending:
+            torch.cuda.synchronize(dev)
+            z_bg[lo:hi] = d_z.cpu().numpy()
+            p_bg[lo:hi] = d_p.cpu().numpy()
+            exceeds += int(d_exc.cpu()[0])
+        if exceeds:
+            raise ValueError("win_size exceeds image extent. Either ensure that your images are "
+                             "at least 7x7; or pass win_size explicitly in the function call, "
+                             "with an odd value less than or equal to the smaller side of your images.")
+        return z_bg, p_bg
+
     def compare(self, pairs, compute_sn=True, default_value=1, **params):
         """Compare (ID, reference_region, query_region) tuples.
 

@@ -211,6 +211,30 @@ int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample *ref, const
  * Fixed-order reduction in one CTA, so the result is deterministic. DEVICE.   */
 int chess_zscore(chess_ctx *ctx, const double *ssim, int64_t n, double *z, void *stream);
 
+/* K7: background statistics of `chess sim --background-query` / `--background-regions`,
+ * bin/chess:259-332.  The REFERENCE region of every pair is compared with every background
+ * region of the query sample (compute_sn = False, bin/chess:300-307); per pair
+ *     z_bg = (ssim - nanmean(bg)) / nanstd(bg)            (ddof 0, bin/chess:323-326)
+ *     p_bg = (1 + #{ssim <= bg}) / len(bg)                (NaNs counted in len, bin/chess:327-329)
+ * and NaN / NaN where the pair's own ssim is NaN (bin/chess:319-321).  Regions are bin spans of
+ * band-resident samples (first bin, bin count; count <= 0 = region not found); strands are small
+ * integer codes, a pair is flipped iff the two codes differ (chess/sim.py:332-333; background BEDs
+ * load with strand None, which differs from '+' and '-').  own_first / own_n / own_strand (nullable
+ * together) give every pair's own QUERY region: a background region with the same bins and the
+ * same orientation repeats the pair's own comparison, where the reference obtains the bit-identical
+ * value (it counts in `ssim <= bg`); the pair's ssim is used for it, so the tie does not depend on
+ * which kernel produced either number.  The n_pairs x n_bg pair descriptors,
+ * their results and the reductions never leave the device.  n_exceeds (nullable) receives the
+ * number of comparisons whose window exceeds the compacted matrix -- where skimage raises and the
+ * reference run aborts.  params->compute_sn is ignored.  All pointers DEVICE.                  */
+int chess_background_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                           const int64_t *ref_first, const int32_t *ref_n, const int32_t *ref_strand,
+                           const int64_t *own_first, const int32_t *own_n, const int32_t *own_strand,
+                           const double *pair_ssim, int64_t n_pairs, const int64_t *bg_first,
+                           const int32_t *bg_n, const int32_t *bg_strand, int64_t n_bg, int32_t max_n,
+                           const chess_params *params, double *z_bg, double *p_bg, int32_t *n_exceeds,
+                           void *stream);
+
 /* SN(M1, M2, size=7), chess/sim.py:15-30, on n x n DEVICE matrices.          */
 int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n, double *out,
                    void *stream);

@@ -340,6 +340,67 @@ def test_sample_against_oracle_at_chr2_scale(cb, chr2_like):
             assert close(sn[k], osn, RTOL), (kw, pid, sn[k], osn)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(absolute_window_size=5)])
+def test_background_statistics_on_device(cb, chr2_like, kw):
+    """chess_background_batch (bin/chess:300-329 on the device) against per-comparison results
+    reduced by the oracle's background_stats, and a sample of the comparisons against the oracle."""
+    from chess_b200.engine import region_spans
+    genome, regions, trees, re_, qe, pairs, ref, qry = chr2_like
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    pick = pairs[5::120] + [pairs[0]]
+    ids, s, sn, st = eng.compare(pick, **kw)
+    s = s.copy()
+    s[1] = np.nan                                   # a pair without a result keeps NaN / NaN
+    rf, rn = region_spans(trees, [p[1] for p in pick])
+    rstrand = np.zeros(len(pick), dtype=np.int32)
+    rstrand[2] = 1
+    starts = np.arange(0, 2400 - 81, 7)
+    bf = np.concatenate([starts, starts, [10, 2390, 50]])
+    bn = np.concatenate([np.full(2 * len(starts), 81), [81, 0, 60]])    # one not found, one smaller (resized)
+    bstrand = np.concatenate([np.zeros(len(starts)), np.ones(len(starts)), [2, 0, 1]]).astype(np.int32)
+    # every pair's own query region = its reference region on '+': where a background region repeats
+    # it, the pair's own value stands in (the reference computes the identical number twice)
+    own_strand = rstrand.copy()               # s was computed unflipped: query strand = reference strand
+    z, pv = eng.background(rf, rn, rstrand, s, bf, bn, bstrand, own=(rf, rn, own_strand), **kw)
+    repeats = 0
+    assert np.isnan(z[1]) and np.isnan(pv[1])
+    for k in range(len(pick)):
+        if np.isnan(s[k]):
+            assert np.isnan(z[k]) and np.isnan(pv[k])
+            continue
+        m = len(bf)
+        vals, _, vst = eng.compare_spans(np.full(m, rf[k]), np.full(m, rn[k]), bf, bn,
+                                         (bstrand != rstrand[k]).astype(np.int32), compute_sn=False, **kw)
+        assert np.isnan(vals[-2]) and np.isfinite(vals[-1]) and np.isfinite(vals[:-2]).sum() > m - 60
+        same = (bf == rf[k]) & (bn == rn[k]) & ((bstrand != rstrand[k]) == (rstrand[k] != own_strand[k]))
+        repeats += int(same.sum())
+        assert np.all(np.abs(vals[same] - s[k]) < 1e-12)
+        vals[same] = s[k]
+        oz, op = O.background_stats(s[k], vals)
+        assert close(z[k], oz, 1e-9), (k, z[k], oz)
+        assert pv[k] == op, (k, pv[k], op)
+    assert repeats >= 1
+    # the comparisons themselves against the oracle (both strands, reference strand '-')
+    oregions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in regions]
+    otrees = O.region_trees(oregions)
+    ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
+    oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
+    k = 2
+    rr = pick[k][1]
+    m = len(bf)
+    vals, _, _ = eng.compare_spans(np.full(m, rf[k]), np.full(m, rn[k]), bf, bn,
+                                   (bstrand != rstrand[k]).astype(np.int32), compute_sn=False, **kw)
+    for j in list(range(0, m, 97)) + [m - 1]:
+        if bn[j] <= 0:
+            continue
+        b0 = regions[int(bf[j])].start
+        b1 = regions[int(bf[j] + bn[j] - 1)].end
+        op = ("x", O.Region(rr.start, rr.end, rr.chromosome, strand="-"),
+              O.Region(b0 + 1, b1 - 1, "chr2", strand={0: "+", 1: "-", 2: None}[int(bstrand[j])]))
+        _, os_, _ = O.compare_pair(op, ore, otrees, oqe, otrees, compute_sn=False, **kw)
+        assert close(vals[j], os_, RTOL), (j, vals[j], os_)
+
+
 def test_multi_gpu_sharding_identical(cb, chr2_like):
     import torch
     if torch.cuda.device_count() < 2:
