@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genome-wide", action="store_true",
                     help="skip the extra configs[2] (hg38 @ 10 kb, ~100k pairs) measurement at N=1")
+    ap.add_argument("--no-background", action="store_true",
+                    help="skip the extra --background-query measurement (a-14) at N=1")
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 auto, 1 force the generic kernel, 2 the CTA-per-pair tuned kernel")
     return ap.parse_args()
@@ -468,11 +470,90 @@ def measure(args, rank, world, local_rank, dist):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if world == 1 and args.workload == "chr2_25kb" and not args.no_background:
+        try:
+            line["background"] = measure_background(args, local_rank, genome, regions, trees, re_, qe, pairs,
+                                                    h_ssim, params)
+        except Exception as exc:  # never lose the contract line over the extra measurement
+            line["background"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(genome, ref, qry, pairs, args, re_, qe, h_ssim, h_sn)
     re_.drop_device_copies()
     qe.drop_device_copies()
     return line
+
+
+def measure_background(args, local_rank, genome, regions, trees, re_, qe, pairs, pair_ssim, params, n_sample=64):
+    """`chess sim --background-query` (bin/chess:259-332) for a sample of the pairs: every
+    query bin start x both strands as background regions, compute_sn off, reduced to z_bg / p_bg on the
+    device.  Throughput in background comparisons per second: device-timed (arrays resident) and through
+    CompareEngine.background (host arrays in, z_bg / p_bg out)."""
+    import torch
+    import chess_b200 as cb
+    from chess_b200.engine import region_spans
+    from chess_b200.cli import _background_regions_from_query
+    dev = torch.device("cuda", local_rank)
+    step = max(1, len(pairs) // n_sample)
+    pick = pairs[::step][:n_sample]
+    idx = list(range(0, len(pairs), step))[:n_sample]
+    t0 = time.perf_counter()
+    regs = _background_regions_from_query(regions, pick[0][2], True)
+    bf, bn = region_spans(trees, regs)
+    bstrand = np.array([0 if r.strand == '+' else 1 for r in regs], dtype=np.int32)
+    host_prep_s = time.perf_counter() - t0
+    rf, rn = region_spans(trees, [p[1] for p in pick])
+    zeros = np.zeros(len(pick), dtype=np.int32)
+    s = np.asarray(pair_ssim)[idx]
+    eng = cb.CompareEngine(re_, trees, qe, trees, devices=[local_rank])
+    n_cmp = len(pick) * len(bf)
+    for _ in range(2):
+        z, pv = eng.background(rf, rn, zeros, s, bf, bn, bstrand, own=(rf, rn, zeros), **params)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    z, pv = eng.background(rf, rn, zeros, s, bf, bn, bstrand, own=(rf, rn, zeros), **params)
+    e2e_s = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = cb.engine.get_context(local_rank)
+    from chess_b200 import _native
+    from chess_b200._native import lib, check
+    p = _native.make_params(compute_sn=False, flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES, **params)
+    max_n = int(max(rn.max(), bn.max()))
+    rw, rband, rsample = re_.sample_on(local_rank, max_n)
+    qw, qband, qsample = qe.sample_on(local_rank, max_n)
+    up = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in
+          (rf.astype(np.int64), rn.astype(np.int32), zeros, s, bf.astype(np.int64), bn.astype(np.int32), bstrand)]
+    d_z = torch.empty(len(pick), dtype=torch.float64, device=dev)
+    d_p = torch.empty(len(pick), dtype=torch.float64, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def device_call():
+        check(lib.chess_background_batch(ctx.handle, C.byref(rsample), C.byref(qsample), ptr(up[0]), ptr(up[1]),
+                                         ptr(up[2]), ptr(up[0]), ptr(up[1]), ptr(up[2]), ptr(up[3]), len(pick),
+                                         ptr(up[4]), ptr(up[5]), ptr(up[6]), len(bf), max_n, C.byref(p), ptr(d_z),
+                                         ptr(d_p), None, sp), ctx.handle, "chess_background_batch")
+
+    for _ in range(2):
+        device_call()
+    torch.cuda.synchronize(dev)
+    launches0 = ctx.launches()
+    e0.record()
+    device_call()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    same = bool(np.allclose(d_z.cpu().numpy(), z, rtol=1e-9, atol=1e-12, equal_nan=True) and
+                np.array_equal(d_p.cpu().numpy(), pv, equal_nan=True))
+    return {"what": "chess sim --background-query --limit-background: %d pairs x %d background regions "
+                    "(every query bin start, both strands), compute_sn off, z_bg / p_bg reduced on the device"
+                    % (len(pick), len(bf)),
+            "comparisons": n_cmp, "value": n_cmp / dev_s, "unit": "background comparisons/s",
+            "seconds_device": dev_s, "gpu_launches": int(ctx.launches() - launches0),
+            "e2e": {"value": n_cmp / e2e_s, "unit": "background comparisons/s", "seconds": e2e_s,
+                    "call": "CompareEngine.background (host spans in, z_bg / p_bg out)",
+                    "host_region_list_s": host_prep_s},
+            "whole_run_estimate_s": len(pairs) * len(bf) / (n_cmp / dev_s),
+            "finite_z": int(np.isfinite(z).sum()), "device_call_matches_engine": same}
 
 
 def cpu_baseline(genome, ref, qry, pairs, args, re_, qe, gpu_ssim, gpu_sn):

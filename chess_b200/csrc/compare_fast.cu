@@ -503,7 +503,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   }
   const int ncol_pad = ((max_n + 31) / 32) * 32;
   const size_t stride = items_stride(ncol_pad);
-  // pairs per launch: at most 16384 (size of the arrival-counter array) and at most ~256 MB of band records
+  // pairs per launch: at most 16384 (size of the arrival-counter array; 64k-pair chunks measured slower -- their
+  // band records no longer stay in L2) and at most ~256 MB of band records
   const int64_t chunk_max = 16384;
   int64_t chunk = (int64_t)((size_t)(256u << 20) / ((size_t)kBands * stride * sizeof(double)));
   if (chunk > chunk_max) chunk = chunk_max;
