@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genome-wide", action="store_true",
                     help="skip the extra configs[2] (hg38 @ 10 kb, ~100k pairs) measurement at N=1")
+    ap.add_argument("--no-ingest", action="store_true",
+                    help="skip the extra sparse-text ingest measurement (8f-1) at N=1")
     ap.add_argument("--no-background", action="store_true",
                     help="skip the extra --background-query measurement (a-14) at N=1")
     ap.add_argument("--kernel", type=int, default=0,
@@ -476,6 +478,11 @@ def measure(args, rank, world, local_rank, dist):
                                                     h_ssim, params)
         except Exception as exc:  # never lose the contract line over the extra measurement
             line["background"] = {"error": repr(exc)}
+    if world == 1 and args.workload == "chr2_25kb" and not args.no_ingest:
+        try:
+            line["ingest"] = measure_ingest(local_rank, ref)
+        except Exception as exc:
+            line["ingest"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(genome, ref, qry, pairs, args, re_, qe, h_ssim, h_sn)
     re_.drop_device_copies()
@@ -554,6 +561,45 @@ def measure_background(args, local_rank, genome, regions, trees, re_, qe, pairs,
                     "host_region_list_s": host_prep_s},
             "whole_run_estimate_s": len(pairs) * len(bf) / (n_cmp / dev_s),
             "finite_z": int(np.isfinite(z).sum()), "device_call_matches_engine": same}
+
+
+def measure_ingest(local_rank, sample):
+    """Sparse-matrix text of the reference sample ("src<TAB>sink<TAB>repr(weight)" lines) -> COO:
+    chess_sparse_text_* on the device (host bytes in, host arrays out) beside the host parser
+    (pandas C reader, round-trip floats) and the reference's own Python loop on a sub-sample."""
+    import torch
+    from chess_b200.ingest import parse_sparse_text
+    src, sink, w = sample[0], sample[1], sample[2]
+    text = "".join("%d\t%d\t%r\n" % t for t in zip(src.tolist(), sink.tolist(), w.tolist())).encode()
+    data = np.frombuffer(bytearray(text), dtype=np.uint8)
+    n_lines = len(w)
+    parse_sparse_text(data, device=local_rank)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a, b, v, n_data, n_bad = parse_sparse_text(data, device=local_rank)
+    dev_s = time.perf_counter() - t0
+    exact = bool(v.tobytes() == np.asarray(w, dtype=np.float64).tobytes() and
+                 np.array_equal(a, np.minimum(src, sink)) and np.array_equal(b, np.maximum(src, sink)))
+    import io
+    import pandas as pd
+    t0 = time.perf_counter()
+    frame = pd.read_csv(io.BytesIO(text), sep="\t", comment="#", header=None, usecols=[0, 1, 2],
+                        dtype={2: np.float64}, engine="c", float_precision="round_trip")
+    host_s = time.perf_counter() - t0
+    sub = text[:text.index(b"\n", len(text) // 20) + 1].decode()
+    t0 = time.perf_counter()
+    k = 0
+    for ln in sub.splitlines():
+        f = ln.rstrip().split("\t")
+        _ = (int(f[0]), int(f[1]), float(f[2]))
+        k += 1
+    loop_s = time.perf_counter() - t0
+    return {"what": "sparse-matrix text of one chr2 sample -> canonical COO (int, int, float per line)",
+            "lines": n_lines, "bytes": len(text), "bit_identical_to_source": exact,
+            "device": {"lines_per_s": n_lines / dev_s, "GB_per_s": len(text) / dev_s / 1e9, "seconds": dev_s,
+                       "call": "chess_b200.ingest.parse_sparse_text (H2D of the text + parse + D2H of the arrays)"},
+            "host_pandas": {"lines_per_s": len(frame) / host_s, "seconds": host_s},
+            "reference_python_loop": {"lines_per_s": k / loop_s, "sample_lines": k}}
 
 
 def cpu_baseline(genome, ref, qry, pairs, args, re_, qe, gpu_ssim, gpu_sn):

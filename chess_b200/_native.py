@@ -88,6 +88,11 @@ SIGNATURES = {
     "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "chess_sparse_text_lines": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp]),
+    "chess_sparse_text_parse": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                          C.POINTER(C.c_int64), _vp]),
+    "chess_sparse_text_compact": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                            C.POINTER(C.c_int64), _vp]),
     "chess_background_batch": (C.c_int, [_vp, _SP, _SP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _PP,
                                          _vp, _vp, _vp, _vp]),
 }

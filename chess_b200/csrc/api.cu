@@ -71,6 +71,7 @@ extern "C" void chess_ctx_destroy(chess_ctx *ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->d_items) cudaFree(ctx->d_items);
   if (ctx->d_bg) cudaFree(ctx->d_bg);
+  if (ctx->d_ingest) cudaFree(ctx->d_ingest);
   delete ctx;
 }
 

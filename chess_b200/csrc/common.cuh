@@ -20,6 +20,8 @@ struct chess_ctx {
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
   // workspace of the item kernel: work counters, retry flags, arrival counters, band records
+  void *d_ingest = nullptr;   // sparse-text parser: tile counts / offsets (+ 256 spare bytes behind d_ingest_bytes)
+  size_t d_ingest_bytes = 0;
   void *d_bg = nullptr;       // background path: pair descriptors + results of one chunk
   size_t d_bg_bytes = 0;
   void *d_items = nullptr;

@@ -263,9 +263,26 @@ def sub_matrix_from_edges_dict(edges, regions, region, default_weight=0.0):
     return contacts.submatrix(start_ix, end_ix - start_ix + 1, default_weight), sr
 
 
+def _cuda_visible():
+    """File parsing alone (no comparison) also works on a host without a GPU: then pandas parses."""
+    import torch
+    return torch.cuda.is_available()
+
+
 def _parse_sparse(file_name, ix_converter=None, sep="\t"):
     """(src, sink, weight) arrays, canonical and finite; the array form of
     edges_from_sparse_matrix (chess/helpers.py:309-339)."""
+    if ix_converter is None and sep == "\t" and _cuda_visible():
+        # index-addressed matrix: the text is parsed on the GPU (csrc/ingest.cu); None = this file
+        # needs the host parser below (lone carriage returns / mostly unusual number spellings)
+        from .ingest import parse_sparse_text
+        parsed = parse_sparse_text(os.path.expanduser(file_name))
+        if parsed is not None:
+            lo, hi, w, total, n_bad = parsed
+            if total and n_bad / total > 0.05:
+                logger.warning("Could not import more than 5% of matrix entries ({}/{}), "
+                               "as they were not finite".format(n_bad, total))
+            return lo, hi, w
     import pandas as pd
     with _open(file_name, "r") as fh:
         try:

@@ -235,6 +235,37 @@ int chess_background_batch(chess_ctx *ctx, const chess_sample *ref, const chess_
                            const chess_params *params, double *z_bg, double *p_bg, int32_t *n_exceeds,
                            void *stream);
 
+/* K8: sparse-matrix text ("source<TAB>sink<TAB>weight" lines) -> COO on the device; replaces the
+ * Python line loop of edges_from_sparse_matrix, chess/helpers.py:309-339.  `text` is the file
+ * content in DEVICE memory (16-byte aligned).  Three synchronous steps:
+ *   chess_sparse_text_lines    number of lines, and of carriage returns not followed by a newline
+ *                              (Python's universal newlines would split there: use the host parser);
+ *   chess_sparse_text_parse    per line k: kind[k] = 0 data (src[k] <= sink[k], weight[k] set),
+ *                              1 comment ('#' first) or blank, 2 non-finite weight (dropped by the
+ *                              reference, helpers.py:328-330), 3 = the device could not decide
+ *                              (spelling outside the plain int / float grammar, > 19 significant
+ *                              digits, subnormal, malformed).  int() / float() results are
+ *                              bit-identical to Python's.  Kind-3 line numbers go to fb_lines (up to
+ *                              fb_cap; *n_fallback is the full count); line_start[n_lines + 1]
+ *                              receives the byte offset of every line (line k ends at
+ *                              line_start[k+1] - 1), so the host can re-parse those lines with
+ *                              Python itself and patch src / sink / weight / kind;
+ *   chess_sparse_text_compact  stable compaction of the kind-0 lines (file order kept: a later
+ *                              duplicate wins, helpers.py:353-356).  counts[0] = kept, counts[1] =
+ *                              data lines (kept + non-finite), counts[2] = non-finite.  With all
+ *                              three outputs NULL only the counts are produced.  Fails if a kind-3
+ *                              line is left.                                                        */
+int chess_sparse_text_lines(chess_ctx *ctx, const char *text, int64_t n_bytes, int64_t *n_lines,
+                            int64_t *n_lone_cr, void *stream);
+int chess_sparse_text_parse(chess_ctx *ctx, const char *text, int64_t n_bytes, int64_t n_lines,
+                            int32_t *src, int32_t *sink, double *weight, uint8_t *kind,
+                            int64_t *line_start, int64_t *fb_lines, int64_t fb_cap, int64_t *n_fallback,
+                            void *stream);
+int chess_sparse_text_compact(chess_ctx *ctx, int64_t n_lines, const int32_t *src, const int32_t *sink,
+                              const double *weight, const uint8_t *kind, int32_t *out_src,
+                              int32_t *out_sink, double *out_weight, int64_t out_capacity,
+                              int64_t *counts, void *stream);
+
 /* SN(M1, M2, size=7), chess/sim.py:15-30, on n x n DEVICE matrices.          */
 int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n, double *out,
                    void *stream);

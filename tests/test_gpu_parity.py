@@ -659,3 +659,90 @@ def test_band_kernels_ill_conditioned_sn_windows(cb):
             if np.isfinite(osn) and osn < 1e6:
                 assert close(first[2][k], osn, RTOL), (kw, pid, first[2][k], osn)
                 assert close(gen[2][k], osn, RTOL), (kw, pid, gen[2][k], osn)
+
+
+# ------------------------------------------------------------------ sparse text on the device (8f-1)
+def _reference_parse(text):
+    """edges_from_sparse_matrix (chess/helpers.py:309-339) on a string, blank lines skipped."""
+    out = []
+    total = bad = 0
+    for line in text.splitlines(True):
+        if line.startswith("#"):
+            continue
+        line = line.rstrip()
+        if line == "":
+            continue
+        total += 1
+        f = line.split("\t")
+        a, b, w = int(f[0]), int(f[1]), float(f[2])
+        if not np.isfinite(w):
+            bad += 1
+            continue
+        out.append((min(a, b), max(a, b), w))
+    return out, total, bad
+
+
+def test_sparse_text_parser_on_device(cb, tmp_path):
+    import gzip
+    from chess_b200.ingest import parse_sparse_text
+    rng = np.random.default_rng(5)
+    lines = ["# header line\tignored", "#another"]
+    for k in range(60000):
+        a, b = int(rng.integers(0, 5000)), int(rng.integers(0, 5000))
+        style = k % 7
+        w = float(rng.lognormal(0, 2))
+        if style == 0:
+            ws = repr(w)
+        elif style == 1:
+            ws = "%.6f" % w
+        elif style == 2:
+            ws = "%d" % int(w * 10)
+        elif style == 3:
+            ws = "%.17e" % w
+        elif style == 4:
+            ws = "%.3g" % (w * 1e-7)
+        elif style == 5:
+            ws = repr(np.float32(w).item())
+        else:
+            ws = "%.12E" % (w * 1e20)
+        lines.append("%d\t%d\t%s" % (a, b, ws))
+    lines += ["7\t3\tnan", "8\t2\tinf", "9\t1\t-Infinity", "", "   ", "12\t4\t 1.5 ", "13\t5\t1_000.5", "+14\t 6\t1e-320",
+              "15\t7\t0.1234567890123456789012345", "16\t8\t1.5\textra\tfields", "17\t9\t2.5\r", "3\t3\t-0.0",
+              "18\t10\t1e400", "19\t11\t.5", "20\t12\t5.", "21\t13\t1E+2"]
+    text = "\n".join(lines)            # no trailing newline: the last line still counts
+    want, total, bad = _reference_parse(text)
+    for name, payload in (("plain.sparse", text.encode()), ("nl.sparse", (text + "\n").encode())):
+        path = tmp_path / name
+        path.write_bytes(payload)
+        a, b, w, n_data, n_bad = parse_sparse_text(str(path))
+        assert (n_data, n_bad) == (total, bad)
+        assert len(w) == len(want)
+        assert a.tolist() == [t[0] for t in want] and b.tolist() == [t[1] for t in want]
+        assert w.tobytes() == np.array([t[2] for t in want]).tobytes()      # bit-identical, file order
+    gz = tmp_path / "z.sparse.gz"
+    with gzip.open(str(gz), "wb") as fh:
+        fh.write(text.encode())
+    a2, b2, w2, _, _ = parse_sparse_text(str(gz))
+    assert w2.tobytes() == w.tobytes() and a2.tolist() == a.tolist()
+    # the loader takes the same path and agrees with the host (pandas) parser
+    import chess_b200.helpers as H
+    clean = tmp_path / "clean.sparse"
+    clean.write_text("\n".join(lines[:60005]) + "\n")   # everyday spellings only (pandas has its own quirks)
+    dev_arrays = H._parse_sparse(str(clean))
+    saved = H._cuda_visible
+    H._cuda_visible = lambda: False
+    try:
+        host_arrays = H._parse_sparse(str(clean))
+    finally:
+        H._cuda_visible = saved
+    for x, y in zip(dev_arrays, host_arrays):
+        assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    # malformed lines raise what Python raises; lone carriage returns defer the whole file
+    bad_file = tmp_path / "bad.sparse"
+    bad_file.write_bytes(b"1\t2\t3.0\n4\t5\tabc\n")
+    with pytest.raises(ValueError):
+        parse_sparse_text(str(bad_file))
+    assert parse_sparse_text(b"1\t2\t3.0\r4\t5\t6.0\r") is None
+    assert parse_sparse_text(b"")[3] == 0
+    e = parse_sparse_text(b"#only a comment\n")
+    assert len(e[0]) == 0 and e[3] == 0
