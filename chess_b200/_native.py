@@ -44,7 +44,7 @@ class chess_pair(C.Structure):
 class chess_sample(C.Structure):
     _fields_ = [("band", C.c_void_p), ("nd_lo", C.c_void_p), ("nd_hi", C.c_void_p),
                 ("pmax", C.c_void_p), ("pmin", C.c_void_p),
-                ("n_bins", C.c_int64), ("W", C.c_int32), ("reserved", C.c_int32)]
+                ("n_bins", C.c_int64), ("W", C.c_int32), ("reserved", C.c_int32), ("rowpre", C.c_void_p)]
 
 
 class chess_params(C.Structure):
@@ -88,6 +88,7 @@ SIGNATURES = {
     "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "chess_band_prefix_build": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "chess_sparse_text_lines": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp]),
     "chess_sparse_text_parse": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                           C.POINTER(C.c_int64), _vp]),

@@ -48,6 +48,7 @@ struct chess_item_args {
   const double *ref_band, *qry_band;
   const int *ref_lo, *ref_hi, *qry_lo, *qry_hi;
   const double *ref_pmax, *ref_pmin, *qry_pmax, *qry_pmin;  // running extrema, may be NULL
+  const double *ref_pre, *qry_pre;                          // band-row prefix sums (triangle kernel only)
   const chess_pair *pairs;
   long long n_pairs;
   chess_params p;
@@ -65,6 +66,8 @@ int chess_items_launch_h0(chess_ctx *ctx, chess_item_args &a, int G, bool multi,
 int chess_items_launch_h1(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
 int chess_items_launch_h2(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
 int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
+// -r 1 over the upper triangle (compare_tri.cuh)
+int chess_items_launch_tri(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 
 // Internal launchers (one per translation unit).
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,

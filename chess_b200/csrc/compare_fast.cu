@@ -470,6 +470,61 @@ extern "C" int chess_band_extrema_build(chess_ctx *ctx, const double *band, int6
   return CHESS_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(128)
+band_prefix_kernel(const double *__restrict__ band, long long n_bins, int W, double *__restrict__ pre) {
+  // one warp per band row: lanes take 32 consecutive entries at a time, an inclusive warp scan plus
+  // the running carry gives the prefix (fixed order, so the array is reproducible)
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_bins) return;
+  const double *src = band + row * (2LL * W - 1);
+  double *dst = pre + row * (2LL * W);
+  const int len = 2 * W - 1;
+  double carry = 0.0;
+  if (lane == 0) dst[0] = 0.0;
+  for (int base = 0; base < len; base += 32) {
+    const int k = base + lane;
+    double v = k < len ? src[k] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    v += carry;
+    if (k < len) dst[k + 1] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+}  // namespace
+
+extern "C" int chess_band_prefix_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                                       double *rowpre, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (!band || n_bins <= 0 || W <= 0 || !rowpre) {
+    ctx->err = "chess_band_prefix_build: bad arguments";
+    return CHESS_ERR_ARG;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  band_prefix_kernel<<<(unsigned)((n_bins + 3) / 4), 128, 0, stream>>>(band, (long long)n_bins, W, rowpre);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+// smallest strip width whose triangle split (compare_tri.cuh: tri_split) fits the warp, 0 if none
+static int tri_strip_width(int n) {
+  for (int G = 3; G <= 8; ++G) {
+    if (n > 31 * G || n < 24) continue;
+    const int x = (n - 3) / 3;
+    const int b1 = n - 2 * x, b2 = n - x;
+    const int l1 = (n - (b1 - 3) + G - 1) / G, l2 = (n - (b2 - 3) + G - 1) / G;
+    if (l1 + l2 <= 30) return G;
+  }
+  return 0;
+}
+
 int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
                                const chess_pair *pairs, int64_t n_pairs, int32_t max_n,
                                const chess_params &p, double *ssim, double *sn, int32_t *status,
@@ -501,13 +556,18 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
       if (best < 0 || cost <= best) { best = cost; G = g; }
     }
   }
+  // -r 1 over the upper triangle when both samples carry their row prefix sums (kernel = 3 keeps the
+  // full-square walk for A/B runs)
+  const int tri_G = (r1 && p.kernel != 3 && ref->rowpre && qry->rowpre) ? tri_strip_width(max_n) : 0;
+  const bool tri = tri_G != 0;
+  if (tri) G = tri_G;
   const int ncol_pad = ((max_n + 31) / 32) * 32;
-  const size_t stride = items_stride(ncol_pad);
+  const size_t stride = tri ? (size_t)16 : items_stride(ncol_pad);
   // pairs per launch: at most 16384 (size of the arrival-counter array; 64k-pair chunks measured slower -- their
   // band records no longer stay in L2) and at most ~256 MB of band records
-  const int64_t chunk_max = 16384;
+  const int64_t chunk_max = 65536;  // arrival counters reserved in the workspace
   int64_t chunk = (int64_t)((size_t)(256u << 20) / ((size_t)kBands * stride * sizeof(double)));
-  if (chunk > chunk_max) chunk = chunk_max;
+  if (chunk > (tri ? chunk_max : 16384)) chunk = tri ? chunk_max : 16384;  // triangle records are 128 B
   if (chunk < 512) chunk = 512;
   const int64_t cap = n_pairs < chunk ? n_pairs : chunk;
   // workspace: [2 counters][2 retry flags + pad][done: chunk ints][scratch: cap * kBands * stride doubles];
@@ -541,6 +601,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   const bool have_extrema = ref->pmax && ref->pmin && qry->pmax && qry->pmin;
   a.ref_pmax = have_extrema ? ref->pmax : nullptr; a.ref_pmin = have_extrema ? ref->pmin : nullptr;
   a.qry_pmax = have_extrema ? qry->pmax : nullptr; a.qry_pmin = have_extrema ? qry->pmin : nullptr;
+  a.ref_pre = ref->rowpre; a.qry_pre = qry->rowpre;
   a.p = p;
   a.ncol_pad = ncol_pad;
   a.done = reinterpret_cast<int *>(base + head);
@@ -555,7 +616,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     int rc;
     const int hh = r1 ? 0 : H;
     const bool multi = max_n > 31 * G;
-    if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, multi, stream);
+    if (tri) rc = chess_items_launch_tri(ctx, a, G, stream);
+    else if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, multi, stream);
     else if (hh == 1) rc = chess_items_launch_h1(ctx, a, G, multi, stream);
     else if (hh == 2) rc = chess_items_launch_h2(ctx, a, G, multi, stream);
     else rc = chess_items_launch_h3(ctx, a, G, multi, stream);

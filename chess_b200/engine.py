@@ -163,10 +163,15 @@ class DeviceContacts(object):
             with torch.cuda.device(dev):
                 check(lib.chess_band_extrema_build(ctx.handle, _ptr(band), self.n_bins, W, _ptr(pmax), _ptr(pmin),
                                                    _stream_ptr(dev)), ctx.handle, "chess_band_extrema_build")
-            have = (nd_lo, nd_hi, pmax, pmin)
+            rowpre = torch.empty(self.n_bins * 2 * W, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.chess_band_prefix_build(ctx.handle, _ptr(band), self.n_bins, W, _ptr(rowpre),
+                                                  _stream_ptr(dev)), ctx.handle, "chess_band_prefix_build")
+            have = (nd_lo, nd_hi, pmax, pmin, rowpre)
             self._index[device] = have
         sample = _native.chess_sample(band.data_ptr(), have[0].data_ptr(), have[1].data_ptr(),
-                                      have[2].data_ptr(), have[3].data_ptr(), self.n_bins, W, 0)
+                                      have[2].data_ptr(), have[3].data_ptr(), self.n_bins, W, 0,
+                                      have[4].data_ptr())
         return W, band, sample
 
     def drop_device_copies(self):

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CHESS_B200_ABI_VERSION 1
+#define CHESS_B200_ABI_VERSION 2
 
 typedef struct chess_ctx chess_ctx;
 
@@ -188,6 +188,8 @@ typedef struct chess_sample {
   int64_t n_bins;
   int32_t W;
   int32_t reserved;
+  const double *rowpre;  /* DEVICE, n_bins*2W: prefix sums along every band row (chess_band_prefix_build);
+                            may be NULL (then the -r 1 kernel walks the full square instead of the triangle) */
 } chess_sample;
 int chess_band_index_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
                            double default_value, int32_t *nd_lo, int32_t *nd_hi, void *stream);
@@ -195,6 +197,13 @@ int chess_band_index_build(chess_ctx *ctx, const double *band, int64_t n_bins, i
  * (chess/sim.py:368-370) starting at bin i0 with n bins is then
  * max_r pmax[(i0+r)*W + n-1-r] - min_r pmin[...]: n lookups instead of n*n
  * compares (the matrix is symmetric, so its upper triangle holds every value). */
+/* Prefix sums along every band row: rowpre[i*2W + k] = sum of band(i, .) over the first k entries
+ * of row i (k = 0 .. 2W-1).  The sum of a submatrix column -- the quantity find_masked_rows tests,
+ * chess/sim.py:74-87 -- is then one subtraction; the -r 1 kernel uses it to screen the columns it
+ * did NOT predict as masked for a coincidental hit of n*default (confirmed exactly, in the
+ * reference's own order, before the pair is handed to the generic kernel).                     */
+int chess_band_prefix_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
+                            double *rowpre, void *stream);
 int chess_band_extrema_build(chess_ctx *ctx, const double *band, int64_t n_bins, int32_t W,
                              double *pmax, double *pmin, void *stream);
 int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,

@@ -508,7 +508,7 @@ def test_band_index_and_extrema_arrays(cb):
             dense[i, j] = dense[j, i] = v
     dc = DeviceContacts(np.array(src), np.array(sink), np.array(val), n_bins=n)
     w, band, sample = dc.sample_on(0, W)
-    nd_lo, nd_hi, pmax, pmin = [t.cpu().numpy() for t in dc._index[0]]
+    nd_lo, nd_hi, pmax, pmin, rowpre = [t.cpu().numpy() for t in dc._index[0]]
     pmax, pmin = pmax.reshape(n, w), pmin.reshape(n, w)
     for i in range(n):
         lo_c = [k for k in range(max(0, i - w + 1), i + 1) if dense[i, k] != 1.0]
@@ -518,6 +518,16 @@ def test_band_index_and_extrema_arrays(cb):
         row = dense[i, i:min(n, i + w)]
         assert np.array_equal(pmax[i, :len(row)], np.maximum.accumulate(row)), i
         assert np.array_equal(pmin[i, :len(row)], np.minimum.accumulate(row)), i
+    # row prefix sums: any window sum of a band row is one subtraction
+    rowpre = rowpre.reshape(n, 2 * w)
+    hband = band.cpu().numpy().reshape(n, 2 * w - 1)
+    assert np.all(rowpre[:, 0] == 0.0)
+    assert np.allclose(rowpre[:, 1:], np.cumsum(hband, axis=1), rtol=1e-13, atol=1e-12)
+    i0, m = 40, 45
+    for c in (0, 7, 44):
+        j = i0 + c
+        got = rowpre[j, w - 1 - c + m] - rowpre[j, w - 1 - c]
+        assert abs(got - dense[i0:i0 + m, j].sum()) < 1e-10
 
 
 def test_bin_masked_in_one_sample_only(cb):
