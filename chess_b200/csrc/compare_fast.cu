@@ -30,6 +30,8 @@
 //     symmetric (column totals = row totals).
 // Pairs this kernel cannot take (unequal sizes, n > 32*G) are marked
 // CHESS_PAIR_RETRY and handled by the generic kernel.
+#include <cstdlib>
+
 #include "compare_kernels.cuh"
 
 namespace {
@@ -515,7 +517,8 @@ extern "C" int chess_band_prefix_build(chess_ctx *ctx, const double *band, int64
 
 // smallest strip width whose triangle split (compare_tri.cuh: tri_split) fits the warp, 0 if none
 static int tri_strip_width(int n) {
-  for (int G = 3; G <= 8; ++G) {
+  static const int g_min = getenv("CHESS_TRI_G") ? atoi(getenv("CHESS_TRI_G")) : 3;  // experiments only
+  for (int G = g_min < 3 ? 3 : g_min; G <= 8; ++G) {
     if (n > 31 * G || n < 24) continue;
     const int x = (n - 3) / 3;
     const int b1 = n - 2 * x, b2 = n - x;
