@@ -129,7 +129,7 @@ extern "C" int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref,
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
   chess_params p = *params;
   p.flags |= CHESS_FLAG_SYMMETRIC;  // a band is symmetric by construction
-  if (p.kernel == 0) {
+  if (p.kernel == 0 || p.kernel == 3) {
     bool handled = false;
     rc = chess_launch_compare_items(ctx, ref, qry, pairs, n_pairs, max_n, p, ssim, sn, status, stream, &handled);
     if (rc) return rc;

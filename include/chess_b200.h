@@ -85,7 +85,8 @@ typedef struct chess_params {
   double mappability_cutoff; /* --mappability-cutoff                           */
   double default_value;      /* fill / masking value, 1 from the CLI           */
   int32_t kernel;            /* 0 = auto, 1 = force the generic kernel,
-                                2 = skip the work-item kernel (A/B testing)    */
+                                2 = skip the work-item kernels, 3 = work-item
+                                kernel without the upper-triangle form (A/B)   */
   int32_t flags;             /* CHESS_FLAG_* promises about the batch          */
 } chess_params;
 

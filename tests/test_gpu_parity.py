@@ -423,7 +423,8 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
                dict(absolute_window_size=3, compute_sn=False), dict(absolute_window_size=8, keep_unmappable_bins=True)):
         for plist in (pairs, flipped):
             gen = eng.compare(plist, kernel=1, **kw)
-            for kernel in (0, 2):   # 0: work-item kernel, 2: CTA-per-pair tuned kernel
+            # 0: work-item kernels (-r 1: upper triangle), 3: full-square work-item kernel, 2: CTA-per-pair kernel
+            for kernel in (0, 3, 2):
                 fast = eng.compare(plist, kernel=kernel, **kw)
                 assert np.array_equal(fast[3], gen[3])
                 np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
@@ -435,7 +436,7 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
         plist = synth.sliding_pairs(genome, window_bp, 900000 if window_bp <= 5000000 else 2900000)
         for kw in (dict(), dict(absolute_window_size=7)):
             gen = eng.compare(plist, kernel=1, **kw)
-            for kernel in (0, 2):
+            for kernel in (0, 3, 2):
                 fast = eng.compare(plist, kernel=kernel, **kw)
                 assert np.array_equal(fast[3], gen[3])
                 np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
@@ -474,7 +475,7 @@ def test_band_kernels_coincidentally_masked_bins(cb):
     ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
     oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
     hits = 0
-    for kernel in (0, 2, 1):
+    for kernel in (0, 3, 2, 1):
       for extra in (dict(), dict(absolute_window_size=7)):
         ids, s, sn, st = eng.compare(pairs, kernel=kernel, mappability_cutoff=0.2, **extra)
         for k, (pid, rr, qr) in enumerate(pairs):
