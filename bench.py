@@ -56,8 +56,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--window", default="r1", choices=["r1", "a7"],
-                    help="r1 = default `chess sim` (-r 1); a7 = -a 7")
+    ap.add_argument("--window", default="r1", choices=["r1", "a3", "a5", "a7", "a9", "a11"],
+                    help="r1 = default `chess sim` (-r 1); aN = -a N")
     ap.add_argument("--workload", default="chr2_25kb", choices=["chr2_25kb", "hg38_10kb"],
                     help="chr2_25kb = BASELINE configs[1] (the contract's bench line); hg38_10kb = configs[2], "
                          "genome-wide 10 kb, ~100k pairs of 2 Mb, pairs sharded over the ranks (strong scaling)")
@@ -76,7 +76,7 @@ def parse_args():
 
 
 def window_params(tag):
-    return dict(absolute_window_size=7) if tag == "a7" else dict()
+    return dict(absolute_window_size=int(tag[1:])) if tag.startswith("a") else dict()
 
 
 def make_workload(rank, workload="chr2_25kb", world=1, bin_size=BIN, window_bp=WINDOW_BP):
@@ -272,7 +272,7 @@ def workload_config(args, n_pairs, n_bins, sample=None):
     else:
         what = ("configs[1]: human chr2 @ 25 kb (%d bins), 2 Mb windows step 100 kb" if args.workload == "chr2_25kb"
                 else "configs[2]: human hg38 @ 10 kb genome-wide (%d bins), 2 Mb windows step 30 kb") % n_bins
-    cfg = {"workload": "%s, chess sim %s, SN on" % (what, "-r 1 (default)" if args.window == "r1" else "-a 7"),
+    cfg = {"workload": "%s, chess sim %s, SN on" % (what, "-r 1 (default)" if args.window == "r1" else "-a " + args.window[1:]),
            "pairs_per_gpu": n_pairs,
            "bins_per_pair": args.window_bp // args.bin_size + 1 if args.workload == "chr2_25kb" else 201,
            "window": args.window,

@@ -70,6 +70,8 @@ int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, bool multi,
 int chess_items_launch_tri(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 // -a 7 over the upper triangle (compare_tri7.cuh)
 int chess_items_launch_tri7(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+// -a 3 / -a 5 over the upper triangle (compare_triw.cuh)
+int chess_items_launch_triw(chess_ctx *ctx, chess_item_args &a, int G, int H, cudaStream_t stream);
 
 // Internal launchers (one per translation unit).
 int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const double *qry_base,

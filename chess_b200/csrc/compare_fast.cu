@@ -561,8 +561,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   }
   // -r 1 over the upper triangle when both samples carry their row prefix sums (kernel = 3 keeps the
   // full-square walk for A/B runs)
-  const bool tri7 = windowed && H == 3;
-  const int tri_G = ((r1 || tri7) && p.kernel != 3 && ref->rowpre && qry->rowpre) ? tri_strip_width(max_n) : 0;
+  const int tri_G = ((r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre) ? tri_strip_width(max_n) : 0;
   const bool tri = tri_G != 0;
   if (tri) G = tri_G;
   const int ncol_pad = ((max_n + 31) / 32) * 32;
@@ -621,7 +620,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     const int hh = r1 ? 0 : H;
     const bool multi = max_n > 31 * G;
     if (tri && r1) rc = chess_items_launch_tri(ctx, a, G, stream);
-    else if (tri) rc = chess_items_launch_tri7(ctx, a, G, stream);
+    else if (tri && H == 3) rc = chess_items_launch_tri7(ctx, a, G, stream);
+    else if (tri) rc = chess_items_launch_triw(ctx, a, G, H, stream);
     else if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, multi, stream);
     else if (hh == 1) rc = chess_items_launch_h1(ctx, a, G, multi, stream);
     else if (hh == 2) rc = chess_items_launch_h2(ctx, a, G, multi, stream);

@@ -1,0 +1,439 @@
+// The -a 3 / -a 5 work-item kernel over the upper triangle: compare_tri.cuh's three packed row bands
+// with the loop of win_rows<G, H> (compare_kernels.cuh; separate running sums for the 2H+1 SSIM window
+// and the 7x7 SN window, both fed from one ring of x and y).  Weights as in compare_tri7.cuh.
+#pragma once
+#include "compare_tri.cuh"
+
+namespace {
+
+template <int G, int H>
+__global__ void __launch_bounds__(128, (G <= 4 ? 3 : 2))
+compare_win_tri_kernel(chess_item_args a) {
+  static_assert(H == 1 || H == 2, "window 3 or 5 (window 7 has its own kernel)");
+  __shared__ int s_susp[4][kSuspCap];
+  __shared__ int s_susp_n[4];
+  extern __shared__ __align__(16) double ringbuf[];  // per warp: 7 rows of x and y, 7*2*G*32 doubles
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int *susp = s_susp[warp];
+  int *susp_n = &s_susp_n[warp];
+  constexpr int RING = 7 * 2 * G * 32;
+  double *myring = ringbuf + (size_t)warp * RING + lane;
+  const int NCOL = a.ncol_pad;
+  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
+  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) +
+                                                          (size_t)4 * NCOL) + (size_t)warp * NCOL;
+  const chess_params &p = a.p;
+  const double qnan = CUDART_NAN;
+  const bool use_masks = p.mappability_cutoff > 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
+  const long long n_items = a.n_pairs * 2;
+
+  while (true) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(a.counter_cur, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const long long pi = item >> 1;
+    const int part = (int)(item & 1);
+    const chess_pair d = a.pairs[pi];
+    int status = CHESS_PAIR_OK;
+    if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
+    else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
+    else if (d.ref_n != d.qry_n || d.ref_n > 31 * G || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
+    if (status != CHESS_PAIR_OK) {
+      if (part == 0 && lane == 0) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = status;
+        if (status == CHESS_PAIR_RETRY) atomicOr(a.retry_cur, 1);
+      }
+      continue;
+    }
+    const int n = d.ref_n, flip = d.flip;
+    const double *R = a.ref_band + d.ref_off;
+    const double *Q = a.qry_band + d.qry_off;
+    const size_t rp = (size_t)d.ref_pitch, qp = (size_t)d.qry_pitch;
+    const long long Wr = d.ref_pitch / 2 + 1, Wq = d.qry_pitch / 2 + 1;
+    const int i0r = (int)((d.ref_off - (Wr - 1)) / (2 * Wr - 1));
+    const int i0q = (int)((d.qry_off - (Wq - 1)) / (2 * Wq - 1));
+
+    // ---- predicted masks -> cutoff test -> compaction map (both items of a pair repeat this; O(n))
+    int np_ = n, tot_r = 0, tot_q = 0, tot_one_sided = 0;
+    if (use_masks) {
+      for (int base = 0; base < n; base += 32) {
+        const int c = base + lane;
+        bool fr = false, fq = false;
+        if (c < n) {
+          const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
+          fr = __ldg(a.ref_lo + jr) < i0r && __ldg(a.ref_hi + jr) >= i0r + n;
+          fq = __ldg(a.qry_lo + jq) < i0q && __ldg(a.qry_hi + jq) >= i0q + n;
+          mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+        }
+        tot_r += __popc(__ballot_sync(0xffffffffu, fr));
+        tot_q += __popc(__ballot_sync(0xffffffffu, fq));
+        tot_one_sided += __popc(__ballot_sync(0xffffffffu, fr != fq));
+      }
+      if ((double)tot_r / (double)n > p.mappability_cutoff || (double)tot_q / (double)n > p.mappability_cutoff) {
+        if (part == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_UNMAPPABLE; }
+        continue;
+      }
+    }
+    __syncwarp();
+    if (use_masks && !p.keep_unmappable && (tot_r + tot_q) > 0) {
+      int carry = 0;
+      for (int base = 0; base < n; base += 32) {
+        const int c = base + lane;
+        const bool keep = c < n && mflag[c] == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) kmap[carry + __popc(bal & ((1u << lane) - 1u))] = (short)c;
+        carry += __popc(bal);
+      }
+      np_ = carry;
+    } else {
+      for (int c = lane; c < n; c += 32) kmap[c] = (short)c;
+    }
+    if (lane == 0) *susp_n = 0;
+    __syncwarp();
+
+    const int win = 2 * H + 1;
+    if (win > np_) {
+      if (part == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      continue;
+    }
+    const int m = np_ - win + 1;
+    const bool with_sn = p.compute_sn != 0;
+
+    // ---- data range from the running extrema (see compare_kernels.cuh), else min / max in the loop
+    bool inloop_minmax = true;
+    double xmax = -CUDART_INF, xmin = CUDART_INF;
+    if (a.ref_pmax != nullptr) {
+      for (int r = lane; r < n; r += 32) {
+        const size_t ir = (size_t)(i0r + r) * (size_t)Wr + (size_t)(n - 1 - r);
+        const size_t iq = (size_t)(i0q + r) * (size_t)Wq + (size_t)(n - 1 - r);
+        xmax = fmax(xmax, fmax(__ldg(a.ref_pmax + ir), __ldg(a.qry_pmax + iq)));
+        xmin = fmin(xmin, fmin(__ldg(a.ref_pmin + ir), __ldg(a.qry_pmin + iq)));
+      }
+      xmax = warp_max(xmax);
+      xmin = warp_min(xmin);
+      inloop_minmax = np_ < n && (tot_one_sided > 0 || !(xmax > p.default_value && xmin < p.default_value));
+    }
+    if (inloop_minmax) {
+      // C1 / C2 are needed before the first window: scan the whole pair once (rare: a bin masked in one
+      // matrix only, or a default value that could be the extreme)
+      double bmax = -CUDART_INF, bmin = CUDART_INF;
+      for (int r = 0; r < np_; ++r) {
+        const int kr = kmap[r];
+        const double *rowR = R + (size_t)kr * rp;
+        const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
+        for (int c = r + lane; c < np_; c += 32) {   // the upper triangle holds every value
+          const int kc = kmap[c];
+          const double x = __ldg(rowR + kc), y = __ldg(rowQ + (flip ? n - 1 - kc : kc));
+          bmax = fmax(bmax, fmax(x, y)); bmin = fmin(bmin, fmin(x, y));
+        }
+      }
+      xmax = warp_max(bmax); xmin = warp_min(bmin);
+    }
+    const double drange = xmax - xmin;
+    const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
+
+    // ---- this item's lanes: rows [lo, hi), first column cbase
+    int B1, B2, L1, L2;
+    tri_split(np_, G, B1, B2, L1, L2);
+    int lo = 0, hi = 0, cbase = 1 << 20;
+    if (part == 0) {
+      lo = 0; hi = B1; cbase = G * lane;
+    } else if (lane < L1) {
+      lo = B1; hi = B2; cbase = B1 - 3 + G * lane;
+    } else if (lane > L1 && lane <= L1 + L2) {
+      lo = B2; hi = np_; cbase = B2 - 3 + G * (lane - L1 - 1);
+    }
+    const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
+    unsigned xo[G], yo[G];
+    bool valid[G];
+    double wc[G];   // column weight: 0 halo / missing, 1 inside the band's diagonal block, 2 right of it
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int c = cbase + g;
+      valid[g] = c < np_;
+      wc[g] = (!valid[g] || c < lo) ? 0.0 : (c < hi ? 1.0 : 2.0);
+      const int kc = valid[g] ? (int)kmap[c] : 0;
+      xo[g] = (unsigned)kc;
+      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
+    }
+    double *rec = a.scratch + ((size_t)pi * 2 + part) * kTriRec;
+    double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
+    bool overflow = false;
+
+    if (rows_max > 0) {
+      const int first = part == 0 ? 0 : max(lo - 3, 0);          // idle lanes have lo = 0
+      const int t_emit0 = part == 0 ? 3 : 6;                      // first iteration with a complete window
+      const int T = rows_max + (part == 0 ? 3 : 6);
+      constexpr int WIN = 2 * H + 1;
+      const double inv_np = 1.0 / (double)(WIN * WIN);
+      const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
+      double ccnt[G], wss[G];
+      double Sd[G], Se[G], Vx[G], Vy[G], Vxx[G], Vyy[G], Vxy[G];
+      unsigned hist[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = cbase + g;
+        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+        wss[g] = (c >= H && c <= np_ - 1 - H) ? wc[g] : 0.0;      // SSIM windows need H columns either side
+        Sd[g] = Se[g] = Vx[g] = Vy[g] = Vxx[g] = Vyy[g] = Vxy[g] = 0.0;
+        hist[g] = 0u;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+      }
+      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+      int slot = 0;
+      double xn[G], yn[G];
+      auto fetch = [&](int row) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
+        if (row < np_) {
+          const unsigned kr = (unsigned)kmap[row];
+          const unsigned ro = kr * (unsigned)rp;
+          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
+          }
+        }
+      };
+      int row = first;
+      fetch(row);
+      for (int t = 0; t < T; ++t, ++row) {
+        double x[G], y[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
+        if (t + 1 < T) fetch(row + 1);
+        // ring positions of the rows that leave the 7-row and the WIN-row windows
+        const int s7 = slot;                                               // row - 7 (about to be overwritten)
+        const int sw = slot + 7 - WIN >= 7 ? slot - WIN : slot + 7 - WIN;  // row - WIN
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
+          const double xow = myring[((sw * G + g) * 2) * 32], yow = myring[((sw * G + g) * 2 + 1) * 32];
+          myring[((slot * G + g) * 2) * 32] = x[g];
+          myring[((slot * G + g) * 2 + 1) * 32] = y[g];
+          const double dv = x[g] - y[g], dold = xo7 - yo7;
+          Sd[g] += dv; Sd[g] -= dold;
+          Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+          hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
+          Se[g] = hist[g] == 0u ? 0.0 : Se[g];
+          Vx[g] += x[g]; Vx[g] -= xow;
+          Vy[g] += y[g]; Vy[g] -= yow;
+          Vxx[g] = fma(x[g], x[g], Vxx[g]); Vxx[g] = fma(-xow, xow, Vxx[g]);
+          Vyy[g] = fma(y[g], y[g], Vyy[g]); Vyy[g] = fma(-yow, yow, Vyy[g]);
+          Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
+        }
+        slot = slot == 6 ? 0 : slot + 1;
+
+        // ---- SSIM windows whose centre row is row - H
+        if (t >= t_emit0 - (3 - H)) {
+          const int rcs = row - H;
+          const bool ssim_row = rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H;
+          double W5[5][G];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vxx : q == 3 ? Vyy : Vxy;
+            double P[G + 1];
+            P[0] = 0.0; P[1] = V[0];
+#pragma unroll
+            for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
+            double up[H], dn[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
+              up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
+              dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int a0 = g - H < 0 ? 0 : g - H;
+              const int b0 = g + H > G - 1 ? G - 1 : g + H;
+              double w = a0 == 0 ? P[b0 + 1] : P[b0 + 1] - P[a0];
+              if (g - H < 0) w += up[H - 1 - g];
+              if (g + H > G - 1) w += dn[g + H - G];
+              W5[q][g] = w;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const double ux = W5[0][g] * inv_np, uy = W5[1][g] * inv_np;
+            const double uxx = W5[2][g] * inv_np, uyy = W5[3][g] * inv_np, uxy = W5[4][g] * inv_np;
+            const double vx = cov_norm * fma(-ux, ux, uxx);
+            const double vy = cov_norm * fma(-uy, uy, uyy);
+            const double vxy = cov_norm * fma(-ux, uy, uxy);
+            const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
+            const double B1s = fma(ux, ux, fma(uy, uy, C1)), B2s = vx + vy + C2;
+            const double den = B1s * B2s;
+            const double num = A1 * A2;
+            double S = num * fast_rcp(den);
+            if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
+            if (ssim_row && wss[g] != 0.0) ss_sum = fma(wss[g], S, ss_sum);
+          }
+        }
+
+        // ---- SN pixels of row - 3
+        if (with_sn && t >= t_emit0) {
+          const int rc = row - 3;
+          const bool emit_row = rc >= lo && rc < hi;
+          const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+          double P1[G + 1], P2[G + 1];
+          P1[0] = 0.0; P2[0] = 0.0;
+          P1[1] = Sd[0]; P2[1] = Se[0];
+#pragma unroll
+          for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+          double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
+            const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+            up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+            up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+            dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+            dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int a0 = g - 3 < 0 ? 0 : g - 3;
+            const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
+            double w1 = a0 == 0 ? P1[b0 + 1] : P1[b0 + 1] - P1[a0];
+            double w2 = a0 == 0 ? P2[b0 + 1] : P2[b0 + 1] - P2[a0];
+            if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+            if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+            const bool own = emit_row & (wc[g] != 0.0);
+            const double cnt = rcnt * ccnt[g];
+            const double m2 = w2 * cnt;
+            const double den = fma(-w1, w1, m2);
+            const bool good = own & (den > fma(m2, 1e-6, 1e-290));
+            const double gq = fabs(w1) * cnt * fast_rcp(den);
+            sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
+            sn_cnt += good ? wc[g] : 0.0;
+            if (!good && own && w2 != 0.0) {
+              const int e = atomicAdd(susp_n, 1);
+              if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+            }
+          }
+        }
+      }
+      if (with_sn) {
+        __syncwarp();
+        const int ns = *susp_n;
+        if (ns > 0 && ns <= kSuspCap) {  // cold: numpy's two passes for the cancelled windows
+          if (lane == 0) {               // fixed order, so the additions are reproducible
+            for (int i = 1; i < ns; ++i) {
+              const int key = susp[i];
+              int j = i - 1;
+              while (j >= 0 && susp[j] > key) { susp[j + 1] = susp[j]; --j; }
+              susp[j + 1] = key;
+            }
+          }
+          __syncwarp();
+          for (int e = lane; e < ns; e += 32) {
+            const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
+            const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                        (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+            const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+            const int band_hi = part == 0 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
+            if (gq == gq) { sn_sum += c >= band_hi ? gq + gq : gq; sn_cnt += c >= band_hi ? 2.0 : 1.0; }
+          }
+        } else if (ns > kSuspCap) {
+          overflow = true;               // too many: the generic kernel redoes the pair exactly
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- record of this item
+    {
+      const double ss = warp_sum(sn_sum);
+      const double sc = warp_sum(sn_cnt);
+      const double sw = warp_sum(ss_sum);
+      if (lane == 0) {
+        rec[5] = xmax; rec[6] = xmin; rec[7] = ss; rec[8] = sc;
+        rec[14] = overflow ? 1.0 : 0.0;
+        rec[15] = sw;
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(a.done + pi, 1);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != 1) continue;
+
+    // ---- second item to arrive: verify the predicted masks, combine, write the result
+    __threadfence();
+    const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
+    bool bad = __ldcg(recs + 14) != 0.0 || __ldcg(recs + kTriRec + 14) != 0.0;
+    if (use_masks) {
+      const double target = (double)n * p.default_value;
+      for (int c = lane; c < np_; c += 32) {
+        const int kc = kmap[c];
+        if (!(mflag[kc] & 1)) {
+          const double *pr = a.ref_pre + (size_t)(i0r + kc) * (size_t)(2 * Wr) + (size_t)(Wr - 1 - kc);
+          const double sr = __ldg(pr + n) - __ldg(pr);
+          if (fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
+            double s2 = 0.0;  // the reference's own order: rows 0 .. n-1 of the uncompacted matrix
+            for (int r = 0; r < n; ++r) s2 += __ldg(R + (size_t)r * rp + kc);
+            bad |= s2 == target;
+          }
+        }
+        if (!(mflag[kc] & 2)) {
+          const int cq = flip ? n - 1 - kc : kc;
+          const double *pq = a.qry_pre + (size_t)(i0q + cq) * (size_t)(2 * Wq) + (size_t)(Wq - 1 - cq);
+          const double sq = __ldg(pq + n) - __ldg(pq);
+          if (fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
+            double s2 = 0.0;
+            for (int r = 0; r < n; ++r) s2 += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
+            bad |= s2 == target;
+          }
+        }
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      if (bad) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+        atomicOr(a.retry_cur, 1);
+      } else {
+        const double ss = __ldcg(recs + 7) + __ldcg(recs + kTriRec + 7);
+        const double sc = __ldcg(recs + 8) + __ldcg(recs + kTriRec + 8);
+        const double sm = __ldcg(recs + 15) + __ldcg(recs + kTriRec + 15);
+        a.ssim[pi] = sm / ((double)m * (double)m);
+        a.sn[pi] = with_sn ? ss / sc : CUDART_NAN;
+        a.status[pi] = CHESS_PAIR_OK;
+      }
+      a.done[pi] = 0;
+    }
+  }
+}
+
+template <int G, int H>
+int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+  auto kern = compare_win_tri_kernel<G, H>;
+  constexpr int RING = 7 * 2 * G * 32;
+  const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
+  const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 256 * 3;
+  static bool configured[64] = {false};
+  if (ctx->device >= 64 || !configured[ctx->device]) {
+    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    if (ctx->device < 64) configured[ctx->device] = true;
+  }
+  static int per_sm = 0, per_sm_ncol = -1;
+  if (per_sm_ncol != a.ncol_pad) {
+    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    per_sm_ncol = a.ncol_pad;
+  }
+  long long grid = (long long)ctx->sm_count * per_sm;
+  const long long need = (a.n_pairs * 2 + 3) / 4;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+}  // namespace
