@@ -516,13 +516,14 @@ extern "C" int chess_band_prefix_build(chess_ctx *ctx, const double *band, int64
 }
 
 // smallest strip width whose triangle split (compare_tri.cuh: tri_split) fits the warp, 0 if none
-static int tri_strip_width(int n) {
-  static const int g_min = getenv("CHESS_TRI_G") ? atoi(getenv("CHESS_TRI_G")) : 3;  // experiments only
+static int tri_strip_width(int n, int halo = 3) {
+  static const int g_env = getenv("CHESS_TRI_G") ? atoi(getenv("CHESS_TRI_G")) : 3;  // experiments only
+  const int g_min = g_env > halo ? g_env : halo;  // a window may reach into one neighbour lane only
   for (int G = g_min < 3 ? 3 : g_min; G <= 8; ++G) {
     if (n > 31 * G || n < 24) continue;
-    const int x = (n - 3) / 3;
+    const int x = (n - halo) / 3;
     const int b1 = n - 2 * x, b2 = n - x;
-    const int l1 = (n - (b1 - 3) + G - 1) / G, l2 = (n - (b2 - 3) + G - 1) / G;
+    const int l1 = (n - (b1 - halo) + G - 1) / G, l2 = (n - (b2 - halo) + G - 1) / G;
     if (l1 + l2 <= 30) return G;
   }
   return 0;
@@ -540,7 +541,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     const int w = window_rule(0, p.abs_window, 1.0);
     H = (w - 1) / 2;
   }
-  const bool windowed = p.abs_window > 0 && H >= 1 && H <= 3 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
+  // windows 3 / 5 / 7 have a full-square and a triangle kernel, 9 / 11 the triangle kernel only
+  const bool windowed = p.abs_window > 0 && H >= 1 && H <= 5 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
   // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
   if (!(r1 || windowed) || !plain_default || max_n > 1024 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
@@ -561,8 +563,10 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   }
   // -r 1 over the upper triangle when both samples carry their row prefix sums (kernel = 3 keeps the
   // full-square walk for A/B runs)
-  const int tri_G = ((r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre) ? tri_strip_width(max_n) : 0;
+  const int tri_G = ((r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre)
+                        ? tri_strip_width(max_n, H > 3 ? H : 3) : 0;
   const bool tri = tri_G != 0;
+  if (H > 3 && !tri) return CHESS_OK;  // the generic kernel takes it
   if (tri) G = tri_G;
   const int ncol_pad = ((max_n + 31) / 32) * 32;
   const size_t stride = tri ? (size_t)16 : items_stride(ncol_pad);

@@ -38,6 +38,19 @@ __host__ __device__ __forceinline__ bool tri_split(int np_, int G, int &B1, int 
   return true;
 }
 
+// the same split with a halo of `halo` >= 3 rows / columns around every band (SSIM windows 9 and 11)
+__host__ __device__ __forceinline__ bool tri_split_halo(int np_, int G, int halo, int &B1, int &B2, int &L1,
+                                                        int &L2) {
+  B1 = np_; B2 = np_; L1 = 0; L2 = 0;
+  if (np_ < 24) return false;
+  const int x = (np_ - halo) / 3;
+  const int b1 = np_ - 2 * x, b2 = np_ - x;
+  const int l1 = (np_ - (b1 - halo) + G - 1) / G, l2 = (np_ - (b2 - halo) + G - 1) / G;
+  if (l1 + l2 > 30) return false;
+  B1 = b1; B2 = b2; L1 = l1; L2 = l2;
+  return true;
+}
+
 template <int G, bool WITH_SN>
 __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2))
 compare_r1_tri_kernel(chess_item_args a) {

@@ -1,6 +1,8 @@
-// The -a 3 / -a 5 work-item kernel over the upper triangle: compare_tri.cuh's three packed row bands
-// with the loop of win_rows<G, H> (compare_kernels.cuh; separate running sums for the 2H+1 SSIM window
-// and the 7x7 SN window, both fed from one ring of x and y).  Weights as in compare_tri7.cuh.
+// The -a 3 / 5 / 9 / 11 work-item kernel over the upper triangle: compare_tri.cuh's three packed row
+// bands with the loop of win_rows<G, H> (compare_kernels.cuh; separate running sums for the 2H+1 SSIM
+// window and the 7x7 SN window, both fed from one ring of x and y).  Weights as in compare_tri7.cuh.
+// Windows 9 and 11 widen the halo around a band to H rows / columns and need strips of G >= H columns,
+// so that a window still reaches into one neighbour lane only.
 #pragma once
 #include "compare_tri.cuh"
 
@@ -9,15 +11,17 @@ namespace {
 template <int G, int H>
 __global__ void __launch_bounds__(128, (G <= 4 ? 3 : 2))
 compare_win_tri_kernel(chess_item_args a) {
-  static_assert(H == 1 || H == 2, "window 3 or 5 (window 7 has its own kernel)");
+  static_assert((H == 1 || H == 2 || H == 4 || H == 5) && G >= H, "window 3 / 5 / 9 / 11 (window 7 has its own kernel)");
+  constexpr int HALO = H > 3 ? H : 3;           // halo rows / columns around a band: the wider of the two windows
+  constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;  // ring depth in rows
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
-  extern __shared__ __align__(16) double ringbuf[];  // per warp: 7 rows of x and y, 7*2*G*32 doubles
+  extern __shared__ __align__(16) double ringbuf[];  // per warp: D rows of x and y, D*2*G*32 doubles
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int *susp = s_susp[warp];
   int *susp_n = &s_susp_n[warp];
-  constexpr int RING = 7 * 2 * G * 32;
+  constexpr int RING = D * 2 * G * 32;
   double *myring = ringbuf + (size_t)warp * RING + lane;
   const int NCOL = a.ncol_pad;
   short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
@@ -137,14 +141,14 @@ compare_win_tri_kernel(chess_item_args a) {
 
     // ---- this item's lanes: rows [lo, hi), first column cbase
     int B1, B2, L1, L2;
-    tri_split(np_, G, B1, B2, L1, L2);
+    tri_split_halo(np_, G, HALO, B1, B2, L1, L2);
     int lo = 0, hi = 0, cbase = 1 << 20;
     if (part == 0) {
       lo = 0; hi = B1; cbase = G * lane;
     } else if (lane < L1) {
-      lo = B1; hi = B2; cbase = B1 - 3 + G * lane;
+      lo = B1; hi = B2; cbase = B1 - HALO + G * lane;
     } else if (lane > L1 && lane <= L1 + L2) {
-      lo = B2; hi = np_; cbase = B2 - 3 + G * (lane - L1 - 1);
+      lo = B2; hi = np_; cbase = B2 - HALO + G * (lane - L1 - 1);
     }
     const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
     unsigned xo[G], yo[G];
@@ -164,9 +168,9 @@ compare_win_tri_kernel(chess_item_args a) {
     bool overflow = false;
 
     if (rows_max > 0) {
-      const int first = part == 0 ? 0 : max(lo - 3, 0);          // idle lanes have lo = 0
-      const int t_emit0 = part == 0 ? 3 : 6;                      // first iteration with a complete window
-      const int T = rows_max + (part == 0 ? 3 : 6);
+      const int first = part == 0 ? 0 : max(lo - HALO, 0);       // idle lanes have lo = 0
+      const int t_own0 = part == 0 ? 0 : HALO;                    // iteration of the band's first own row
+      const int T = rows_max + (part == 0 ? HALO : 2 * HALO);
       constexpr int WIN = 2 * H + 1;
       const double inv_np = 1.0 / (double)(WIN * WIN);
       const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
@@ -181,7 +185,7 @@ compare_win_tri_kernel(chess_item_args a) {
         Sd[g] = Se[g] = Vx[g] = Vy[g] = Vxx[g] = Vyy[g] = Vxy[g] = 0.0;
         hist[g] = 0u;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+        for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
       }
       const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
       int slot = 0;
@@ -207,8 +211,8 @@ compare_win_tri_kernel(chess_item_args a) {
         for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
         if (t + 1 < T) fetch(row + 1);
         // ring positions of the rows that leave the 7-row and the WIN-row windows
-        const int s7 = slot;                                               // row - 7 (about to be overwritten)
-        const int sw = slot + 7 - WIN >= 7 ? slot - WIN : slot + 7 - WIN;  // row - WIN
+        const int s7 = slot + D - 7 >= D ? slot - 7 : slot + D - 7;        // row - 7
+        const int sw = slot + D - WIN >= D ? slot - WIN : slot + D - WIN;  // row - WIN
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
@@ -226,10 +230,10 @@ compare_win_tri_kernel(chess_item_args a) {
           Vyy[g] = fma(y[g], y[g], Vyy[g]); Vyy[g] = fma(-yow, yow, Vyy[g]);
           Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
         }
-        slot = slot == 6 ? 0 : slot + 1;
+        slot = slot == D - 1 ? 0 : slot + 1;
 
         // ---- SSIM windows whose centre row is row - H
-        if (t >= t_emit0 - (3 - H)) {
+        if (t >= t_own0 + H) {
           const int rcs = row - H;
           const bool ssim_row = rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H;
           double W5[5][G];
@@ -275,7 +279,7 @@ compare_win_tri_kernel(chess_item_args a) {
         }
 
         // ---- SN pixels of row - 3
-        if (with_sn && t >= t_emit0) {
+        if (with_sn && t >= t_own0 + 3) {
           const int rc = row - 3;
           const bool emit_row = rc >= lo && rc < hi;
           const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
@@ -413,7 +417,8 @@ compare_win_tri_kernel(chess_item_args a) {
 template <int G, int H>
 int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   auto kern = compare_win_tri_kernel<G, H>;
-  constexpr int RING = 7 * 2 * G * 32;
+  constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;
+  constexpr int RING = D * 2 * G * 32;
   const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
   const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 256 * 3;
   static bool configured[64] = {false};

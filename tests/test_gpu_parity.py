@@ -420,7 +420,9 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
                for pid, r, q in pairs[::5]]
     for kw in (dict(), dict(keep_unmappable_bins=True), dict(mappability_cutoff=0.3), dict(compute_sn=False),
                dict(absolute_window_size=7), dict(absolute_window_size=5, mappability_cutoff=0.3),
-               dict(absolute_window_size=3, compute_sn=False), dict(absolute_window_size=8, keep_unmappable_bins=True)):
+               dict(absolute_window_size=3, compute_sn=False), dict(absolute_window_size=8, keep_unmappable_bins=True),
+               dict(absolute_window_size=9), dict(absolute_window_size=11, mappability_cutoff=0.3),
+               dict(absolute_window_size=12, compute_sn=False)):
         for plist in (pairs, flipped):
             gen = eng.compare(plist, kernel=1, **kw)
             # 0: work-item kernels (-r 1: upper triangle), 3: full-square work-item kernel, 2: CTA-per-pair kernel
@@ -434,7 +436,8 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
     # ... and 300 / 400 / 640 bins are swept in two or three column blocks
     for window_bp in (1000000, 2600000, 3500000, 4400000, 5000000, 7500000, 10000000, 16000000):
         plist = synth.sliding_pairs(genome, window_bp, 900000 if window_bp <= 5000000 else 2900000)
-        for kw in (dict(), dict(absolute_window_size=7)):
+        for kw in (dict(), dict(absolute_window_size=7), dict(absolute_window_size=5), dict(absolute_window_size=9),
+                   dict(absolute_window_size=11)):
             gen = eng.compare(plist, kernel=1, **kw)
             for kernel in (0, 3, 2):
                 fast = eng.compare(plist, kernel=kernel, **kw)
