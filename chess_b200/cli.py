@@ -60,6 +60,77 @@ class Chess(object):
         args = commands.sim_parser().parse_args(argv[2:])
         run_sim(args)
 
+    def oe(self, argv):
+        """bin/chess:360-380: O/E of a sparse-format matrix, values written with six decimals."""
+        args = commands.oe_parser().parse_args(argv[2:])
+        import gzip
+        from .oe import observed_expected
+        from .helpers import is_gzipped
+        _, edges = observed_expected(args.regions, args.input_matrix)
+        text = "".join("{}\t{}\t{:.6e}\n".format(a, b, w) for a, b, w in edges)
+        if is_gzipped(args.output_matrix):
+            with gzip.open(args.output_matrix, 'w') as o:
+                o.write(text.encode('utf-8'))
+        else:
+            with open(args.output_matrix, 'w') as o:
+                o.write(text)
+
+    @staticmethod
+    def _checked_output(path):
+        output_dir = os.path.dirname(path)
+        if output_dir != '' and not os.path.exists(output_dir):
+            logger.error("Specified output directory does not exist!")
+            raise RuntimeError("Specified output path not found.")
+        return path
+
+    @staticmethod
+    def _ucsc_sizes(genome):
+        """pybedtools' chromosome-size table if that package is there (bin/chess:414-432)."""
+        try:
+            import pybedtools as pbt  # third-party, optional
+        except ImportError:
+            raise ValueError("pybedtools is not installed")
+        sizes = pbt.chromsizes(genome)
+        if len(sizes) == 0:
+            raise ValueError("Genome not recognised in pybedtools.chromsizes: {}".format(genome))
+        return {k: v[1] for k, v in sizes.items()}
+
+    def pairs(self, argv):
+        """bin/chess:382-458."""
+        args = commands.pairs_parser().parse_args(argv[2:])
+        from . import emit
+        self._checked_output(args.output)
+        if args.file_input:
+            sizes = emit.load_chromosome_sizes(args.genome)
+        else:
+            try:
+                sizes = self._ucsc_sizes(args.genome)
+            except (OSError, ValueError):
+                logger.info('No entry found with pybedtools. Trying to read from file.')
+                sizes = emit.load_chromosome_sizes(args.genome)
+        emit.write_pairs(args.output, sizes, args.window, args.step, args.chromosome)
+
+    def background(self, argv):
+        """bin/chess:460-518."""
+        args = commands.background_parser().parse_args(argv[2:])
+        from . import emit
+        from .helpers import read_chromosome_sizes, GenomicRegion
+        self._checked_output(args.output)
+        if args.strand not in ['-', '+', None]:
+            raise ValueError("--strand must be either - or +")
+        try:
+            sizes = self._ucsc_sizes(args.genome_or_region)
+            regions = [(c, 1, end) for c, end in sizes.items()]
+        except ValueError:
+            logger.info('No entry found with pybedtools. Trying to read from file.')
+            if os.path.exists(args.genome_or_region):
+                sizes = read_chromosome_sizes(args.genome_or_region)
+                regions = [(c, 1, end) for c, end in sizes.items()]
+            else:
+                region = GenomicRegion.from_string(args.genome_or_region)
+                regions = [(region.chromosome, region.start, region.end)]
+        emit.write_background(args.output, regions, args.window, args.step, args.strand)
+
 
 def _zscores(ssim):
     """z_ssim over the run; bin/chess:216-233 (nanmean / nanstd, ddof 0)."""

@@ -27,6 +27,9 @@ def chess_parser():
 
         Commands:
             sim             Calculate structural similarity (B200 engine)
+            oe              Observed/expected transform of a sparse-format matrix
+            pairs           Sliding-window region pairs for a genome scan (BEDPE)
+            background      Sliding-window background regions (BED)
 
         Run chess <command> -h for help on a specific command.
         '''
@@ -89,4 +92,46 @@ def sim_parser():
                         help='Input contacts are already observed/expected transformed.')
     parser.add_argument('--limit-background', action='store_true', default=False,
                         help='Restrict --background-query to the chromosome of the paired query region.')
+    return parser
+
+
+def oe_parser():
+    """`chess oe`; positionals as chess/commands.py:188-212."""
+    parser = MyParser(description='Observed/expected transform of a balanced matrix in sparse format '
+                                  '(expected values per chromosome and distance, computed on the GPU).',
+                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('input_matrix', type=str, help='Balanced matrix, sparse text format.')
+    parser.add_argument('regions', type=str, help='BED file (no header), one line per matrix bin.')
+    parser.add_argument('output_matrix', type=str, help='Output matrix, same format (gzipped if it ends in .gz).')
+    return parser
+
+
+def pairs_parser():
+    """`chess pairs`; positionals and flags as chess/commands.py:215-262."""
+    parser = MyParser(description='Write every position of a sliding window over a genome as a region pair '
+                                  '(reference = query) in the 10-column BEDPE format `chess sim` reads.',
+                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('genome', type=str,
+                        help='Tab- or space-separated chromosome sizes file (<name> <size>). A UCSC genome name '
+                             'is looked up with pybedtools only if that package is installed.')
+    parser.add_argument('window', type=int, help='Window size in base pairs')
+    parser.add_argument('step', type=int, help='Step size in base pairs')
+    parser.add_argument('output', type=str, help='Path to output file')
+    parser.add_argument('--file-input', action='store_true', default=False,
+                        help='Treat `genome` as a file without trying pybedtools first.')
+    parser.add_argument('--chromosome', type=str, help='Write pairs for this chromosome only.')
+    return parser
+
+
+def background_parser():
+    """`chess background`; positionals and flags as chess/commands.py:265-301."""
+    parser = MyParser(description='Write sliding-window regions for the background model of `chess sim` (BED).',
+                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('genome_or_region', type=str,
+                        help='Chromosome sizes file (<name><TAB><size>), or a region <chromosome>:<start>-<end>; '
+                             'a UCSC genome name only if pybedtools is installed.')
+    parser.add_argument('window', type=int, help='Window size in base pairs')
+    parser.add_argument('step', type=int, help='Step size in base pairs')
+    parser.add_argument('output', type=str, help='Path to output file')
+    parser.add_argument('--strand', type=str, help='[+/-] Regions on this strand only. Default: both strands')
     return parser

@@ -760,3 +760,15 @@ def test_sparse_text_parser_on_device(cb, tmp_path):
     assert parse_sparse_text(b"")[3] == 0
     e = parse_sparse_text(b"#only a comment\n")
     assert len(e[0]) == 0 and e[3] == 0
+
+
+def test_cli_oe_matches_reference_file(cb, toy, tmp_path):
+    """`chess oe` (bin/chess:360-380) writes the file the reference writes, character for character."""
+    from chess_b200.cli import Chess
+    out = str(tmp_path / "oe.sparse")
+    Chess(["chess", "oe", toy("ref.sparse"), toy("ref.bed"), out])
+    assert open(out).read() == open(toy("emit_oe.sparse")).read()
+    import gzip
+    out_gz = str(tmp_path / "oe.sparse.gz")
+    Chess(["chess", "oe", toy("ref.sparse"), toy("ref.bed"), out_gz])
+    assert gzip.open(out_gz, "rt").read() == open(toy("emit_oe.sparse")).read()
