@@ -25,7 +25,6 @@ compare_win7_tri_kernel(chess_item_args a) {
                                                           (size_t)4 * NCOL) + (size_t)warp * NCOL;
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
-  const bool use_masks = p.mappability_cutoff > 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
   const long long n_items = a.n_pairs * 2;
 
@@ -34,63 +33,12 @@ compare_win7_tri_kernel(chess_item_args a) {
     if (lane == 0) item = (long long)atomicAdd(a.counter_cur, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    const long long pi = item >> 1;
-    const int part = (int)(item & 1);
-    const chess_pair d = a.pairs[pi];
-    int status = CHESS_PAIR_OK;
-    if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
-    else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
-    else if (d.ref_n != d.qry_n || d.ref_n > 31 * G || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
-    if (status != CHESS_PAIR_OK) {
-      if (part == 0 && lane == 0) {
-        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = status;
-        if (status == CHESS_PAIR_RETRY) atomicOr(a.retry_cur, 1);
-      }
-      continue;
-    }
-    const int n = d.ref_n, flip = d.flip;
-    const double *R = a.ref_band + d.ref_off;
-    const double *Q = a.qry_band + d.qry_off;
-    const size_t rp = (size_t)d.ref_pitch, qp = (size_t)d.qry_pitch;
-    const long long Wr = d.ref_pitch / 2 + 1, Wq = d.qry_pitch / 2 + 1;
-    const int i0r = (int)((d.ref_off - (Wr - 1)) / (2 * Wr - 1));
-    const int i0q = (int)((d.qry_off - (Wq - 1)) / (2 * Wq - 1));
-
-    // ---- predicted masks -> cutoff test -> compaction map (both items of a pair repeat this; O(n))
-    int np_ = n, tot_r = 0, tot_q = 0, tot_one_sided = 0;
-    if (use_masks) {
-      for (int base = 0; base < n; base += 32) {
-        const int c = base + lane;
-        bool fr = false, fq = false;
-        if (c < n) {
-          const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
-          fr = __ldg(a.ref_lo + jr) < i0r && __ldg(a.ref_hi + jr) >= i0r + n;
-          fq = __ldg(a.qry_lo + jq) < i0q && __ldg(a.qry_hi + jq) >= i0q + n;
-          mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
-        }
-        tot_r += __popc(__ballot_sync(0xffffffffu, fr));
-        tot_q += __popc(__ballot_sync(0xffffffffu, fq));
-        tot_one_sided += __popc(__ballot_sync(0xffffffffu, fr != fq));
-      }
-      if ((double)tot_r / (double)n > p.mappability_cutoff || (double)tot_q / (double)n > p.mappability_cutoff) {
-        if (part == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_UNMAPPABLE; }
-        continue;
-      }
-    }
-    __syncwarp();
-    if (use_masks && !p.keep_unmappable && (tot_r + tot_q) > 0) {
-      int carry = 0;
-      for (int base = 0; base < n; base += 32) {
-        const int c = base + lane;
-        const bool keep = c < n && mflag[c] == 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) kmap[carry + __popc(bal & ((1u << lane) - 1u))] = (short)c;
-        carry += __popc(bal);
-      }
-      np_ = carry;
-    } else {
-      for (int c = lane; c < n; c += 32) kmap[c] = (short)c;
-    }
+    TriItem it;
+    if (!tri_item_begin<G>(a, item, lane, kmap, mflag, it)) continue;
+    const long long pi = it.pi;
+    const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
+    const double *R = it.R, *Q = it.Q;
+    const size_t rp = it.rp, qp = it.qp;
     if (lane == 0) *susp_n = 0;
     __syncwarp();
 
@@ -102,20 +50,9 @@ compare_win7_tri_kernel(chess_item_args a) {
     const int m = np_ - win + 1;
     const bool with_sn = p.compute_sn != 0;
 
-    // ---- data range from the running extrema (see compare_kernels.cuh), else min / max in the loop
-    bool inloop_minmax = true;
-    double xmax = -CUDART_INF, xmin = CUDART_INF;
-    if (a.ref_pmax != nullptr) {
-      for (int r = lane; r < n; r += 32) {
-        const size_t ir = (size_t)(i0r + r) * (size_t)Wr + (size_t)(n - 1 - r);
-        const size_t iq = (size_t)(i0q + r) * (size_t)Wq + (size_t)(n - 1 - r);
-        xmax = fmax(xmax, fmax(__ldg(a.ref_pmax + ir), __ldg(a.qry_pmax + iq)));
-        xmin = fmin(xmin, fmin(__ldg(a.ref_pmin + ir), __ldg(a.qry_pmin + iq)));
-      }
-      xmax = warp_max(xmax);
-      xmin = warp_min(xmin);
-      inloop_minmax = np_ < n && (tot_one_sided > 0 || !(xmax > p.default_value && xmin < p.default_value));
-    }
+    // ---- data range from the running extrema, else min / max from the data
+    double xmax, xmin;
+    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);
     if (inloop_minmax) {
       // C1 / C2 are needed before the first window: scan the whole pair once (rare: a bin masked in one
       // matrix only, or a default value that could be the extreme)
@@ -336,31 +273,7 @@ compare_win7_tri_kernel(chess_item_args a) {
     __threadfence();
     const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
     bool bad = __ldcg(recs + 14) != 0.0 || __ldcg(recs + kTriRec + 14) != 0.0;
-    if (use_masks) {
-      const double target = (double)n * p.default_value;
-      for (int c = lane; c < np_; c += 32) {
-        const int kc = kmap[c];
-        if (!(mflag[kc] & 1)) {
-          const double *pr = a.ref_pre + (size_t)(i0r + kc) * (size_t)(2 * Wr) + (size_t)(Wr - 1 - kc);
-          const double sr = __ldg(pr + n) - __ldg(pr);
-          if (fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
-            double s2 = 0.0;  // the reference's own order: rows 0 .. n-1 of the uncompacted matrix
-            for (int r = 0; r < n; ++r) s2 += __ldg(R + (size_t)r * rp + kc);
-            bad |= s2 == target;
-          }
-        }
-        if (!(mflag[kc] & 2)) {
-          const int cq = flip ? n - 1 - kc : kc;
-          const double *pq = a.qry_pre + (size_t)(i0q + cq) * (size_t)(2 * Wq) + (size_t)(Wq - 1 - cq);
-          const double sq = __ldg(pq + n) - __ldg(pq);
-          if (fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
-            double s2 = 0.0;
-            for (int r = 0; r < n; ++r) s2 += __ldg(Q + (size_t)(flip ? n - 1 - r : r) * qp + cq);
-            bad |= s2 == target;
-          }
-        }
-      }
-    }
+    bad |= !tri_masks_hold(a, it, lane, kmap, mflag);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
       if (bad) {
