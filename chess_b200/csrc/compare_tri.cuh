@@ -156,6 +156,24 @@ __device__ __forceinline__ bool tri_extrema(const chess_item_args &a, const TriI
   return it.np_ < n && (it.tot_one_sided > 0 || !(xmax > a.p.default_value && xmin < a.p.default_value));
 }
 
+// Min / max of the compacted pair from the data (rare: a bin masked in one matrix only, or a
+// default value that could be the extreme).  The upper triangle holds every value.
+__device__ __forceinline__ void tri_scan_extrema(const TriItem &it, int lane, const short *kmap, double &xmax,
+                                                 double &xmin) {
+  double bmax = -CUDART_INF, bmin = CUDART_INF;
+  for (int r = 0; r < it.np_; ++r) {
+    const int kr = kmap[r];
+    const double *rowR = it.R + (size_t)kr * it.rp;
+    const double *rowQ = it.Q + (size_t)(it.flip ? it.n - 1 - kr : kr) * it.qp;
+    for (int c = r + lane; c < it.np_; c += 32) {
+      const int kc = kmap[c];
+      const double x = __ldg(rowR + kc), y = __ldg(rowQ + (it.flip ? it.n - 1 - kc : kc));
+      bmax = fmax(bmax, fmax(x, y)); bmin = fmin(bmin, fmin(x, y));
+    }
+  }
+  xmax = warp_max(bmax); xmin = warp_min(bmin);
+}
+
 // Verification of the predicted masks by the item that arrives last: a column that was NOT
 // predicted as masked must not sum to n*default.  The sum is screened with one subtraction in the
 // row-prefix arrays; a hit within 1e-7 is summed exactly in the reference's order (rows 0 .. n-1 of
@@ -237,8 +255,7 @@ compare_r1_tri_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);
-    if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }
+    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
 
     // ---- this item's lanes: rows [lo, hi), first column cbase
     int B1, B2, L1, L2;
@@ -281,7 +298,6 @@ compare_r1_tri_kernel(chess_item_args a) {
     }
 
     double T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
-    double vmax = -CUDART_INF, vmin = CUDART_INF;
     double sn_sum = 0.0;
     int sn_cnt = 0;
     bool overflow = false;
@@ -338,13 +354,6 @@ compare_r1_tri_kernel(chess_item_args a) {
             const double wx = wt * xn[g], wy = wt * yn[g];  // columns that do not exist were fetched as 0
             T0 += wx; T1 += wy;
             T2 = fma(wx, xn[g], T2); T3 = fma(wy, yn[g], T3); T4 = fma(wx, yn[g], T4);
-            if (inloop_minmax) {
-              const bool xgt = xn[g] > yn[g];
-              const double hi2 = xgt ? xn[g] : yn[g];
-              const double lo2 = xgt ? yn[g] : xn[g];
-              vmax = (valid[g] & (hi2 > vmax)) ? hi2 : vmax;
-              vmin = (valid[g] & (lo2 < vmin)) ? lo2 : vmin;
-            }
           }
         }
         if (t + 1 < T) fetch(row + 1);
@@ -435,7 +444,6 @@ compare_r1_tri_kernel(chess_item_args a) {
     // ---- record of this item
     {
       const double t0 = warp_sum(T0), t1 = warp_sum(T1), t2 = warp_sum(T2), t3 = warp_sum(T3), t4 = warp_sum(T4);
-      if (inloop_minmax) { xmax = warp_max(vmax); xmin = warp_min(vmin); }
       const double ss = warp_sum(sn_sum);
       const int sc = warp_sum_int(sn_cnt);
       if (lane == 0) {

@@ -56,23 +56,8 @@ compare_win_tri_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);
-    if (inloop_minmax) {
-      // C1 / C2 are needed before the first window: scan the whole pair once (rare: a bin masked in one
-      // matrix only, or a default value that could be the extreme)
-      double bmax = -CUDART_INF, bmin = CUDART_INF;
-      for (int r = 0; r < np_; ++r) {
-        const int kr = kmap[r];
-        const double *rowR = R + (size_t)kr * rp;
-        const double *rowQ = Q + (size_t)(flip ? n - 1 - kr : kr) * qp;
-        for (int c = r + lane; c < np_; c += 32) {   // the upper triangle holds every value
-          const int kc = kmap[c];
-          const double x = __ldg(rowR + kc), y = __ldg(rowQ + (flip ? n - 1 - kc : kc));
-          bmax = fmax(bmax, fmax(x, y)); bmin = fmin(bmin, fmin(x, y));
-        }
-      }
-      xmax = warp_max(bmax); xmin = warp_min(bmin);
-    }
+    // C1 / C2 are needed before the first window: the rare data scan runs up front
+    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
 
