@@ -389,6 +389,7 @@ compare_r1_tri_kernel(chess_item_args a) {
               dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
             }
             const int d0 = cbase - rc;
+            unsigned suspect = 0u;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               const int a0 = g - 3 < 0 ? 0 : g - 3;
@@ -406,9 +407,15 @@ compare_r1_tri_kernel(chess_item_args a) {
               const double gq = fabs(w1) * cnt * fast_rcp(den);
               sn_sum += good ? (dd > 0 ? gq + gq : gq) : 0.0;
               sn_cnt += good ? (dd > 0 ? 2 : 1) : 0;
-              if (!good && own && w2 != 0.0) {  // rare: cancellation -> exact recompute after the loop
-                const int e = atomicAdd(susp_n, 1);
-                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+              if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
+            }
+            if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                if (suspect & (1u << g)) {
+                  const int e = atomicAdd(susp_n, 1);
+                  if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+                }
               }
             }
           }

@@ -172,6 +172,7 @@ compare_win7_tri_kernel(chess_item_args a) {
             }
           }
           const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+          unsigned suspect = 0u;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             {
@@ -200,7 +201,13 @@ compare_win7_tri_kernel(chess_item_args a) {
               const double gq = fabs(w1) * cnt * fast_rcp(den);
               sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
               sn_cnt += good ? wc[g] : 0.0;
-              if (!good && own && w2 != 0.0) {
+              if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
+            }
+          }
+          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (suspect & (1u << g)) {
                 const int e = atomicAdd(susp_n, 1);
                 if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
               }

@@ -210,6 +210,7 @@ compare_win_tri_kernel(chess_item_args a) {
           P1[1] = Sd[0]; P2[1] = Se[0];
 #pragma unroll
           for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+          unsigned suspect = 0u;
           double up1[3], up2[3], dn1[3], dn2[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
@@ -236,9 +237,15 @@ compare_win_tri_kernel(chess_item_args a) {
             const double gq = fabs(w1) * cnt * fast_rcp(den);
             sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
             sn_cnt += good ? wc[g] : 0.0;
-            if (!good && own && w2 != 0.0) {
-              const int e = atomicAdd(susp_n, 1);
-              if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+            if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
+          }
+          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (suspect & (1u << g)) {
+                const int e = atomicAdd(susp_n, 1);
+                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+              }
             }
           }
         }
