@@ -254,7 +254,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(args, len(pairs), n_bins, sample=len(idx)),
+        "config": {k: v for k, v in workload_config(args, len(pairs), n_bins, sample=len(idx)).items() if k != "l2"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": "%d of %d pairs per step, evenly spaced; oracle/chess_oracle.py (reference "
                                    "algorithm restated: dict-of-dict gather, restated skimage SSIM, reference SN) "
