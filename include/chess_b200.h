@@ -276,6 +276,18 @@ int chess_sparse_text_compact(chess_ctx *ctx, int64_t n_lines, const int32_t *sr
                               int32_t *out_sink, double *out_weight, int64_t out_capacity,
                               int64_t *counts, void *stream);
 
+/* K9: first stage of `chess extract`, chess/get_structures.py:99-121.  ref_base / qry_base are
+ * bands (or dense tiles) built with default value 0 (sub_matrix_from_edges_dict(..., default_weight=0.)).
+ * Per pair k with equal sizes n: OR = log(query / reference), NaN and +-inf -> 0; std = np.std(OR);
+ * positive[k*max_n*max_n + r*n + c] = OR > 0.5 std ? OR : 0, negative = OR < -0.5 std ? -OR : 0
+ * (n*n doubles, row-major, at a stride of max_n*max_n per pair); stats[4k..] = {std, mean(positive),
+ * mean(negative), n}.  status: 0 ok, 1 region not found, 100 the two regions differ in size (numpy
+ * cannot divide them: the reference raises).  No strand handling: the reference has none here.
+ * All pointers DEVICE.                                                                          */
+int chess_log_ratio_batch(chess_ctx *ctx, const double *ref_base, const double *qry_base,
+                          const chess_pair *pairs, int64_t n_pairs, int32_t max_n, double *positive,
+                          double *negative, double *stats, int32_t *status, void *stream);
+
 /* SN(M1, M2, size=7), chess/sim.py:15-30, on n x n DEVICE matrices.          */
 int chess_sn_dense(chess_ctx *ctx, const double *m1, const double *m2, int32_t n, double *out,
                    void *stream);

@@ -639,6 +639,24 @@ def background_regions_from_query(query_regions, query_region, limit_background=
     return out
 
 
+def log_ratio_stage(ref_edges, ref_trees, qry_edges, qry_trees, pair):
+    """Head of `extract_structures`, chess/get_structures.py:99-113 (numpy code restated verbatim):
+    gather with default weight 0, OR = log(query / reference) with NaN / +-inf -> 0, 0.5-std thresholds.
+    Returns (positive, negative, std, mean(positive), mean(negative))."""
+    _, rr, qr = pair
+    reference, _ = sub_matrix_from_edges_dict(ref_edges, ref_trees, rr, default_weight=0.)
+    query, _ = sub_matrix_from_edges_dict(qry_edges, qry_trees, qr, default_weight=0.)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        or_matrix = np.log(np.divide(query, reference))
+    or_matrix[np.isnan(or_matrix)] = 0.
+    or_matrix[or_matrix == -np.inf] = 0.
+    or_matrix[or_matrix == np.inf] = 0.
+    std = np.std(or_matrix)
+    positive = np.where(or_matrix > (0.5 * std), or_matrix, 0.)
+    negative = np.abs(np.where(or_matrix < -(0.5 * std), or_matrix, 0.))
+    return positive, negative, std, np.mean(positive), np.mean(negative)
+
+
 def sim(ref_edges, ref_regions, qry_edges, qry_regions, pairs, background_regions=None,
         background_query=False, limit_background=False, **kw):
     """Serial equivalent of `Chess.sim` after loading (bin/chess:189-353).

@@ -772,3 +772,35 @@ def test_cli_oe_matches_reference_file(cb, toy, tmp_path):
     out_gz = str(tmp_path / "oe.sparse.gz")
     Chess(["chess", "oe", toy("ref.sparse"), toy("ref.bed"), out_gz])
     assert gzip.open(out_gz, "rt").read() == open(toy("emit_oe.sparse")).read()
+
+
+def test_extract_log_ratio_stage(cb, chr2_like):
+    """K9, the head of `chess extract` (get_structures.py:99-121), against the numpy restatement."""
+    from chess_b200.extract import log_ratio_stage
+    genome, regions, trees, re_, qe, pairs, ref, qry = chr2_like
+    pick = pairs[3::97] + [("far", pairs[0][1], cb.GenomicRegion(chromosome="chr2", start=1, end=1000000, strand="+")),
+                           ("gone", pairs[0][1], cb.GenomicRegion(chromosome="chr2", start=10 ** 9, end=10 ** 9 + 10))]
+    got = log_ratio_stage(re_, trees, qe, trees, pick)
+    assert len(got) == len(pick) and got[-1] is None and got[-2] is None     # unequal sizes / not found
+    oregions = [O.Region(r.start, r.end, r.chromosome, ix=r.ix) for r in regions]
+    otrees = O.region_trees(oregions)
+    ore = O.edges_dict(zip(*[x.tolist() for x in re_.triples()]))
+    oqe = O.edges_dict(zip(*[x.tolist() for x in qe.triples()]))
+    checked = 0
+    for (pid, rr, qr), g in zip(pick[:-2], got[:-2]):
+        op = (pid, O.Region(rr.start, rr.end, rr.chromosome, strand=rr.strand),
+              O.Region(qr.start, qr.end, qr.chromosome, strand=qr.strand))
+        pos, neg, std, mp, mn = O.log_ratio_stage(ore, otrees, oqe, otrees, op)
+        assert g[0].shape == pos.shape
+        assert close(g[2], std, 1e-12)
+        # a value within rounding of the threshold may fall on either side (log is not correctly rounded)
+        edge = (np.abs(np.abs(pos + g[0] - np.minimum(pos, g[0])) - 0.5 * std) < 1e-12) | \
+               (np.abs(np.abs(neg + g[1] - np.minimum(neg, g[1])) - 0.5 * std) < 1e-12)
+        assert edge.sum() <= 2
+        np.testing.assert_allclose(g[0][~edge], pos[~edge], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(g[1][~edge], neg[~edge], rtol=1e-12, atol=0)
+        if not edge.any():
+            assert close(g[3], mp, 1e-11) and close(g[4], mn, 1e-11)
+        assert (pos > 0).sum() > 10 and (neg > 0).sum() > 10
+        checked += 1
+    assert checked >= 5
