@@ -804,3 +804,31 @@ def test_extract_log_ratio_stage(cb, chr2_like):
         assert (pos > 0).sum() > 10 and (neg > 0).sum() > 10
         checked += 1
     assert checked >= 5
+
+
+def test_triangle_kernels_every_size(cb, chr2_like):
+    """The three-band split of the triangle kernels changes shape with the matrix size (band
+    boundaries, lanes per band, strip width, fallback to a single band): every size from 20 to 230
+    bins, all window regimes, against the generic kernel."""
+    from chess_b200 import synth
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    regimes = (dict(), dict(compute_sn=False), dict(absolute_window_size=7), dict(absolute_window_size=5),
+               dict(absolute_window_size=3, mappability_cutoff=0.3), dict(absolute_window_size=9),
+               dict(absolute_window_size=11, keep_unmappable_bins=True))
+    worst = 0.0
+    for k, n_bins in enumerate(range(20, 231)):
+        plist = synth.sliding_pairs(genome, (n_bins - 1) * 25000, 4100000 + 25000 * (k % 7))
+        plist = plist[:12]
+        rn = {p[1].end - p[1].start for p in plist}
+        assert len(rn) == 1
+        for kw in (regimes[k % len(regimes)], regimes[(k + 3) % len(regimes)]):
+            gen = eng.compare(plist, kernel=1, **kw)
+            fast = eng.compare(plist, kernel=0, **kw)
+            assert np.array_equal(fast[3], gen[3]), (n_bins, kw)
+            for a, b in ((fast[1], gen[1]), (fast[2], gen[2])):
+                ok = ~np.isnan(b)
+                assert np.array_equal(np.isnan(a), np.isnan(b)), (n_bins, kw)
+                if ok.any():
+                    worst = max(worst, float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-300))))
+    assert worst < 1e-9, worst
