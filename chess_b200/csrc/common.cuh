@@ -55,6 +55,7 @@ struct chess_item_args {
   double *ssim, *sn;
   int *status;
   int ncol_pad;               // columns reserved per pair in maps and records (max n, rounded to 32)
+  int blocks;                 // block-triangle kernel: blocks per matrix side
   double *scratch;            // n_pairs * kBands * (kItemHdr + 2*ncol_pad)
   int *done;                  // n_pairs, zero on entry, zero on exit
   unsigned long long *counter_cur, *counter_next;
@@ -68,6 +69,8 @@ int chess_items_launch_h2(chess_ctx *ctx, chess_item_args &a, int G, bool multi,
 int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, bool multi, cudaStream_t stream);
 // -r 1 over the upper triangle (compare_tri.cuh)
 int chess_items_launch_tri(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+// -r 1, matrices wider than one warp: square blocks on and above the diagonal (compare_blk.cuh)
+int chess_items_launch_blk(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 // -a 7 over the upper triangle (compare_tri7.cuh)
 int chess_items_launch_tri7(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 // -a 3 / -a 5 over the upper triangle (compare_triw.cuh)

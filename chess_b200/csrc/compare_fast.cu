@@ -568,20 +568,34 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   const bool tri = tri_G != 0;
   if (H > 3 && !tri) return CHESS_OK;  // the generic kernel takes it
   if (tri) G = tri_G;
+  // -r 1 on matrices wider than one warp: square blocks on and above the diagonal; strip width and block
+  // count that cost the fewest lane-columns (blocks x rows per block x strip width)
+  int blk_nb = 0;
+  if (!tri && r1 && p.kernel != 3 && ref->rowpre && qry->rowpre && max_n > 93) {
+    long best = -1;
+    for (int g = 5; g <= 8; ++g) {
+      const int nb = (max_n + (31 * g - 6) - 1) / (31 * g - 6);
+      if (nb < 2 || nb > 7) continue;
+      const long cost = (long)(nb * (nb + 1) / 2) * ((max_n + nb - 1) / nb + 6) * g;
+      if (best < 0 || cost < best) { best = cost; G = g; blk_nb = nb; }
+    }
+  }
+  const bool blk = blk_nb != 0;
+  const int ipp = tri ? 2 : blk ? blk_nb * (blk_nb + 1) / 2 : kBands;  // work items (records) per pair
   const int ncol_pad = ((max_n + 31) / 32) * 32;
-  const size_t stride = tri ? (size_t)16 : items_stride(ncol_pad);
+  const size_t stride = (tri || blk) ? (size_t)16 : items_stride(ncol_pad);
   // pairs per launch: at most 16384 (size of the arrival-counter array; 64k-pair chunks measured slower -- their
   // band records no longer stay in L2) and at most ~256 MB of band records
   const int64_t chunk_max = 65536;  // arrival counters reserved in the workspace
-  int64_t chunk = (int64_t)((size_t)(256u << 20) / ((size_t)kBands * stride * sizeof(double)));
-  if (chunk > (tri ? chunk_max : 16384)) chunk = tri ? chunk_max : 16384;  // triangle records are 128 B
+  int64_t chunk = (int64_t)((size_t)(256u << 20) / ((size_t)ipp * stride * sizeof(double)));
+  if (chunk > ((tri || blk) ? chunk_max : 16384)) chunk = (tri || blk) ? chunk_max : 16384;  // triangle records are 128 B
   if (chunk < 512) chunk = 512;
   const int64_t cap = n_pairs < chunk ? n_pairs : chunk;
   // workspace: [2 counters][2 retry flags + pad][done: chunk ints][scratch: cap * kBands * stride doubles];
   // the arrival counters sit at a fixed offset and size so that scratch records can never overlap them
   const size_t head = 64;
   const size_t done_bytes = (size_t)chunk_max * sizeof(int);
-  const size_t need = head + done_bytes + (size_t)cap * kBands * stride * sizeof(double);
+  const size_t need = head + done_bytes + (size_t)cap * ipp * stride * sizeof(double);
   if (ctx->d_items_bytes < need) {
     if (ctx->d_items) cudaFree(ctx->d_items);
     ctx->d_items = nullptr;
@@ -611,6 +625,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   a.ref_pre = ref->rowpre; a.qry_pre = qry->rowpre;
   a.p = p;
   a.ncol_pad = ncol_pad;
+  a.blocks = blk_nb;
   a.done = reinterpret_cast<int *>(base + head);
   a.scratch = reinterpret_cast<double *>(base + head + done_bytes);
   for (int64_t off = 0; off < n_pairs; off += chunk) {
@@ -623,7 +638,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     int rc;
     const int hh = r1 ? 0 : H;
     const bool multi = max_n > 31 * G;
-    if (tri && r1) rc = chess_items_launch_tri(ctx, a, G, stream);
+    if (blk) rc = chess_items_launch_blk(ctx, a, G, stream);
+    else if (tri && r1) rc = chess_items_launch_tri(ctx, a, G, stream);
     else if (tri && H == 3) rc = chess_items_launch_tri7(ctx, a, G, stream);
     else if (tri) rc = chess_items_launch_triw(ctx, a, G, H, stream);
     else if (hh == 0) rc = chess_items_launch_h0(ctx, a, G, multi, stream);

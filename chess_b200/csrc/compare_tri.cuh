@@ -68,20 +68,19 @@ struct TriItem {
 // Descriptor, soft failures, predicted masks, cutoff test and compaction map (chess/sim.py:319-353).
 // Returns false when the item is already done (a status was written by item A, or nothing is left
 // for this item to do).
-template <int G>
-__device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long long item, int lane, short *kmap,
-                                               unsigned char *mflag, TriItem &it) {
+//   pi        pair index in the launch;   part      which of the pair's items this is (0 writes the soft failures)
+//   n_limit   widest matrix the calling kernel can hold
+__device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long long pi, int part, int n_limit, int lane,
+                                               short *kmap, unsigned char *mflag, TriItem &it) {
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
   const bool use_masks = p.mappability_cutoff > 0;
   const int NCOL = a.ncol_pad;
-  const long long pi = item >> 1;
-  const int part = (int)(item & 1);
   const chess_pair d = a.pairs[pi];
   int status = CHESS_PAIR_OK;
   if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
   else if (d.qry_n < p.min_bins || d.ref_n < p.min_bins) status = CHESS_PAIR_TOO_SMALL;
-  else if (d.ref_n != d.qry_n || d.ref_n > 31 * G || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
+  else if (d.ref_n != d.qry_n || d.ref_n > n_limit || d.ref_n > NCOL) status = CHESS_PAIR_RETRY;
   if (status != CHESS_PAIR_OK) {
     if (part == 0 && lane == 0) {
       a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = status;
@@ -237,7 +236,7 @@ compare_r1_tri_kernel(chess_item_args a) {
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin<G>(a, item, lane, kmap, mflag, it)) continue;
+    if (!tri_item_begin(a, item >> 1, (int)(item & 1), 31 * G, lane, kmap, mflag, it)) continue;
     const long long pi = it.pi;
     const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;

@@ -38,7 +38,7 @@ compare_win_tri_kernel(chess_item_args a) {
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin<G>(a, item, lane, kmap, mflag, it)) continue;
+    if (!tri_item_begin(a, item >> 1, (int)(item & 1), 31 * G, lane, kmap, mflag, it)) continue;
     const long long pi = it.pi;
     const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;
