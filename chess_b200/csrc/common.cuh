@@ -71,6 +71,7 @@ int chess_items_launch_h3(chess_ctx *ctx, chess_item_args &a, int G, bool multi,
 int chess_items_launch_tri(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 // -r 1, matrices wider than one warp: square blocks on and above the diagonal (compare_blk.cuh)
 int chess_items_launch_blk(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
+int chess_items_launch_blkw(chess_ctx *ctx, chess_item_args &a, int G, int H, cudaStream_t stream);  // windows 3..11
 // -a 7 over the upper triangle (compare_tri7.cuh)
 int chess_items_launch_tri7(chess_ctx *ctx, chess_item_args &a, int G, cudaStream_t stream);
 // -a 3 / -a 5 over the upper triangle (compare_triw.cuh)

@@ -1,0 +1,359 @@
+// The -a 3 / 5 / 9 / 11 kernel of compare_triw.cuh on the block decomposition of compare_blk.cuh (matrices
+// wider than one warp): equal square blocks on and above the diagonal, the ones above it counting twice.
+#pragma once
+#include "compare_tri.cuh"
+
+namespace {
+
+template <int G, int H>
+__global__ void __launch_bounds__(128, 2)
+compare_win_blk_kernel(chess_item_args a) {
+  static_assert((H == 1 || H == 2 || H == 4 || H == 5) && G >= H, "window 3 / 5 / 9 / 11 (window 7 has its own kernel)");
+  constexpr int HALO = H > 3 ? H : 3;           // halo rows / columns around a band: the wider of the two windows
+  constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;  // ring depth in rows
+  __shared__ int s_susp[4][kSuspCap];
+  __shared__ int s_susp_n[4];
+  extern __shared__ __align__(16) double ringbuf[];  // per warp: D rows of x and y, D*2*G*32 doubles
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int *susp = s_susp[warp];
+  int *susp_n = &s_susp_n[warp];
+  constexpr int RING = D * 2 * G * 32;
+  double *myring = ringbuf + (size_t)warp * RING + lane;
+  const int NCOL = a.ncol_pad;
+  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
+  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) +
+                                                          (size_t)4 * NCOL) + (size_t)warp * NCOL;
+  const chess_params &p = a.p;
+  const double qnan = CUDART_NAN;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
+  const int nb = a.blocks;                       // blocks per side
+  const int ipp = nb * (nb + 1) / 2;             // items per pair: blocks on and above the diagonal
+  const long long n_items = a.n_pairs * ipp;
+
+  while (true) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(a.counter_cur, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    TriItem it;
+    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * (31 * G - 2 * HALO), lane, kmap, mflag, it)) continue;
+    const long long pi = it.pi;
+    const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
+    const double *R = it.R, *Q = it.Q;
+    const size_t rp = it.rp, qp = it.qp;
+    if (lane == 0) *susp_n = 0;
+    __syncwarp();
+
+    const int win = 2 * H + 1;
+    if (win > np_) {
+      if (part == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      continue;
+    }
+    const int m = np_ - win + 1;
+    const bool with_sn = p.compute_sn != 0;
+
+    // ---- data range from the running extrema, else min / max from the data
+    double xmax, xmin;
+    // C1 / C2 are needed before the first window: the rare data scan runs up front
+    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    const double drange = xmax - xmin;
+    const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
+
+    // ---- this item's block (bi, bj), bj >= bi, of nb x nb equal blocks of the compacted pair:
+    // rows [lo, hi), emitted columns [clo, chi), HALO rows / columns either side
+    if ((np_ + nb - 1) / nb < 8 + HALO) {  // blocks narrower than their halos (almost everything masked)
+      if (part == 0 && lane == 0) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+        atomicOr(a.retry_cur, 1);
+      }
+      continue;
+    }
+    int bi = 0, bj = 0;
+    {
+      int left = part;
+      while (left >= nb - bi) { left -= nb - bi; ++bi; }
+      bj = bi + left;
+    }
+    const int side = (np_ + nb - 1) / nb;
+    const int lo = min(bi * side, np_), hi = min(lo + side, np_);
+    const int clo = min(bj * side, np_), chi = min(clo + side, np_);
+    const int cbase = clo - HALO + G * lane;
+    const int rows_max = (chi > clo) ? hi - lo : 0;
+    const double wblock = bi == bj ? 1.0 : 2.0;   // a block above the diagonal stands for its mirror image too
+    unsigned xo[G], yo[G];
+    bool valid[G];
+    double wc[G];   // weight of the column: 0 in the halo, the block's weight inside
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int c = cbase + g;
+      valid[g] = c >= 0 && c < np_ && c < chi + HALO;
+      wc[g] = (c >= clo && c < chi) ? wblock : 0.0;
+      const int kc = valid[g] ? (int)kmap[c] : 0;
+      xo[g] = (unsigned)kc;
+      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
+    }
+    double *rec = a.scratch + ((size_t)pi * ipp + part) * kTriRec;
+    double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
+    bool overflow = false;
+
+    if (rows_max > 0) {
+      const int first = max(lo - HALO, 0);                        // the top blocks start at row 0
+      const int t_own0 = bi == 0 ? 0 : HALO;                      // iteration of the block's first own row
+      const int T = rows_max + (bi == 0 ? HALO : 2 * HALO);
+      constexpr int WIN = 2 * H + 1;
+      const double inv_np = 1.0 / (double)(WIN * WIN);
+      const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
+      double ccnt[G], wss[G];
+      double Sd[G], Se[G], Vx[G], Vy[G], Vxx[G], Vyy[G], Vxy[G];
+      unsigned hist[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = cbase + g;
+        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
+        wss[g] = (c >= H && c <= np_ - 1 - H) ? wc[g] : 0.0;      // SSIM windows need H columns either side
+        Sd[g] = Se[g] = Vx[g] = Vy[g] = Vxx[g] = Vyy[g] = Vxy[g] = 0.0;
+        hist[g] = 0u;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+      }
+      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+      int slot = 0;
+      double xn[G], yn[G];
+      auto fetch = [&](int row) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
+        if (row < np_) {
+          const unsigned kr = (unsigned)kmap[row];
+          const unsigned ro = kr * (unsigned)rp;
+          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
+          }
+        }
+      };
+      int row = first;
+      fetch(row);
+      for (int t = 0; t < T; ++t, ++row) {
+        double x[G], y[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
+        if (t + 1 < T) fetch(row + 1);
+        // ring positions of the rows that leave the 7-row and the WIN-row windows
+        const int s7 = slot + D - 7 >= D ? slot - 7 : slot + D - 7;        // row - 7
+        const int sw = slot + D - WIN >= D ? slot - WIN : slot + D - WIN;  // row - WIN
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
+          const double xow = myring[((sw * G + g) * 2) * 32], yow = myring[((sw * G + g) * 2 + 1) * 32];
+          myring[((slot * G + g) * 2) * 32] = x[g];
+          myring[((slot * G + g) * 2 + 1) * 32] = y[g];
+          const double dv = x[g] - y[g], dold = xo7 - yo7;
+          Sd[g] += dv; Sd[g] -= dold;
+          Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+          hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
+          Se[g] = hist[g] == 0u ? 0.0 : Se[g];
+          Vx[g] += x[g]; Vx[g] -= xow;
+          Vy[g] += y[g]; Vy[g] -= yow;
+          Vxx[g] = fma(x[g], x[g], Vxx[g]); Vxx[g] = fma(-xow, xow, Vxx[g]);
+          Vyy[g] = fma(y[g], y[g], Vyy[g]); Vyy[g] = fma(-yow, yow, Vyy[g]);
+          Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
+        }
+        slot = slot == D - 1 ? 0 : slot + 1;
+
+        // ---- SSIM windows whose centre row is row - H
+        if (t >= t_own0 + H) {
+          const int rcs = row - H;
+          const bool ssim_row = rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H;
+          double W5[5][G];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vxx : q == 3 ? Vyy : Vxy;
+            double P[G + 1];
+            P[0] = 0.0; P[1] = V[0];
+#pragma unroll
+            for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
+            double up[H], dn[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
+              up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
+              dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int a0 = g - H < 0 ? 0 : g - H;
+              const int b0 = g + H > G - 1 ? G - 1 : g + H;
+              double w = a0 == 0 ? P[b0 + 1] : P[b0 + 1] - P[a0];
+              if (g - H < 0) w += up[H - 1 - g];
+              if (g + H > G - 1) w += dn[g + H - G];
+              W5[q][g] = w;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const double ux = W5[0][g] * inv_np, uy = W5[1][g] * inv_np;
+            const double uxx = W5[2][g] * inv_np, uyy = W5[3][g] * inv_np, uxy = W5[4][g] * inv_np;
+            const double vx = cov_norm * fma(-ux, ux, uxx);
+            const double vy = cov_norm * fma(-uy, uy, uyy);
+            const double vxy = cov_norm * fma(-ux, uy, uxy);
+            const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
+            const double B1s = fma(ux, ux, fma(uy, uy, C1)), B2s = vx + vy + C2;
+            const double den = B1s * B2s;
+            const double num = A1 * A2;
+            double S = num * fast_rcp(den);
+            if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
+            if (ssim_row && wss[g] != 0.0) ss_sum = fma(wss[g], S, ss_sum);
+          }
+        }
+
+        // ---- SN pixels of row - 3
+        if (with_sn && t >= t_own0 + 3) {
+          const int rc = row - 3;
+          const bool emit_row = rc >= lo && rc < hi;
+          const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+          double P1[G + 1], P2[G + 1];
+          P1[0] = 0.0; P2[0] = 0.0;
+          P1[1] = Sd[0]; P2[1] = Se[0];
+#pragma unroll
+          for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+          unsigned suspect = 0u;
+          double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
+            const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+            up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+            up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+            dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+            dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int a0 = g - 3 < 0 ? 0 : g - 3;
+            const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
+            double w1 = a0 == 0 ? P1[b0 + 1] : P1[b0 + 1] - P1[a0];
+            double w2 = a0 == 0 ? P2[b0 + 1] : P2[b0 + 1] - P2[a0];
+            if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+            if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+            const bool own = emit_row & (wc[g] != 0.0);
+            const double cnt = rcnt * ccnt[g];
+            const double m2 = w2 * cnt;
+            const double den = fma(-w1, w1, m2);
+            const bool good = own & (den > fma(m2, 1e-6, 1e-290));
+            const double gq = fabs(w1) * cnt * fast_rcp(den);
+            sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
+            sn_cnt += good ? wc[g] : 0.0;
+            if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
+          }
+          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (suspect & (1u << g)) {
+                const int e = atomicAdd(susp_n, 1);
+                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+              }
+            }
+          }
+        }
+      }
+      if (with_sn) {
+        __syncwarp();
+        const int ns = *susp_n;
+        if (ns > 0 && ns <= kSuspCap) {  // cold: numpy's two passes for the cancelled windows
+          if (lane == 0) {               // fixed order, so the additions are reproducible
+            for (int i = 1; i < ns; ++i) {
+              const int key = susp[i];
+              int j = i - 1;
+              while (j >= 0 && susp[j] > key) { susp[j + 1] = susp[j]; --j; }
+              susp[j + 1] = key;
+            }
+          }
+          __syncwarp();
+          for (int e = lane; e < ns; e += 32) {
+            const int rc = susp[e] >> 16, c = susp[e] & 0xffff;
+            const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
+                                        (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
+            const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
+            if (gq == gq) { sn_sum += wblock * gq; sn_cnt += wblock; }
+          }
+        } else if (ns > kSuspCap) {
+          overflow = true;               // too many: the generic kernel redoes the pair exactly
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- record of this item
+    {
+      const double ss = warp_sum(sn_sum);
+      const double sc = warp_sum(sn_cnt);
+      const double sw = warp_sum(ss_sum);
+      if (lane == 0) {
+        rec[5] = xmax; rec[6] = xmin; rec[7] = ss; rec[8] = sc;
+        rec[14] = overflow ? 1.0 : 0.0;
+        rec[15] = sw;
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(a.done + pi, 1);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != ipp - 1) continue;
+
+    // ---- last item to arrive: verify the predicted masks, combine in block order, write the result
+    __threadfence();
+    const double *recs = a.scratch + (size_t)pi * ipp * kTriRec;
+    bool bad = false;
+    for (int b = lane; b < ipp; b += 32) bad |= __ldcg(recs + (size_t)b * kTriRec + 14) != 0.0;
+    bad |= !tri_masks_hold(a, it, lane, kmap, mflag);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      if (bad) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+        atomicOr(a.retry_cur, 1);
+      } else {
+        double ss = 0.0, sc = 0.0, sm = 0.0;
+        for (int b = 0; b < ipp; ++b) {
+          const double *rb = recs + (size_t)b * kTriRec;
+          ss += __ldcg(rb + 7); sc += __ldcg(rb + 8); sm += __ldcg(rb + 15);
+        }
+        a.ssim[pi] = sm / ((double)m * (double)m);
+        a.sn[pi] = with_sn ? ss / sc : CUDART_NAN;
+        a.status[pi] = CHESS_PAIR_OK;
+      }
+      a.done[pi] = 0;
+    }
+  }
+}
+
+template <int G, int H>
+int launch_blkw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+  auto kern = compare_win_blk_kernel<G, H>;
+  constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;
+  constexpr int RING = D * 2 * G * 32;
+  const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
+  const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 1024 * 3;
+  static bool configured[64] = {false};
+  if (ctx->device >= 64 || !configured[ctx->device]) {
+    CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    if (ctx->device < 64) configured[ctx->device] = true;
+  }
+  static int per_sm = 0, per_sm_ncol = -1;
+  if (per_sm_ncol != a.ncol_pad) {
+    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    per_sm_ncol = a.ncol_pad;
+  }
+  long long grid = (long long)ctx->sm_count * per_sm;
+  const long long need = (a.n_pairs * (a.blocks * (a.blocks + 1) / 2) + 3) / 4;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+}  // namespace

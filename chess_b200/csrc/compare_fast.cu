@@ -566,21 +566,22 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   const int tri_G = ((r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre)
                         ? tri_strip_width(max_n, H > 3 ? H : 3) : 0;
   const bool tri = tri_G != 0;
-  if (H > 3 && !tri) return CHESS_OK;  // the generic kernel takes it
   if (tri) G = tri_G;
   // -r 1 on matrices wider than one warp: square blocks on and above the diagonal; strip width and block
   // count that cost the fewest lane-columns (blocks x rows per block x strip width)
   int blk_nb = 0;
-  if (!tri && r1 && p.kernel != 3 && ref->rowpre && qry->rowpre && max_n > 93) {
+  if (!tri && (r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre && max_n > 93) {
     long best = -1;
+    const int halo = H > 3 ? H : 3;
     for (int g = 5; g <= 8; ++g) {
-      const int nb = (max_n + (31 * g - 6) - 1) / (31 * g - 6);
+      const int nb = (max_n + (31 * g - 2 * halo) - 1) / (31 * g - 2 * halo);
       if (nb < 2 || nb > 7) continue;
-      const long cost = (long)(nb * (nb + 1) / 2) * ((max_n + nb - 1) / nb + 6) * g;
+      const long cost = (long)(nb * (nb + 1) / 2) * ((max_n + nb - 1) / nb + 2 * halo) * g;
       if (best < 0 || cost < best) { best = cost; G = g; blk_nb = nb; }
     }
   }
   const bool blk = blk_nb != 0;
+  if (H > 3 && !tri && !blk) return CHESS_OK;  // windows 9 / 11 have no full-square kernel: generic
   const int ipp = tri ? 2 : blk ? blk_nb * (blk_nb + 1) / 2 : kBands;  // work items (records) per pair
   const int ncol_pad = ((max_n + 31) / 32) * 32;
   const size_t stride = (tri || blk) ? (size_t)16 : items_stride(ncol_pad);
@@ -638,7 +639,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     int rc;
     const int hh = r1 ? 0 : H;
     const bool multi = max_n > 31 * G;
-    if (blk) rc = chess_items_launch_blk(ctx, a, G, stream);
+    if (blk && r1) rc = chess_items_launch_blk(ctx, a, G, stream);
+    else if (blk) rc = chess_items_launch_blkw(ctx, a, G, H, stream);
     else if (tri && r1) rc = chess_items_launch_tri(ctx, a, G, stream);
     else if (tri && H == 3) rc = chess_items_launch_tri7(ctx, a, G, stream);
     else if (tri) rc = chess_items_launch_triw(ctx, a, G, H, stream);
