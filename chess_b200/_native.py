@@ -103,6 +103,12 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
+# the struct layouts above follow include/chess_b200.h at this ABI version (chess_sample grew `rowpre` in 2)
+ABI_VERSION = 2
+if lib.chess_abi_version() != ABI_VERSION:
+    raise ChessNativeError("libchess_b200.so has ABI version {}, this binding expects {}: rebuild with "
+                           "python -m chess_b200.build".format(lib.chess_abi_version(), ABI_VERSION))
+
 
 def last_error(ctx=None):
     msg = lib.chess_last_error(ctx)

@@ -20,7 +20,8 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
-    assert lib.chess_abi_version() == 2
+    from chess_b200 import _native
+    assert lib.chess_abi_version() == _native.ABI_VERSION == 2
     assert ctypes.sizeof(_native.chess_pair) == 40 and ctypes.sizeof(_native.chess_params) == 48
 
 
