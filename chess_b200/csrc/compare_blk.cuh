@@ -6,6 +6,7 @@
 // with the full-square walk (two row bands x column blocks) a 601-bin pair costs 6 blocks of 207
 // rows at G = 7 instead of 6 strips of 306 rows at G = 8.
 #pragma once
+#include <type_traits>
 #include "compare_tri.cuh"
 
 namespace {
@@ -64,7 +65,9 @@ compare_r1_blk_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);  // rare in aligned samples, common against
+                                                                      // background regions (a bin masked on one side)
+    if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 
     // ---- this item's block (bi, bj), bj >= bi, of nb x nb equal blocks of the compacted pair:
     // rows [lo, hi), emitted columns [clo, chi), three halo rows / columns either side
@@ -150,6 +153,10 @@ compare_r1_blk_kernel(chess_item_args a) {
           }
         }
       };
+      // two instances of the row loop: the usual one, and one that also tracks min / max of the data
+      double vmax = -CUDART_INF, vmin = CUDART_INF;
+      auto run = [&](auto minmax_tag) {
+      constexpr bool MINMAX = decltype(minmax_tag)::value;
       int row = first;
       fetch(row);
       for (int t = 0; t < T; ++t, ++row) {
@@ -163,6 +170,13 @@ compare_r1_blk_kernel(chess_item_args a) {
             const double wx = wc[g] * xn[g], wy = wc[g] * yn[g];
             T0 += wx; T1 += wy;
             T2 = fma(wx, xn[g], T2); T3 = fma(wy, yn[g], T3); T4 = fma(wx, yn[g], T4);
+            if (MINMAX) {  // every loaded element of an own row belongs to the compacted pair
+              const bool xgt = xn[g] > yn[g];
+              const double hi2 = xgt ? xn[g] : yn[g];
+              const double lo2 = xgt ? yn[g] : xn[g];
+              vmax = (valid[g] & (hi2 > vmax)) ? hi2 : vmax;
+              vmin = (valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+            }
           }
         }
         if (t + 1 < T) fetch(row + 1);
@@ -227,6 +241,13 @@ compare_r1_blk_kernel(chess_item_args a) {
             }
           }
         }
+      }
+      };
+      if (inloop_minmax) {
+        run(std::true_type());
+        xmax = warp_max(vmax); xmin = warp_min(vmin);
+      } else {
+        run(std::false_type());
       }
       if (WITH_SN) {
         __syncwarp();

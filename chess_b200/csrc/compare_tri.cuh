@@ -20,6 +20,7 @@
 // per-sample prefix-sum array over the band rows (chess_band_prefix_build), and only a column
 // whose approximate sum hits n*default is summed exactly, in the reference's order.
 #pragma once
+#include <type_traits>
 #include "compare_kernels.cuh"
 
 namespace {
@@ -254,7 +255,9 @@ compare_r1_tri_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);  // rare in aligned samples, common against
+                                                                      // background regions (a bin masked on one side)
+    if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 
     // ---- this item's lanes: rows [lo, hi), first column cbase
     int B1, B2, L1, L2;
@@ -337,6 +340,10 @@ compare_r1_tri_kernel(chess_item_args a) {
           }
         }
       };
+      // two instances of the row loop: the usual one, and one that also tracks min / max of the data
+      double vmax = -CUDART_INF, vmin = CUDART_INF;
+      auto run = [&](auto minmax_tag) {
+      constexpr bool MINMAX = decltype(minmax_tag)::value;
       int row = first;
       fetch(row);
       for (int t = 0; t < T; ++t, ++row) {
@@ -353,6 +360,13 @@ compare_r1_tri_kernel(chess_item_args a) {
             const double wx = wt * xn[g], wy = wt * yn[g];  // columns that do not exist were fetched as 0
             T0 += wx; T1 += wy;
             T2 = fma(wx, xn[g], T2); T3 = fma(wy, yn[g], T3); T4 = fma(wx, yn[g], T4);
+            if (MINMAX) {  // every loaded element of an own row belongs to the compacted pair
+              const bool xgt = xn[g] > yn[g];
+              const double hi2 = xgt ? xn[g] : yn[g];
+              const double lo2 = xgt ? yn[g] : xn[g];
+              vmax = (valid[g] & (hi2 > vmax)) ? hi2 : vmax;
+              vmin = (valid[g] & (lo2 < vmin)) ? lo2 : vmin;
+            }
           }
         }
         if (t + 1 < T) fetch(row + 1);
@@ -419,6 +433,13 @@ compare_r1_tri_kernel(chess_item_args a) {
             }
           }
         }
+      }
+      };
+      if (inloop_minmax) {
+        run(std::true_type());
+        xmax = warp_max(vmax); xmin = warp_min(vmin);
+      } else {
+        run(std::false_type());
       }
       if (WITH_SN) {
         __syncwarp();
