@@ -65,7 +65,7 @@ compare_r1_blk_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);  // rare in aligned samples, common against
+    const bool inloop_minmax = tri_extrema(a, it, lane, mflag, xmax, xmin);  // rare in aligned samples, common against
                                                                       // background regions (a bin masked on one side)
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 

@@ -56,7 +56,7 @@ compare_win_blk_kernel(chess_item_args a) {
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
     // C1 / C2 are needed before the first window: the rare data scan runs up front
-    if (tri_extrema(a, it, lane, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
 

@@ -137,11 +137,14 @@ __device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long lo
 
 // Data range of the pair from the running-extrema arrays: n lookups give max / min of the
 // uncompacted pair.  They are the extrema of the compacted pair too if every removed cell holds the
-// default value in both matrices (bins masked in one matrix only are removed from the other, where
-// they carry data) and the default is neither the max nor the min.  Returns true when the caller
-// has to take min / max from the data instead.
-__device__ __forceinline__ bool tri_extrema(const chess_item_args &a, const TriItem &it, int lane, double &xmax,
-                                            double &xmin) {
+// default value in both matrices and the default is neither the max nor the min.  Otherwise (a bin
+// masked in one matrix only is removed from the other, where it carries data: the norm when a
+// region is compared with background regions) the removed rows alone are scanned -- k*n cells for
+// k removed bins: if none of them reaches the uncompacted extremes, those are attained by cells
+// that stay, and the lookup stands.  Returns true only when that fails too and the caller has to
+// take min / max from all the data.
+__device__ __forceinline__ bool tri_extrema(const chess_item_args &a, const TriItem &it, int lane,
+                                            const unsigned char *mflag, double &xmax, double &xmin) {
   xmax = -CUDART_INF; xmin = CUDART_INF;
   if (a.ref_pmax == nullptr) return true;
   const int n = it.n;
@@ -153,7 +156,22 @@ __device__ __forceinline__ bool tri_extrema(const chess_item_args &a, const TriI
   }
   xmax = warp_max(xmax);
   xmin = warp_min(xmin);
-  return it.np_ < n && (it.tot_one_sided > 0 || !(xmax > a.p.default_value && xmin < a.p.default_value));
+  if (it.np_ == n) return false;                         // nothing was removed
+  if (it.tot_one_sided == 0 && xmax > a.p.default_value && xmin < a.p.default_value) return false;
+  // removed rows (= removed columns: both matrices are symmetric), all n cells of each, both matrices
+  double rmax = -CUDART_INF, rmin = CUDART_INF;
+  for (int r = 0; r < n; ++r) {
+    if (mflag[r] == 0) continue;
+    const double *rowR = it.R + (size_t)r * it.rp;
+    const double *rowQ = it.Q + (size_t)(it.flip ? n - 1 - r : r) * it.qp;
+    for (int c = lane; c < n; c += 32) {
+      const double x = __ldg(rowR + c), y = __ldg(rowQ + c);   // the order inside a row does not matter here
+      rmax = fmax(rmax, fmax(x, y)); rmin = fmin(rmin, fmin(x, y));
+    }
+  }
+  rmax = warp_max(rmax);
+  rmin = warp_min(rmin);
+  return !(rmax < xmax && rmin > xmin);
 }
 
 // Min / max of the compacted pair from the data (rare: a bin masked in one matrix only, or a
@@ -255,7 +273,7 @@ compare_r1_tri_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, xmax, xmin);  // rare in aligned samples, common against
+    const bool inloop_minmax = tri_extrema(a, it, lane, mflag, xmax, xmin);  // rare in aligned samples, common against
                                                                       // background regions (a bin masked on one side)
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 
