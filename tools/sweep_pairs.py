@@ -18,6 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--window", default="r1")
     ap.add_argument("--counts", default="148,296,592,1184,1776,2368,2402,2960,3552,4736")
+    ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between launches")
     ap.add_argument("--bin-size", type=int, default=25000)
     ap.add_argument("--window-bp", type=int, default=2000000)
     args = ap.parse_args()
@@ -58,7 +59,8 @@ def main():
     for cnt in counts:
         ts = []
         for k in range(35):
-            flush.zero_()
+            if not args.no_flush:
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             check(lib.chess_compare_band_batch(ctx.handle, C.byref(rsample), C.byref(qsample), ptr(d_table), cnt,
