@@ -28,10 +28,17 @@ compare_win7_blk_kernel(chess_item_args a) {
   const int ipp = nb * (nb + 1) / 2;             // items per pair: blocks on and above the diagonal
   const long long n_items = a.n_pairs * ipp;
 
+  // the first item of every warp is its own index: no storm of atomics on one counter when the grid
+  // starts; later items come from the counter, offset by the number of warps
+  const long long n_warps = (long long)gridDim.x * 4;
+  bool first_item = true;
   while (true) {
-    long long item = 0;
-    if (lane == 0) item = (long long)atomicAdd(a.counter_cur, 1ull);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    long long item = (long long)blockIdx.x * 4 + warp;
+    if (!first_item) {
+      if (lane == 0) item = n_warps + (long long)atomicAdd(a.counter_cur, 1ull);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    }
+    first_item = false;
     if (item >= n_items) break;
     TriItem it;
     if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * (31 * G - 2 * 3), lane, kmap, mflag, it)) continue;
