@@ -348,14 +348,16 @@ def measure(args, rank, world, local_rank, dist):
     h_ssim, h_sn = np.empty(n_pairs), np.empty(n_pairs)
     h_status = np.empty(n_pairs, dtype=np.int32)
 
+    h_z = np.empty(n_pairs)
+
     def host_step():
-        check(lib.chess_compare_band_batch_host(ctx.handle, C.byref(rsample), C.byref(qsample),
-                                                table.ctypes.data_as(C.c_void_p), n_pairs, max_n, C.byref(p),
-                                                h_ssim.ctypes.data_as(C.c_void_p), h_sn.ctypes.data_as(C.c_void_p),
-                                                h_status.ctypes.data_as(C.c_void_p), sp),
-              ctx.handle, "chess_compare_band_batch_host")
-        valid = h_ssim[~np.isnan(h_ssim)]
-        return (h_ssim - valid.mean()) / valid.std()
+        # one C-ABI call with host buffers: pair table in, ssim / SN / status / z_ssim out
+        check(lib.chess_sim_band_batch_host(ctx.handle, C.byref(rsample), C.byref(qsample),
+                                            table.ctypes.data_as(C.c_void_p), n_pairs, max_n, C.byref(p),
+                                            h_ssim.ctypes.data_as(C.c_void_p), h_sn.ctypes.data_as(C.c_void_p),
+                                            h_status.ctypes.data_as(C.c_void_p), h_z.ctypes.data_as(C.c_void_p), sp),
+              ctx.handle, "chess_sim_band_batch_host")
+        return h_z
 
     host_step()
     cold_s = time.perf_counter() - t0
@@ -428,8 +430,11 @@ def measure(args, rank, world, local_rank, dist):
 
     ok = int((h_status == 0).sum())
     z_dev = d_z.cpu().numpy()
-    z_host = host_step()
-    z_dev_ok = bool(np.allclose(z_dev, z_host, rtol=1e-9, atol=1e-12, equal_nan=True))
+    host_step()
+    valid = h_ssim[~np.isnan(h_ssim)]
+    z_numpy = (h_ssim - valid.mean()) / valid.std()            # bin/chess:228-233
+    z_dev_ok = bool(np.allclose(z_dev, z_numpy, rtol=1e-9, atol=1e-12, equal_nan=True) and
+                    np.allclose(h_z, z_numpy, rtol=1e-9, atol=1e-12, equal_nan=True))
 
     # ---- max over ranks
     if dist is not None:
@@ -467,8 +472,8 @@ def measure(args, rank, world, local_rank, dist):
                      "kernel": "compare (gather+mask+SSIM+SN), %.1f us per launch, %d pairs" % (kavg_ms * 1e3, n_pairs),
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pairs/s",
-                "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_pairs * 20),
-                "call": "chess_compare_band_batch_host + host z-score"},
+                "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_pairs * 28),
+                "call": "chess_sim_band_batch_host (host pair table in; ssim, SN, status, z_ssim out)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

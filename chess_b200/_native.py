@@ -86,6 +86,7 @@ SIGNATURES = {
     "chess_band_extrema_build": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "chess_compare_band_batch": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
+    "chess_sim_band_batch_host": (C.c_int, [_vp, _SP, _SP, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp, _vp]),
     "chess_sn_dense": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_zscore": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "chess_band_prefix_build": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),

@@ -138,12 +138,14 @@ extern "C" int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref,
   return chess_compare_batch(ctx, ref->band, qry->band, pairs, n_pairs, max_n, &p, ssim, sn, status, stream_);
 }
 
-// Shared body of the *_host entry points: stage the pair table, run `launch`, copy the results back.
+// Shared body of the *_host entry points: stage the pair table, run `launch`, (optionally) the run-level
+// z-score on the device, copy the results back in one transfer.
 template <typename Launch>
 static int host_roundtrip(chess_ctx *ctx, const chess_pair *pairs_host, int64_t n_pairs, double *ssim_host,
-                          double *sn_host, int32_t *status_host, cudaStream_t stream, Launch launch) {
+                          double *sn_host, int32_t *status_host, double *z_host, cudaStream_t stream,
+                          Launch launch) {
   const size_t pair_bytes = (size_t)n_pairs * sizeof(chess_pair);
-  const size_t res_bytes = (size_t)n_pairs * (2 * sizeof(double) + sizeof(int32_t));
+  const size_t res_bytes = (size_t)n_pairs * ((z_host ? 3 : 2) * sizeof(double) + sizeof(int32_t));
   int rc;
   if ((rc = grow(ctx, &ctx->d_pairs, &ctx->d_pairs_bytes, pair_bytes, false))) return rc;
   if ((rc = grow(ctx, &ctx->d_results, &ctx->d_results_bytes, res_bytes, false))) return rc;
@@ -154,15 +156,19 @@ static int host_roundtrip(chess_ctx *ctx, const chess_pair *pairs_host, int64_t 
   CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, ctx->h_pinned, pair_bytes, cudaMemcpyHostToDevice, stream));
   double *d_ssim = reinterpret_cast<double *>(ctx->d_results);
   double *d_sn = d_ssim + n_pairs;
-  int32_t *d_status = reinterpret_cast<int32_t *>(d_sn + n_pairs);
+  double *d_z = d_sn + n_pairs;                      // only if z_host
+  int32_t *d_status = reinterpret_cast<int32_t *>(d_sn + (z_host ? 2 : 1) * n_pairs);
   rc = launch(reinterpret_cast<const chess_pair *>(ctx->d_pairs), d_ssim, d_sn, d_status);
   if (rc) return rc;
+  if (z_host && (rc = chess_zscore(ctx, d_ssim, n_pairs, d_z, stream))) return rc;
   CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_results, res_bytes, cudaMemcpyDeviceToHost, stream));
   CHESS_CUDA(ctx, cudaStreamSynchronize(stream));
   const char *h = reinterpret_cast<const char *>(ctx->h_pinned);
-  std::memcpy(ssim_host, h, (size_t)n_pairs * sizeof(double));
-  std::memcpy(sn_host, h + (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(double));
-  std::memcpy(status_host, h + 2 * (size_t)n_pairs * sizeof(double), (size_t)n_pairs * sizeof(int32_t));
+  const size_t col = (size_t)n_pairs * sizeof(double);
+  std::memcpy(ssim_host, h, col);
+  std::memcpy(sn_host, h + col, col);
+  if (z_host) std::memcpy(z_host, h + 2 * col, col);
+  std::memcpy(status_host, h + (z_host ? 3 : 2) * col, (size_t)n_pairs * sizeof(int32_t));
   return CHESS_OK;
 }
 
@@ -178,10 +184,28 @@ extern "C" int chess_compare_batch_host(chess_ctx *ctx, const double *ref_base,
   }
   if (n_pairs == 0) return CHESS_OK;
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
-  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, (cudaStream_t)stream_,
+  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, nullptr, (cudaStream_t)stream_,
                         [&](const chess_pair *d_pairs, double *d_ssim, double *d_sn, int32_t *d_status) {
                           return chess_compare_batch(ctx, ref_base, qry_base, d_pairs, n_pairs, max_n, params,
                                                      d_ssim, d_sn, d_status, stream_);
+                        });
+}
+
+extern "C" int chess_sim_band_batch_host(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                                        const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
+                                        const chess_params *params, double *ssim_host, double *sn_host,
+                                        int32_t *status_host, double *z_host, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
+    ctx->err = "chess_sim_band_batch_host: NULL buffer";
+    return CHESS_ERR_ARG;
+  }
+  if (n_pairs == 0) return CHESS_OK;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, z_host, (cudaStream_t)stream_,
+                        [&](const chess_pair *d_pairs, double *d_ssim, double *d_sn, int32_t *d_status) {
+                          return chess_compare_band_batch(ctx, ref, qry, d_pairs, n_pairs, max_n, params,
+                                                          d_ssim, d_sn, d_status, stream_);
                         });
 }
 
@@ -190,18 +214,8 @@ extern "C" int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample 
                                              int64_t n_pairs, int32_t max_n, const chess_params *params,
                                              double *ssim_host, double *sn_host, int32_t *status_host,
                                              void *stream_) {
-  if (!ctx) return CHESS_ERR_ARG;
-  if (n_pairs < 0 || (n_pairs > 0 && (!pairs_host || !ssim_host || !sn_host || !status_host))) {
-    ctx->err = "chess_compare_band_batch_host: NULL buffer";
-    return CHESS_ERR_ARG;
-  }
-  if (n_pairs == 0) return CHESS_OK;
-  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
-  return host_roundtrip(ctx, pairs_host, n_pairs, ssim_host, sn_host, status_host, (cudaStream_t)stream_,
-                        [&](const chess_pair *d_pairs, double *d_ssim, double *d_sn, int32_t *d_status) {
-                          return chess_compare_band_batch(ctx, ref, qry, d_pairs, n_pairs, max_n, params,
-                                                          d_ssim, d_sn, d_status, stream_);
-                        });
+  return chess_sim_band_batch_host(ctx, ref, qry, pairs_host, n_pairs, max_n, params, ssim_host, sn_host,
+                                   status_host, nullptr, stream_);
 }
 
 namespace {

@@ -215,6 +215,12 @@ int chess_compare_band_batch_host(chess_ctx *ctx, const chess_sample *ref, const
                                   const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
                                   const chess_params *params, double *ssim_host, double *sn_host,
                                   int32_t *status_host, void *stream);
+/* The same plus the run-level z-score (K6, bin/chess:216-233) of this batch, computed on the device and
+ * returned in the same transfer; z_host may be NULL.  One call = what `chess sim` reports per pair.  */
+int chess_sim_band_batch_host(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
+                              const chess_pair *pairs_host, int64_t n_pairs, int32_t max_n,
+                              const chess_params *params, double *ssim_host, double *sn_host,
+                              int32_t *status_host, double *z_host, void *stream);
 
 /* K6: run-level z-score, bin/chess:216-233: z = (ssim - nanmean) / nanstd
  * (ddof 0) over the non-NaN entries; entries that are not finite keep NaN.

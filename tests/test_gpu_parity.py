@@ -572,6 +572,36 @@ def test_bin_masked_in_one_sample_only(cb):
             assert close(sn[k], osn, RTOL), (kw, pid, sn[k], osn)
 
 
+def test_sim_host_call_returns_zscores(cb, chr2_like):
+    """chess_sim_band_batch_host: host pair table in, ssim / SN / status and the run-level z out."""
+    import ctypes as C
+    import torch
+    from chess_b200 import _native
+    from chess_b200._native import lib, check
+    from chess_b200.engine import get_context, region_spans, build_pair_table
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    rf, rn = region_spans(trees, [q[1] for q in pairs])
+    rw, rband, rsample = re_.sample_on(0, int(rn.max()))
+    qw, qband, qsample = qe.sample_on(0, int(rn.max()))
+    table = build_pair_table(rf, rn, rw, rf, rn, qw, np.zeros(len(pairs), dtype=np.int32))
+    p = _native.make_params(flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES)
+    n = len(pairs)
+    ssim, sn, z = np.empty(n), np.empty(n), np.empty(n)
+    status = np.empty(n, dtype=np.int32)
+    ctx = get_context(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    check(lib.chess_sim_band_batch_host(ctx.handle, C.byref(rsample), C.byref(qsample), vp(table), n, int(rn.max()),
+                                        C.byref(p), vp(ssim), vp(sn), vp(status), vp(z),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), ctx.handle, "sim")
+    ids, s2, sn2, st2 = cb.CompareEngine(re_, trees, qe, trees).compare(pairs)
+    assert np.array_equal(ssim, s2, equal_nan=True) and np.array_equal(sn, sn2, equal_nan=True)
+    assert np.array_equal(status, st2)
+    valid = ssim[~np.isnan(ssim)]
+    want = (ssim - valid.mean()) / valid.std()
+    assert np.allclose(z, want, rtol=1e-10, atol=1e-12, equal_nan=True)
+    assert np.array_equal(np.isnan(z), np.isnan(ssim))
+
+
 def test_zscore_kernel(cb):
     import ctypes as C
     import torch
