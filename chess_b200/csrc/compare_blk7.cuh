@@ -158,6 +158,25 @@ compare_win7_blk_kernel(chess_item_args a) {
           if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
         }
         slot = slot == 6 ? 0 : slot + 1;
+        if (slot == 0) {
+          // the ring has just wrapped: rebuild the four column sums from its seven rows.  A running sum keeps the
+          // rounding of every value that ever passed through it; rebuilt once per window height it is exact to a
+          // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            double vx = 0.0, vy = 0.0, vq = 0.0, vxy = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+              const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
+              vx += xk; vy += yk;
+              vq = fma(xk, xk, fma(yk, yk, vq));
+              vxy = fma(xk, yk, vxy);
+            }
+            Vx[g] = vx; Vy[g] = vy; Vq[g] = vq; Vxy[g] = vxy;
+            if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
+          }
+        }
+
         if (t >= t_emit0) {
           const int rc = row - 3;   // centre row of the SSIM window and SN pixel row
           const bool emit_row = rc >= lo && rc < hi;
@@ -213,7 +232,7 @@ compare_win7_blk_kernel(chess_item_args a) {
               const double m2 = w2 * cnt;
               const double den = fma(-w1, w1, m2);
               // trusted: one-pass variance well conditioned AND the q - 2xy subtraction kept >= 10 digits
-              const bool good = own & (den > fma(m2, 1e-6, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
+              const bool good = own & (den > fma(m2, kVarGuard, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
               const double gq = fabs(w1) * cnt * fast_rcp(den);
               sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
               sn_cnt += good ? wc[g] : 0.0;

@@ -79,6 +79,11 @@ __device__ __forceinline__ bool is_nonzero(double v) {
 
 constexpr int kSuspCap = 24;
 
+// The one-pass variance of a 7x7 window, cnt*sum(d^2) - sum(d)^2, is trusted when it keeps at least this
+// fraction of cnt*sum(d^2): the running column sums and prefix differences carry some hundred ulps, so the
+// result is good to ~1e-14 / kVarGuard.  Windows below it are recomputed in numpy's own two-pass order.
+constexpr double kVarGuard = 1e-4;
+
 struct Band2 {
   double T0, T1, T2, T3, T4, vmax, vmin, sn_sum;
   int sn_cnt;
@@ -231,6 +236,19 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
       Se[g] = hist[g] == 0u ? 0.0 : Se[g];
     }
     if (slot == 6) { slot = 0; ringrow = myring; } else { slot += 1; ringrow += G * 32; }
+    if (slot == 0) {
+      // the ring has just wrapped: rebuild the column sums from its seven rows.  A running sum keeps the
+      // rounding of every value that ever passed through it; rebuilt once per window height it is exact
+      // to a few ulps of the current window, which the quiet windows after a loud stretch need
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s1 += v; s2 = fma(v, v, s2); }
+        Sd[g] = s1;
+        Se[g] = hist[g] == 0u ? 0.0 : s2;
+      }
+    }
     const int rc = rr - 3;
     if (rc >= lo && rc < hi) {
       const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
@@ -241,12 +259,19 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
       P1[1] = Sd[0]; P2[1] = Se[0];
 #pragma unroll
       for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+      // suffix sums as well: a window that ends at the strip's right edge is a suffix, and no window of 7
+      // starts after column 0 without reaching that edge (G <= 8), so nothing is ever subtracted -- a
+      // difference of prefixes would carry the rounding of every column left of the window
+      double X1[G], X2[G];
+      X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
+#pragma unroll
+      for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
       double up1[3], up2[3], dn1[3], dn2[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         // suffix of j+1 columns of the previous lane, prefix of j+1 columns of the next lane
-        const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
-        const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+        const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
+        const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
         up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
         up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
         dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
@@ -256,15 +281,15 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
       for (int g = 0; g < G; ++g) {
         const int a = g - 3 < 0 ? 0 : g - 3;
         const int b = g + 3 > G - 1 ? G - 1 : g + 3;
-        double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
-        double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+        double w1 = a == 0 ? P1[b + 1] : X1[a];
+        double w2 = a == 0 ? P2[b + 1] : X2[a];
         if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
         if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
         const double cnt = rcnt * ccnt[g];
         const double m2 = w2 * cnt;
         const double den = fma(-w1, w1, m2);
         // one-pass variance is trusted when var > 1e-6 * E[d^2] (and E[d^2] is not denormal-small)
-        const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290));
+        const bool good = lc.em(g) & (den > fma(m2, kVarGuard, 1e-290));
         const double gq = fabs(w1) * cnt * fast_rcp(den);
         sn_sum += good ? gq : 0.0;
         sn_cnt += good ? 1 : 0;
@@ -371,6 +396,23 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
       Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
     }
     slot = slot == D - 1 ? 0 : slot + 1;
+    if (slot == 0) {
+      // the ring has just wrapped: rebuild the 7-row difference sums from its most recent seven rows
+      // (slots D-7 .. D-1).  A running sum keeps the rounding of every value that ever passed through it;
+      // rebuilt once per wrap it is exact to a few ulps of the current window
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int k = D - 7; k < D; ++k) {
+          const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
+          s1 += dk; s2 = fma(dk, dk, s2);
+        }
+        Sd[g] = s1;
+        Se[g] = hist[g] == 0u ? 0.0 : s2;
+      }
+    }
+
 
     // ---- SSIM windows whose centre row is rr - H
     const int rcs = rr - H;
@@ -427,11 +469,18 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
       P1[1] = Sd[0]; P2[1] = Se[0];
 #pragma unroll
       for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+      // suffix sums as well: a window that ends at the strip's right edge is a suffix, and no window of 7
+      // starts after column 0 without reaching that edge (G <= 8), so nothing is ever subtracted -- a
+      // difference of prefixes would carry the rounding of every column left of the window
+      double X1[G], X2[G];
+      X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
+#pragma unroll
+      for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
       double up1[3], up2[3], dn1[3], dn2[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
-        const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+        const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
+        const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
         up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
         up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
         dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
@@ -441,14 +490,14 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
       for (int g = 0; g < G; ++g) {
         const int a = g - 3 < 0 ? 0 : g - 3;
         const int b = g + 3 > G - 1 ? G - 1 : g + 3;
-        double w1 = a == 0 ? P1[b + 1] : P1[b + 1] - P1[a];
-        double w2 = a == 0 ? P2[b + 1] : P2[b + 1] - P2[a];
+        double w1 = a == 0 ? P1[b + 1] : X1[a];
+        double w2 = a == 0 ? P2[b + 1] : X2[a];
         if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
         if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
         const double cnt = rcnt * ccnt[g];
         const double m2 = w2 * cnt;
         const double den = fma(-w1, w1, m2);
-        const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290));
+        const bool good = lc.em(g) & (den > fma(m2, kVarGuard, 1e-290));
         const double gq = fabs(w1) * cnt * fast_rcp(den);
         sn_sum += good ? gq : 0.0;
         sn_cnt += good ? 1 : 0;
@@ -544,6 +593,25 @@ __device__ __forceinline__ void win7_rows(const double *__restrict__ R, const do
       if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
     }
     slot = slot == D - 1 ? 0 : slot + 1;
+    if (slot == 0) {
+      // the ring has just wrapped: rebuild the four column sums from its seven rows.  A running sum keeps the
+      // rounding of every value that ever passed through it; rebuilt once per window height it is exact to a
+      // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        double vx = 0.0, vy = 0.0, vq = 0.0, vxy = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
+          vx += xk; vy += yk;
+          vq = fma(xk, xk, fma(yk, yk, vq));
+          vxy = fma(xk, yk, vxy);
+        }
+        Vx[g] = vx; Vy[g] = vy; Vq[g] = vq; Vxy[g] = vxy;
+        if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
+      }
+    }
+
 
     const int rc = rr - 3;   // centre row of the SSIM window and SN pixel row
     if (rc >= lo && rc < hi) {
@@ -598,7 +666,7 @@ __device__ __forceinline__ void win7_rows(const double *__restrict__ R, const do
           const double m2 = w2 * cnt;
           const double den = fma(-w1, w1, m2);
           // trusted: one-pass variance well conditioned AND the q - 2xy subtraction kept >= 10 digits
-          const bool good = lc.em(g) & (den > fma(m2, 1e-6, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
+          const bool good = lc.em(g) & (den > fma(m2, kVarGuard, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
           const double gq = fabs(w1) * cnt * fast_rcp(den);
           sn_sum += good ? gq : 0.0;
           sn_cnt += good ? 1 : 0;

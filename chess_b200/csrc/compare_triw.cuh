@@ -160,6 +160,23 @@ compare_win_tri_kernel(chess_item_args a) {
           Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
         }
         slot = slot == D - 1 ? 0 : slot + 1;
+        if (slot == 0) {
+          // the ring has just wrapped: rebuild the 7-row difference sums from its most recent seven rows
+          // (slots D-7 .. D-1).  A running sum keeps the rounding of every value that ever passed through it;
+          // rebuilt once per wrap it is exact to a few ulps of the current window
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int k = D - 7; k < D; ++k) {
+              const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
+              s1 += dk; s2 = fma(dk, dk, s2);
+            }
+            Sd[g] = s1;
+            Se[g] = hist[g] == 0u ? 0.0 : s2;
+          }
+        }
+
 
         // ---- SSIM windows whose centre row is row - H
         if (t >= t_own0 + H) {
@@ -217,12 +234,19 @@ compare_win_tri_kernel(chess_item_args a) {
           P1[1] = Sd[0]; P2[1] = Se[0];
 #pragma unroll
           for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+          // suffix sums as well: a window that ends at the strip's right edge is a suffix, and no window of 7
+          // starts after column 0 without reaching that edge (G <= 8), so nothing is ever subtracted -- a
+          // difference of prefixes would carry the rounding of every column left of the window
+          double X1[G], X2[G];
+          X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
+#pragma unroll
+          for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
           unsigned suspect = 0u;
           double up1[3], up2[3], dn1[3], dn2[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const double s1 = j == 0 ? Sd[G - 1] : (G - 1 - j == 0 ? P1[G] : P1[G] - P1[G - 1 - j]);
-            const double s2 = j == 0 ? Se[G - 1] : (G - 1 - j == 0 ? P2[G] : P2[G] - P2[G - 1 - j]);
+            const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
+            const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
             up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
             up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
             dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
@@ -232,15 +256,15 @@ compare_win_tri_kernel(chess_item_args a) {
           for (int g = 0; g < G; ++g) {
             const int a0 = g - 3 < 0 ? 0 : g - 3;
             const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
-            double w1 = a0 == 0 ? P1[b0 + 1] : P1[b0 + 1] - P1[a0];
-            double w2 = a0 == 0 ? P2[b0 + 1] : P2[b0 + 1] - P2[a0];
+            double w1 = a0 == 0 ? P1[b0 + 1] : X1[a0];
+            double w2 = a0 == 0 ? P2[b0 + 1] : X2[a0];
             if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
             if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
             const bool own = emit_row & (wc[g] != 0.0);
             const double cnt = rcnt * ccnt[g];
             const double m2 = w2 * cnt;
             const double den = fma(-w1, w1, m2);
-            const bool good = own & (den > fma(m2, 1e-6, 1e-290));
+            const bool good = own & (den > fma(m2, kVarGuard, 1e-290));
             const double gq = fabs(w1) * cnt * fast_rcp(den);
             sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
             sn_cnt += good ? wc[g] : 0.0;
