@@ -164,15 +164,14 @@ compare_win7_blk_kernel(chess_item_args a) {
           // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            double vx = 0.0, vy = 0.0, vq = 0.0, vxy = 0.0;
+            double vq = 0.0, vxy = 0.0;   // the quadratic sums only: errors in sum x, sum y enter linearly
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
               const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
-              vx += xk; vy += yk;
               vq = fma(xk, xk, fma(yk, yk, vq));
               vxy = fma(xk, yk, vxy);
             }
-            Vx[g] = vx; Vy[g] = vy; Vq[g] = vq; Vxy[g] = vxy;
+            Vq[g] = vq; Vxy[g] = vxy;
             if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
           }
         }

@@ -242,10 +242,9 @@ __device__ __forceinline__ void sn_rows(const double *__restrict__ R, const doub
       // to a few ulps of the current window, which the quiet windows after a loud stretch need
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        double s1 = 0.0, s2 = 0.0;
+        double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s1 += v; s2 = fma(v, v, s2); }
-        Sd[g] = s1;
+        for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s2 = fma(v, v, s2); }
         Se[g] = hist[g] == 0u ? 0.0 : s2;
       }
     }
@@ -402,13 +401,12 @@ __device__ __forceinline__ void win_rows(const double *__restrict__ R, const dou
       // rebuilt once per wrap it is exact to a few ulps of the current window
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        double s1 = 0.0, s2 = 0.0;
+        double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
 #pragma unroll
         for (int k = D - 7; k < D; ++k) {
           const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
-          s1 += dk; s2 = fma(dk, dk, s2);
+          s2 = fma(dk, dk, s2);
         }
-        Sd[g] = s1;
         Se[g] = hist[g] == 0u ? 0.0 : s2;
       }
     }
@@ -599,15 +597,14 @@ __device__ __forceinline__ void win7_rows(const double *__restrict__ R, const do
       // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        double vx = 0.0, vy = 0.0, vq = 0.0, vxy = 0.0;
+        double vq = 0.0, vxy = 0.0;   // the quadratic sums only: errors in sum x, sum y enter linearly
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
           const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
-          vx += xk; vy += yk;
           vq = fma(xk, xk, fma(yk, yk, vq));
           vxy = fma(xk, yk, vxy);
         }
-        Vx[g] = vx; Vy[g] = vy; Vq[g] = vq; Vxy[g] = vxy;
+        Vq[g] = vq; Vxy[g] = vxy;
         if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
       }
     }

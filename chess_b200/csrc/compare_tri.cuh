@@ -413,10 +413,9 @@ compare_r1_tri_kernel(chess_item_args a) {
             // to a few ulps of the current window, which the quiet windows after a loud stretch need
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-              double s1 = 0.0, s2 = 0.0;
+              double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
 #pragma unroll
-              for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s1 += v; s2 = fma(v, v, s2); }
-              Sd[g] = s1;
+              for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s2 = fma(v, v, s2); }
               Se[g] = hist[g] == 0u ? 0.0 : s2;
             }
           }

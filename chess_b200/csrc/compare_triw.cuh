@@ -166,13 +166,12 @@ compare_win_tri_kernel(chess_item_args a) {
           // rebuilt once per wrap it is exact to a few ulps of the current window
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            double s1 = 0.0, s2 = 0.0;
+            double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
 #pragma unroll
             for (int k = D - 7; k < D; ++k) {
               const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
-              s1 += dk; s2 = fma(dk, dk, s2);
+              s2 = fma(dk, dk, s2);
             }
-            Sd[g] = s1;
             Se[g] = hist[g] == 0u ? 0.0 : s2;
           }
         }
