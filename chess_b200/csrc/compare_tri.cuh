@@ -369,9 +369,13 @@ compare_r1_tri_kernel(chess_item_args a) {
       double vmax = -CUDART_INF, vmin = CUDART_INF;
       auto run = [&](auto minmax_tag) {
       constexpr bool MINMAX = decltype(minmax_tag)::value;
+      // strips of 3 / 4 columns run 16 warps per SM at 128 registers: the row is loaded where it is used, the
+      // other warps cover the latency; wider strips (8 warps per SM) keep the one-row software prefetch
+      constexpr bool PREFETCH = G >= 5;
       int row = first;
-      fetch(row);
+      if (PREFETCH) fetch(row);
       for (int t = 0; t < T; ++t, ++row) {
+        if (!PREFETCH) fetch(row);
         double dv[G];
         bool nzv[G];
 #pragma unroll
@@ -394,7 +398,7 @@ compare_r1_tri_kernel(chess_item_args a) {
             }
           }
         }
-        if (t + 1 < T) fetch(row + 1);
+        if (PREFETCH && t + 1 < T) fetch(row + 1);
         if (WITH_SN) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
