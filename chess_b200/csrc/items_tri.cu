@@ -6,18 +6,18 @@ int chess_items_launch_tri(chess_ctx *ctx, chess_item_args &a, int G, cudaStream
     switch (G) {
       case 3: return launch_tri<3, true>(ctx, a, stream);
       case 4: return launch_tri<4, true>(ctx, a, stream);
-      case 5: return launch_tri<5, true>(ctx, a, stream);
-      case 6: return launch_tri<6, true>(ctx, a, stream);
-      case 7: return launch_tri<7, true>(ctx, a, stream);
-      default: return launch_tri<8, true>(ctx, a, stream);
+      case 5: return launch_tri_half<5, true>(ctx, a, stream);
+      case 6: return launch_tri_half<6, true>(ctx, a, stream);
+      case 7: return launch_tri_half<7, true>(ctx, a, stream);
+      default: return launch_tri_half<8, true>(ctx, a, stream);
     }
   }
   switch (G) {
     case 3: return launch_tri<3, false>(ctx, a, stream);
     case 4: return launch_tri<4, false>(ctx, a, stream);
-    case 5: return launch_tri<5, false>(ctx, a, stream);
-    case 6: return launch_tri<6, false>(ctx, a, stream);
-    case 7: return launch_tri<7, false>(ctx, a, stream);
-    default: return launch_tri<8, false>(ctx, a, stream);
+    case 5: return launch_tri_half<5, false>(ctx, a, stream);
+    case 6: return launch_tri_half<6, false>(ctx, a, stream);
+    case 7: return launch_tri_half<7, false>(ctx, a, stream);
+    default: return launch_tri_half<8, false>(ctx, a, stream);
   }
 }
