@@ -16,6 +16,8 @@ compare_win_tri_kernel(chess_item_args a) {
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;  // ring depth in rows
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
+  __shared__ double s_part[4][4];   // per warp: totals of the parts of the current item (pair items)
+  constexpr bool HYB = G <= 4;      // pair items only for the narrow strips (see compare_tri.cuh)
   extern __shared__ __align__(16) double ringbuf[];  // per warp: D rows of x and y, D*2*G*32 doubles
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -30,7 +32,8 @@ compare_win_tri_kernel(chess_item_args a) {
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
-  const long long n_items = a.n_pairs * 2;
+  const long long n_pair_items = HYB ? a.pair_items : 0;
+  const long long n_items = n_pair_items + 2 * (a.n_pairs - n_pair_items);
 
   // the first item of every warp is its own index: no storm of atomics on one counter when the grid
   // starts; later items come from the counter, offset by the number of warps
@@ -45,9 +48,13 @@ compare_win_tri_kernel(chess_item_args a) {
     first_item = false;
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin(a, item >> 1, (int)(item & 1), 31 * G, lane, kmap, mflag, it)) continue;
+    const bool PAIR = HYB && item < n_pair_items;
+    const long long half = item - n_pair_items;   // index among the half items
+    if (!tri_item_begin(a, PAIR ? item : n_pair_items + (half >> 1), PAIR ? 0 : (int)(half & 1), 31 * G, lane, kmap,
+                        mflag, it))
+      continue;
     const long long pi = it.pi;
-    const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
+    const int part0 = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;
     const size_t rp = it.rp, qp = it.qp;
     if (lane == 0) *susp_n = 0;
@@ -55,7 +62,7 @@ compare_win_tri_kernel(chess_item_args a) {
 
     const int win = 2 * H + 1;
     if (win > np_) {
-      if (part == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
+      if (part0 == 0 && lane == 0) { a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_WINDOW_EXCEEDS; }
       continue;
     }
     const int m = np_ - win + 1;
@@ -71,6 +78,13 @@ compare_win_tri_kernel(chess_item_args a) {
     // ---- this item's lanes: rows [lo, hi), first column cbase
     int B1, B2, L1, L2;
     tri_split_halo(np_, G, HALO, B1, B2, L1, L2);
+    double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
+    bool overflow = false;
+    for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
+    if (PAIR && part == 1) {
+      if (lane == 0) *susp_n = 0;
+      __syncwarp();
+    }
     int lo = 0, hi = 0, cbase = 1 << 20;
     if (part == 0) {
       lo = 0; hi = B1; cbase = G * lane;
@@ -92,9 +106,6 @@ compare_win_tri_kernel(chess_item_args a) {
       xo[g] = (unsigned)kc;
       yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
     }
-    double *rec = a.scratch + ((size_t)pi * 2 + part) * kTriRec;
-    double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
-    bool overflow = false;
 
     if (rows_max > 0) {
       const int first = part == 0 ? 0 : max(lo - HALO, 0);       // idle lanes have lo = 0
@@ -308,16 +319,45 @@ compare_win_tri_kernel(chess_item_args a) {
       }
     }
 
-    // ---- record of this item
+    // this part's totals, reduced over the warp: exactly the numbers a half item writes to its record, added up
+    // in the order the combine adds two records -- a pair gives the same bits whichever way it ran
     {
-      const double ss = warp_sum(sn_sum);
-      const double sc = warp_sum(sn_cnt);
-      const double sw = warp_sum(ss_sum);
+      const double ws = warp_sum(sn_sum), wc = warp_sum(sn_cnt), ww = warp_sum(ss_sum);
       if (lane == 0) {
-        rec[5] = xmax; rec[6] = xmin; rec[7] = ss; rec[8] = sc;
-        rec[14] = overflow ? 1.0 : 0.0;
-        rec[15] = sw;
+        double *ptot = s_part[warp];
+        const bool first_part = part == part0;
+        ptot[0] = first_part ? ws : ptot[0] + ws;
+        ptot[1] = first_part ? wc : ptot[1] + wc;
+        ptot[2] = first_part ? ww : ptot[2] + ww;
       }
+      sn_sum = 0.0; sn_cnt = 0.0; ss_sum = 0.0;
+    }
+    }  // parts
+    __syncwarp();
+    const double PS = s_part[warp][0], PC = s_part[warp][1], PW = s_part[warp][2];
+
+    if (PAIR) {  // the whole pair was walked by this warp: verify the predicted masks and finish
+      bool bad = overflow || !tri_masks_hold(a, it, lane, kmap, mflag);
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) {
+        if (bad) {
+          a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+          atomicOr(a.retry_cur, 1);
+        } else {
+          a.ssim[pi] = PW / ((double)m * (double)m);
+          a.sn[pi] = with_sn ? PS / PC : CUDART_NAN;
+          a.status[pi] = CHESS_PAIR_OK;
+        }
+      }
+      continue;
+    }
+
+    // ---- record of this item
+    double *rec = a.scratch + ((size_t)pi * 2 + part0) * kTriRec;
+    if (lane == 0) {
+      rec[5] = xmax; rec[6] = xmin; rec[7] = PS; rec[8] = PC;
+      rec[14] = overflow ? 1.0 : 0.0;
+      rec[15] = PW;
     }
     __threadfence();
     __syncwarp();
@@ -368,7 +408,14 @@ int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
     per_sm_ncol = a.ncol_pad;
   }
   long long grid = (long long)ctx->sm_count * per_sm;
-  const long long need = (a.n_pairs * 2 + 3) / 4;
+  // narrow strips: whole waves of pairs run as pair items (compare_tri.cuh: launch_tri)
+  const long long slots = grid * 4;
+  long long pair_items = G > 4 ? 0 : (a.n_pairs >= 8 * slots ? a.n_pairs : (a.n_pairs / slots) * slots);
+  static const int pair_env = getenv("CHESS_TRI_PAIR") ? atoi(getenv("CHESS_TRI_PAIR")) : -1;  // A/B runs
+  if (pair_env == 0) pair_items = 0;
+  if (pair_env == 1 && G <= 4) pair_items = a.n_pairs;
+  a.pair_items = pair_items;
+  const long long need = (pair_items + 2 * (a.n_pairs - pair_items) + 3) / 4;
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, 128, smem, stream>>>(a);
   ctx->launches += 1;
