@@ -51,7 +51,8 @@ class chess_params(C.Structure):
     _fields_ = [("min_bins", C.c_int32), ("keep_unmappable", C.c_int32),
                 ("abs_window", C.c_int32), ("compute_sn", C.c_int32),
                 ("rel_window", C.c_double), ("mappability_cutoff", C.c_double),
-                ("default_value", C.c_double), ("kernel", C.c_int32), ("flags", C.c_int32)]
+                ("default_value", C.c_double), ("kernel", C.c_int32), ("flags", C.c_int32),
+                ("data_range", C.c_double)]
 
 
 PAIR_DTYPE = np.dtype([("ref_off", "<i8"), ("qry_off", "<i8"), ("ref_pitch", "<i4"),
@@ -104,8 +105,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-# the struct layouts above follow include/chess_b200.h at this ABI version (chess_sample grew `rowpre` in 2)
-ABI_VERSION = 2
+# the struct layouts above follow include/chess_b200.h at this ABI version (chess_sample grew `rowpre` in 2,
+# chess_params grew `data_range` in 3)
+ABI_VERSION = 3
 if lib.chess_abi_version() != ABI_VERSION:
     raise ChessNativeError("libchess_b200.so has ABI version {}, this binding expects {}: rebuild with "
                            "python -m chess_b200.build".format(lib.chess_abi_version(), ABI_VERSION))
@@ -150,8 +152,9 @@ class Context(object):
 
 def make_params(min_bins=20, keep_unmappable_bins=False, absolute_window_size=None,
                 relative_window_size=1.0, mappability_cutoff=0.1, default_value=1,
-                compute_sn=True, kernel=0, flags=0):
+                compute_sn=True, kernel=0, flags=0, data_range=None):
     p = chess_params()
+    p.data_range = float(data_range) if data_range else 0.0
     p.min_bins = int(min_bins)
     p.keep_unmappable = 1 if keep_unmappable_bins else 0
     p.abs_window = int(absolute_window_size) if absolute_window_size else 0

@@ -84,6 +84,7 @@ extern "C" int64_t chess_launch_count(const chess_ctx *ctx) { return ctx ? ctx->
 static int validate(chess_ctx *ctx, const chess_params *p) {
   if (!p) { ctx->err = "params is NULL"; return CHESS_ERR_ARG; }
   if (p->abs_window < 0) { ctx->err = "abs_window must be >= 0"; return CHESS_ERR_ARG; }
+  if (!(p->data_range >= 0.0)) { ctx->err = "data_range must be >= 0 (0 = from the data)"; return CHESS_ERR_ARG; }
   return CHESS_OK;
 }
 
@@ -101,7 +102,7 @@ extern "C" int chess_compare_batch(chess_ctx *ctx, const double *ref_base, const
   if (n_pairs == 0) return CHESS_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (params->kernel != 1) {
+  if (params->kernel != 1 && params->data_range == 0.0) {   // a fixed data range is the generic kernel's
     bool handled = false;
     rc = chess_launch_compare_fast(ctx, ref_base, qry_base, pairs, n_pairs, max_n, *params, ssim, sn,
                                    status, stream, &handled);
@@ -129,7 +130,7 @@ extern "C" int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref,
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
   chess_params p = *params;
   p.flags |= CHESS_FLAG_SYMMETRIC;  // a band is symmetric by construction
-  if (p.kernel == 0 || p.kernel == 3) {
+  if ((p.kernel == 0 || p.kernel == 3) && p.data_range == 0.0) {
     bool handled = false;
     rc = chess_launch_compare_items(ctx, ref, qry, pairs, n_pairs, max_n, p, ssim, sn, status, stream, &handled);
     if (rc) return rc;

@@ -296,7 +296,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
     }
     const double dmax = block_max<BLOCK>(vmax, red);
     const double dmin = -block_max<BLOCK>(-vmin, red);
-    const double drange = dmax - dmin;
+    const double drange = p.data_range > 0.0 ? p.data_range : dmax - dmin;
 
     // ---- 5. SSIM over every valid window
     const int m = np_ - win + 1;

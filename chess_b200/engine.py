@@ -437,24 +437,36 @@ def compare_dense_pairs(references, queries, flips, device=None, default_value=1
 
     The matrices are packed back to back in one device buffer per side and
     described to the kernel as pitch-n views (the dense branch of chess_pair).
+    An array object that occurs several times in a list is uploaded once: the
+    one-vs-many shape of utils/run_synthetic_test.py:105-110 (one reference
+    against the truth and 1000 decoys) costs one copy of the reference.
+    `data_range=2.0` reproduces what that script's legacy `compare_ssim` call
+    assumes for float images (run_synthetic_test.py:306); the default takes the
+    range from the data as `chess sim` does (sim.py:368-374).
     """
     device = visible_devices()[0] if device is None else int(device)
     ctx = get_context(device)
     dev = torch.device("cuda", device)
     n_pairs = len(references)
     tab = np.zeros(n_pairs, dtype=PAIR_DTYPE)
-    r_off = q_off = 0
+
+    def pack(mats):
+        offs, seen, parts, total = [], {}, [], 0
+        for m in mats:
+            if m.ndim != 2 or m.shape[0] != m.shape[1]:
+                raise ValueError("compare_dense_pairs expects square matrices")
+            if id(m) not in seen:
+                seen[id(m)] = total
+                parts.append(np.ascontiguousarray(m, dtype=np.float64).ravel())
+                total += m.size
+            offs.append(seen[id(m)])
+        return offs, (np.concatenate(parts) if parts else np.zeros(1))
+
+    r_offs, h_ref = pack(references)
+    q_offs, h_qry = pack(queries)
     for k, (r, q) in enumerate(zip(references, queries)):
-        if r.ndim != 2 or q.ndim != 2 or r.shape[0] != r.shape[1] or q.shape[0] != q.shape[1]:
-            raise ValueError("compare_dense_pairs expects square matrices")
-        tab[k] = (r_off, q_off, r.shape[0], q.shape[0], r.shape[0], q.shape[0], 1 if flips[k] else 0, 0)
-        r_off += r.size
-        q_off += q.size
+        tab[k] = (r_offs[k], q_offs[k], r.shape[0], q.shape[0], r.shape[0], q.shape[0], 1 if flips[k] else 0, 0)
     max_n = int(max([r.shape[0] for r in references] + [q.shape[0] for q in queries] + [1]))
-    h_ref = np.concatenate([np.ascontiguousarray(r, dtype=np.float64).ravel() for r in references]) \
-        if n_pairs else np.zeros(1)
-    h_qry = np.concatenate([np.ascontiguousarray(q, dtype=np.float64).ravel() for q in queries]) \
-        if n_pairs else np.zeros(1)
     p = _native.make_params(default_value=default_value, **params)
     ssim = np.empty(n_pairs)
     sn = np.empty(n_pairs)

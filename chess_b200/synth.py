@@ -156,3 +156,50 @@ def write_dataset(directory, genome, ref, qry, pairs):
     return {k: os.path.join(directory, v) for k, v in (
         ("regions", "regions.bed"), ("reference", "reference.sparse"),
         ("query", "query.sparse"), ("pairs", "pairs.bedpe"))}
+
+
+# ---------------------------------------------------------------- dense matrices of BASELINE configs[0]
+def dense_decay(n):
+    """Distance-decay background of utils/make_synthetic_references.py:93-109:
+    linspace(1e-4, 1, 1000)^-0.85 along the diagonals (first n values), clipped at 1."""
+    decay = np.power(np.linspace(0.0001, 1, 1000), -0.85)
+    d = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
+    return np.maximum(decay[np.minimum(d, 999)], 1.0)
+
+
+def dense_features(n, rng, levels=(75.0, 100.0, 150.0), loop_prob=0.5):
+    """Nested TAD blocks (+75 / +100 / +150 per level) with corner loops, after
+    make_synthetic_references.py:66-90; returns the symmetric feature matrix to add
+    to `dense_decay`.  Level k cuts every level k-1 domain into smaller ones."""
+    m = np.zeros((n, n))
+    borders = [0, n]
+    for lvl, inc in enumerate(levels):
+        nxt = [0]
+        for a, b in zip(borders[:-1], borders[1:]):
+            k = int(rng.integers(2, 5)) if b - a >= 12 else 1
+            cuts = np.sort(rng.choice(np.arange(a + 3, max(b - 3, a + 4)), size=k - 1, replace=False)) if k > 1 else []
+            nxt.extend(int(c) for c in cuts)
+            nxt.append(b)
+        borders = sorted(set(nxt))
+        for a, b in zip(borders[:-1], borders[1:]):
+            m[a:b, a:b] += inc
+            if rng.random() < loop_prob and b - a >= 6:
+                rad = max(int((b - a) * 0.05), 1)
+                m[max(a - rad, 0):a + rad, b - rad:min(b + rad, n)] += inc * float(rng.uniform(0.5, 1.5))
+    return np.triu(m) + np.triu(m, 1).T
+
+
+def dense_noisy(m, rng, noise=0.2):
+    """Multiplicative lognormal noise, symmetric, strictly positive (so that log2(O/E) stays finite)."""
+    e = rng.lognormal(0.0, noise, m.shape)
+    e = np.triu(e) + np.triu(e, 1).T
+    return m * e
+
+
+def dense_oe(m):
+    """Matrix divided by its per-diagonal mean (utils/run_synthetic_test.py:335-346)."""
+    n = m.shape[0]
+    d = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
+    sums = np.bincount(d.ravel(), weights=m.ravel(), minlength=n)
+    cnt = np.bincount(d.ravel(), minlength=n)
+    return m / (sums / cnt)[d]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CHESS_B200_ABI_VERSION 2
+#define CHESS_B200_ABI_VERSION 3
 
 typedef struct chess_ctx chess_ctx;
 
@@ -88,6 +88,12 @@ typedef struct chess_params {
                                 2 = skip the work-item kernels, 3 = work-item
                                 kernel without the upper-triangle form (A/B)   */
   int32_t flags;             /* CHESS_FLAG_* promises about the batch          */
+  double data_range;         /* 0 = max - min of the compacted pair, as chess sim
+                                passes it (sim.py:368-374); > 0 = this value, e.g.
+                                2.0, what skimage's legacy compare_ssim assumes for
+                                float images when utils/run_synthetic_test.py:306
+                                calls it without data_range.  Such batches run on
+                                the generic kernel.  (ABI 3)                      */
 } chess_params;
 
 /* Promises the caller makes about a batch; they only select faster kernels and

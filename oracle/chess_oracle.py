@@ -421,6 +421,40 @@ def structural_similarity_bruteforce(im1, im2, win_size, data_range):
     return s.mean(dtype=np.float64)
 
 
+def synthetic_window_size(n_bins, rel_window):
+    """Window of `compare_matrices`, utils/run_synthetic_test.py:302-305."""
+    win = int(n_bins * rel_window)
+    if win % 2 == 0:
+        win -= 1
+    return max(win, 7)
+
+
+def synthetic_compare_matrices(a, b, rel_window, data_range=2.0):
+    """`compare_matrices` of utils/run_synthetic_test.py:279-308 (BASELINE configs[0]), scaling mode 1:
+    the smaller matrix is resized up (order 0), then `compare_ssim(a, b, win_size=...)` -- the legacy
+    skimage call without data_range, which for float images takes the dtype's range -1 .. 1 = 2.0
+    (un-vendored dependency, PARITY UNPINNED; the value is stated and is a parameter)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.shape[0] > b.shape[0]:
+        big, small = a, resize_order0(b, a.shape)
+        a, b = big, small
+    elif b.shape[0] > a.shape[0]:
+        a, b = b, resize_order0(a, b.shape)
+    win = synthetic_window_size(a.shape[0], rel_window)
+    return structural_similarity(a, b, win_size=win, data_range=data_range)
+
+
+def synthetic_truth_and_controls(reference, query, pool, rel_window, data_range=2.0):
+    """Truth SSIM, control SSIMs, p and z of utils/run_synthetic_test.py:105-115."""
+    truth = synthetic_compare_matrices(reference, query, rel_window, data_range)
+    control = np.array([synthetic_compare_matrices(reference, t, rel_window, data_range) for t in pool])
+    p = float(np.sum(control >= truth)) / max(len(pool), 1)
+    allv = np.concatenate([control, [truth]])
+    z = float((truth - allv.mean()) / allv.std())
+    return truth, control, p, z
+
+
 def resize_nearest_index(n_in, n_out):
     """Source index for every output index of an order-0 resize n_in -> n_out.
 
