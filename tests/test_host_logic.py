@@ -21,8 +21,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     from chess_b200 import _native
-    assert lib.chess_abi_version() == _native.ABI_VERSION == 2
-    assert ctypes.sizeof(_native.chess_pair) == 40 and ctypes.sizeof(_native.chess_params) == 48
+    assert lib.chess_abi_version() == _native.ABI_VERSION == 3
+    assert ctypes.sizeof(_native.chess_pair) == 40 and ctypes.sizeof(_native.chess_params) == 56
 
 
 def test_no_gpu_fails_loudly():
