@@ -170,8 +170,8 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *red = reinterpret_cast<double *>(smem_raw);
-  double *buf = red + kRed;                       // max(5*ncap, 9*ncap+12) doubles
-  int *mr = reinterpret_cast<int *>(buf + 9 * (size_t)ncap + 12);
+  double *buf = red + kRed;                       // max(10*ncap, 9*ncap+12) doubles
+  int *mr = reinterpret_cast<int *>(buf + 10 * (size_t)ncap + 12);
   int *mq = mr + ncap;                            // pre-compaction source indices
   int *kr = mq + ncap;
   int *kq = kr + ncap;                            // compacted source indices
@@ -209,10 +209,11 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
     const double masked_sum = (double)n * p.default_value;
     double vmax = -CUDART_INF, vmin = CUDART_INF;
     int cnt_r = 0, cnt_q = 0;
+    const bool need_pass = use_masks || !(p.data_range > 0.0);   // neither sums nor extremes are wanted otherwise
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       const int c = tid + j * BLOCK;
-      if (c < n) {
+      if (need_pass && c < n) {
         const int cr = mr[c], cq = mq[c];
         double sr = 0.0, sq = 0.0;
         for (int r = 0; r < n; ++r) {
@@ -306,59 +307,131 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
     const double C2 = (0.03 * drange) * (0.03 * drange);
     double acc = 0.0;
     {
+      // Thread t owns the CPT adjacent compacted columns CPT*t .. CPT*t+CPT-1: five running sums down
+      // each column (add the incoming row, subtract the row that left the window).  Across the row the
+      // window sum is a difference of prefix sums; the prefix is built in registers -- over the thread's
+      // columns, then a shuffle scan over the lanes -- and only the warp-level prefixes and the warp
+      // totals go through shared memory, double-buffered by row parity: ONE barrier per row.
+      constexpr int NW = BLOCK / 32;
+      double *pre = buf;            // [2][5][ncap] inclusive prefix within the owning warp
+      double *wtot = red + 64;      // [2][5][8]    totals of the warps
+      const int c0 = CPT * tid;
       double V[CPT][5];
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
 #pragma unroll
         for (int k = 0; k < 5; ++k) V[j][k] = 0.0;
+      int kcr[CPT], kcq[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        kcr[j] = c0 + j < np_ ? kr[c0 + j] : 0;
+        kcq[j] = c0 + j < np_ ? kq[c0 + j] : 0;
+      }
+      // S = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)) with every mean written as
+      // window sum / NP: numerator and denominator are scaled by NP^4, one division per window
+      const double c1s = C1 * NP * NP, c2s = C2 * NP * NP;
+      // rows enter and leave through registers loaded one iteration ahead (the loads of row r+1 are in
+      // flight while row r goes through the scan and the barrier)
+      double nx[CPT], ny[CPT], ox[CPT], oy[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const bool live = c0 + j < np_;
+        nx[j] = live ? __ldg(R + (size_t)kr[0] * rp + kcr[j]) : 0.0;
+        ny[j] = live ? __ldg(Q + (size_t)kq[0] * qp + kcq[j]) : 0.0;
+        ox[j] = 0.0; oy[j] = 0.0;
+      }
       for (int r = 0; r < np_; ++r) {
-        const size_t ro = (size_t)kr[r] * rp, qo = (size_t)kq[r] * qp;
-        const bool sub = r >= win;
-        const size_t ro2 = sub ? (size_t)kr[r - win] * rp : 0, qo2 = sub ? (size_t)kq[r - win] * qp : 0;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const int c = tid + j * BLOCK;
-          if (c < np_) {
-            const double x = __ldg(R + ro + kr[c]), y = __ldg(Q + qo + kq[c]);
-            V[j][0] += x; V[j][1] += y; V[j][2] += x * x; V[j][3] += y * y; V[j][4] += x * y;
-            if (sub) {
-              const double xo = __ldg(R + ro2 + kr[c]), yo = __ldg(Q + qo2 + kq[c]);
-              V[j][0] -= xo; V[j][1] -= yo; V[j][2] -= xo * xo; V[j][3] -= yo * yo; V[j][4] -= xo * yo;
-            }
+          const double x = nx[j], y = ny[j], xo = ox[j], yo = oy[j];
+          V[j][0] += x; V[j][1] += y; V[j][2] += x * x; V[j][3] += y * y; V[j][4] += x * y;
+          V[j][0] -= xo; V[j][1] -= yo; V[j][2] -= xo * xo; V[j][3] -= yo * yo; V[j][4] -= xo * yo;
+        }
+        if (r + 1 < np_) {
+          const size_t ro = (size_t)kr[r + 1] * rp, qo = (size_t)kq[r + 1] * qp;
+          const bool sub = r + 1 >= win;
+          const size_t ro2 = sub ? (size_t)kr[r + 1 - win] * rp : 0, qo2 = sub ? (size_t)kq[r + 1 - win] * qp : 0;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const bool live = c0 + j < np_;
+            nx[j] = live ? __ldg(R + ro + kcr[j]) : 0.0;
+            ny[j] = live ? __ldg(Q + qo + kcq[j]) : 0.0;
+            ox[j] = live && sub ? __ldg(R + ro2 + kcr[j]) : 0.0;
+            oy[j] = live && sub ? __ldg(Q + qo2 + kcq[j]) : 0.0;
           }
         }
-        if (r >= win - 1) {
+        if (r >= win - 1) {   // uniform across the CTA
+          const int par = r & 1;
+          double W[5], E[5];
 #pragma unroll
-          for (int j = 0; j < CPT; ++j) {
-            const int c = tid + j * BLOCK;
-            if (c < np_) {
+          for (int k = 0; k < 5; ++k) {
+            W[k] = V[0][k];
 #pragma unroll
-              for (int k = 0; k < 5; ++k) buf[k * ncap + c] = V[j][k];
+            for (int j = 1; j < CPT; ++j) W[k] += V[j][k];
+          }
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              const double t = __shfl_up_sync(0xffffffffu, W[k], o);
+              if (lane >= o) W[k] += t;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const double t = __shfl_up_sync(0xffffffffu, W[k], 1);
+            E[k] = lane ? t : 0.0;                       // exclusive prefix of this thread within its warp
+            if (lane == 31) wtot[(par * 5 + k) * 8 + warp] = W[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            double run = E[k];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              run += V[j][k];
+              if (c0 + j < np_) pre[(size_t)(par * 5 + k) * ncap + c0 + j] = run;
             }
           }
           __syncthreads();
-          block_scan5<BLOCK>(buf, ncap, np_, red);
+          // inclusive scan of the warp totals (lanes 0 .. NW-1 of every warp, redundantly)
+          double inc[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            inc[k] = lane < NW ? wtot[(par * 5 + k) * 8 + lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < NW; o <<= 1) {
+              const double t = __shfl_up_sync(0xffffffffu, inc[k], o);
+              if (lane >= o) inc[k] += t;
+            }
+            const double t = __shfl_sync(0xffffffffu, inc[k], warp ? warp - 1 : 0);
+            E[k] += warp ? t : 0.0;                      // + the warps left of this one: prefix left of column c0
+          }
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
-            const int c = tid + j * BLOCK;
+            const int c = c0 + j;
+            const int hi = min(c + win - 1, np_ - 1);
+            const int whi = (hi / CPT) >> 5;             // warp that owns column hi
+            double h[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {                // shuffles outside the divergent branch below
+              const double t = __shfl_sync(0xffffffffu, inc[k], whi ? whi - 1 : 0);
+              h[k] = whi ? t : 0.0;
+            }
             if (c < m) {
-              double h[5];
 #pragma unroll
-              for (int k = 0; k < 5; ++k)
-                h[k] = buf[k * ncap + c + win - 1] - (c ? buf[k * ncap + c - 1] : 0.0);
-              const double ux = h[0] / NP, uy = h[1] / NP;
-              const double uxx = h[2] / NP, uyy = h[3] / NP, uxy = h[4] / NP;
-              const double vx = cov_norm * (uxx - ux * ux);
-              const double vy = cov_norm * (uyy - uy * uy);
-              const double vxy = cov_norm * (uxy - ux * uy);
-              const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2;
-              const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
-              acc += (A1 * A2) / (B1 * B2);
+              for (int k = 0; k < 5; ++k) h[k] = (pre[(size_t)(par * 5 + k) * ncap + hi] + h[k]) - E[k];
+              const double pxy = h[0] * h[1], pxx = h[0] * h[0], pyy = h[1] * h[1];
+              const double a1 = 2.0 * pxy + c1s, b1 = pxx + pyy + c1s;
+              const double a2 = 2.0 * cov_norm * (NP * h[4] - pxy) + c2s;
+              const double b2 = cov_norm * ((NP * h[2] - pxx) + (NP * h[3] - pyy)) + c2s;
+              acc += (a1 * a2) / (b1 * b2);
             }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) E[k] += V[j][k];   // prefix left of the next column
           }
-          __syncthreads();
         }
       }
+      __syncthreads();   // the last row's reads of wtot / pre are done before red / buf are reused
     }
     const double ssim = block_sum<BLOCK>(acc, red) / ((double)m * (double)m);
 
@@ -433,7 +506,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
 }
 
 size_t generic_smem_bytes(int ncap) {
-  size_t doubles = kRed + 9 * (size_t)ncap + 12;
+  size_t doubles = kRed + 10 * (size_t)ncap + 12;
   size_t ints = 4 * (size_t)ncap + 64;
   size_t bytes = doubles * 8 + ints * 4 + (size_t)ncap;
   return (bytes + 15) & ~size_t(15);
