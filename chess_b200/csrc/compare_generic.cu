@@ -63,54 +63,6 @@ __device__ __forceinline__ double block_max(double v, double *red) {
   return v;
 }
 
-// In-place inclusive scan of five arrays buf[k*stride + 0..len) across the block.
-template <int BLOCK>
-__device__ __forceinline__ void block_scan5(double *buf, int stride, int len, double *red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = BLOCK / 32;
-  double carry[5] = {0, 0, 0, 0, 0};
-  for (int base = 0; base < len; base += BLOCK) {
-    const int idx = base + threadIdx.x;
-    double v[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) v[k] = idx < len ? buf[k * stride + idx] : 0.0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        double t = __shfl_up_sync(0xffffffffu, v[k], o);
-        if (lane >= o) v[k] += t;
-      }
-    }
-    if (lane == 31) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) red[k * 32 + warp] = v[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        double t = lane < NW ? red[k * 32 + lane] : 0.0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          double u = __shfl_up_sync(0xffffffffu, t, o);
-          if (lane >= o) t += u;
-        }
-        red[k * 32 + lane] = t;  // inclusive prefix of warp totals
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      double off = carry[k] + (warp ? red[k * 32 + warp - 1] : 0.0);
-      v[k] += off;
-      if (idx < len) buf[k * stride + idx] = v[k];
-      carry[k] += red[k * 32 + NW - 1];
-    }
-    __syncthreads();
-  }
-}
-
 // numpy's pairwise summation for n = 49 contiguous doubles (n < 128: eight
 // running accumulators over blocks of eight, combined as a tree, then the tail).
 __device__ __forceinline__ double numpy_sum49(const double *a) {
@@ -170,8 +122,8 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *red = reinterpret_cast<double *>(smem_raw);
-  double *buf = red + kRed;                       // max(10*ncap, 9*ncap+12) doubles
-  int *mr = reinterpret_cast<int *>(buf + 10 * (size_t)ncap + 12);
+  double *buf = red + kRed;                       // max(10*(ncap+3), 9*ncap+12) doubles
+  int *mr = reinterpret_cast<int *>(buf + 10 * (size_t)ncap + 44);
   int *mq = mr + ncap;                            // pre-compaction source indices
   int *kr = mq + ncap;
   int *kq = kr + ncap;                            // compacted source indices
@@ -313,7 +265,10 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
       // columns, then a shuffle scan over the lanes -- and only the warp-level prefixes and the warp
       // totals go through shared memory, double-buffered by row parity: ONE barrier per row.
       constexpr int NW = BLOCK / 32;
-      double *pre = buf;            // [2][5][ncap] inclusive prefix within the owning warp
+      // column c of a prefix array sits at (c % CPT) * PS + c / CPT: the threads of a warp store and
+      // load consecutive words (no bank conflicts at any CPT)
+      const int PS = (ncap + CPT - 1) / CPT, PA = PS * CPT;
+      double *pre = buf;            // [2][5][PA] inclusive prefix within the owning warp
       double *wtot = red + 64;      // [2][5][8]    totals of the warps
       const int c0 = CPT * tid;
       double V[CPT][5];
@@ -333,13 +288,27 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
       // rows enter and leave through registers loaded one iteration ahead (the loads of row r+1 are in
       // flight while row r goes through the scan and the barrier)
       double nx[CPT], ny[CPT], ox[CPT], oy[CPT];
+      // dense, uncompacted, unresized views with an even pitch and a 16-byte aligned origin: the thread's
+      // adjacent columns are adjacent in memory and come in 16-byte loads (half the L1 wavefronts)
+      static_assert(CPT % 2 == 0, "columns are loaded in pairs");
+      const bool vecx = np_ == n && d.ref_n == n && (rp & 1) == 0 && (reinterpret_cast<size_t>(R) & 15) == 0;
+      const bool vecy = np_ == n && d.qry_n == n && !d.flip && (qp & 1) == 0 && (reinterpret_cast<size_t>(Q) & 15) == 0;
+      auto load_cols = [&](const double *row, const int *kc, bool vec, bool on, double *out) {
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const bool live = c0 + j < np_;
-        nx[j] = live ? __ldg(R + (size_t)kr[0] * rp + kcr[j]) : 0.0;
-        ny[j] = live ? __ldg(Q + (size_t)kq[0] * qp + kcq[j]) : 0.0;
-        ox[j] = 0.0; oy[j] = 0.0;
-      }
+        for (int i = 0; i < CPT; i += 2) {
+          if (on && vec && c0 + i + 1 < np_) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(row + c0 + i));
+            out[i] = v.x; out[i + 1] = v.y;
+          } else {
+            out[i] = on && c0 + i < np_ ? __ldg(row + kc[i]) : 0.0;
+            out[i + 1] = on && c0 + i + 1 < np_ ? __ldg(row + kc[i + 1]) : 0.0;
+          }
+        }
+      };
+      load_cols(R + (size_t)kr[0] * rp, kcr, vecx, true, nx);
+      load_cols(Q + (size_t)kq[0] * qp, kcq, vecy, true, ny);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { ox[j] = 0.0; oy[j] = 0.0; }
       for (int r = 0; r < np_; ++r) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
@@ -348,17 +317,11 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
           V[j][0] -= xo; V[j][1] -= yo; V[j][2] -= xo * xo; V[j][3] -= yo * yo; V[j][4] -= xo * yo;
         }
         if (r + 1 < np_) {
-          const size_t ro = (size_t)kr[r + 1] * rp, qo = (size_t)kq[r + 1] * qp;
           const bool sub = r + 1 >= win;
-          const size_t ro2 = sub ? (size_t)kr[r + 1 - win] * rp : 0, qo2 = sub ? (size_t)kq[r + 1 - win] * qp : 0;
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) {
-            const bool live = c0 + j < np_;
-            nx[j] = live ? __ldg(R + ro + kcr[j]) : 0.0;
-            ny[j] = live ? __ldg(Q + qo + kcq[j]) : 0.0;
-            ox[j] = live && sub ? __ldg(R + ro2 + kcr[j]) : 0.0;
-            oy[j] = live && sub ? __ldg(Q + qo2 + kcq[j]) : 0.0;
-          }
+          load_cols(R + (size_t)kr[r + 1] * rp, kcr, vecx, true, nx);
+          load_cols(Q + (size_t)kq[r + 1] * qp, kcq, vecy, true, ny);
+          load_cols(R + (size_t)kr[sub ? r + 1 - win : 0] * rp, kcr, vecx, sub, ox);
+          load_cols(Q + (size_t)kq[sub ? r + 1 - win : 0] * qp, kcq, vecy, sub, oy);
         }
         if (r >= win - 1) {   // uniform across the CTA
           const int par = r & 1;
@@ -381,7 +344,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
           for (int k = 0; k < 5; ++k) {
             const double t = __shfl_up_sync(0xffffffffu, W[k], 1);
             E[k] = lane ? t : 0.0;                       // exclusive prefix of this thread within its warp
-            if (lane == 31) wtot[(par * 5 + k) * 8 + warp] = W[k];
+            if (NW > 1 && lane == 31) wtot[(par * 5 + k) * 8 + warp] = W[k];
           }
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
@@ -389,22 +352,24 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
               run += V[j][k];
-              if (c0 + j < np_) pre[(size_t)(par * 5 + k) * ncap + c0 + j] = run;
+              if (c0 + j < np_) pre[(par * 5 + k) * PA + j * PS + tid] = run;
             }
           }
           __syncthreads();
           // inclusive scan of the warp totals (lanes 0 .. NW-1 of every warp, redundantly)
           double inc[5];
+          if (NW > 1) {
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            inc[k] = lane < NW ? wtot[(par * 5 + k) * 8 + lane] : 0.0;
+            for (int k = 0; k < 5; ++k) {
+              inc[k] = lane < NW ? wtot[(par * 5 + k) * 8 + lane] : 0.0;
 #pragma unroll
-            for (int o = 1; o < NW; o <<= 1) {
-              const double t = __shfl_up_sync(0xffffffffu, inc[k], o);
-              if (lane >= o) inc[k] += t;
+              for (int o = 1; o < NW; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc[k], o);
+                if (lane >= o) inc[k] += t;
+              }
+              const double t = __shfl_sync(0xffffffffu, inc[k], warp ? warp - 1 : 0);
+              E[k] += warp ? t : 0.0;                    // + the warps left of this one: prefix left of column c0
             }
-            const double t = __shfl_sync(0xffffffffu, inc[k], warp ? warp - 1 : 0);
-            E[k] += warp ? t : 0.0;                      // + the warps left of this one: prefix left of column c0
           }
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
@@ -414,12 +379,15 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
             double h[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {                // shuffles outside the divergent branch below
-              const double t = __shfl_sync(0xffffffffu, inc[k], whi ? whi - 1 : 0);
-              h[k] = whi ? t : 0.0;
+              h[k] = 0.0;
+              if (NW > 1) {
+                const double t = __shfl_sync(0xffffffffu, inc[k], whi ? whi - 1 : 0);
+                h[k] = whi ? t : 0.0;
+              }
             }
             if (c < m) {
 #pragma unroll
-              for (int k = 0; k < 5; ++k) h[k] = (pre[(size_t)(par * 5 + k) * ncap + hi] + h[k]) - E[k];
+              for (int k = 0; k < 5; ++k) h[k] = (pre[(par * 5 + k) * PA + (hi % CPT) * PS + hi / CPT] + h[k]) - E[k];
               const double pxy = h[0] * h[1], pxx = h[0] * h[0], pyy = h[1] * h[1];
               const double a1 = 2.0 * pxy + c1s, b1 = pxx + pyy + c1s;
               const double a2 = 2.0 * cov_norm * (NP * h[4] - pxy) + c2s;
@@ -506,7 +474,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
 }
 
 size_t generic_smem_bytes(int ncap) {
-  size_t doubles = kRed + 10 * (size_t)ncap + 12;
+  size_t doubles = kRed + 10 * (size_t)ncap + 44;
   size_t ints = 4 * (size_t)ncap + 64;
   size_t bytes = doubles * 8 + ints * 4 + (size_t)ncap;
   return (bytes + 15) & ~size_t(15);
@@ -565,8 +533,9 @@ int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const d
     return CHESS_ERR_UNSUPPORTED;
   }
   const int ncap = max_n < 32 ? 32 : max_n;
-  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  // four adjacent columns per thread in the SSIM loop: a pair of <= 128 bins is one warp (no cross-warp step)
+  if (ncap <= 128) return launch<32, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 256) return launch<64, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 512) return launch<128, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
   return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
 }
