@@ -290,19 +290,23 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
       double nx[CPT], ny[CPT], ox[CPT], oy[CPT];
       // dense, uncompacted, unresized views with an even pitch and a 16-byte aligned origin: the thread's
       // adjacent columns are adjacent in memory and come in 16-byte loads (half the L1 wavefronts)
-      static_assert(CPT % 2 == 0, "columns are loaded in pairs");
       const bool vecx = np_ == n && d.ref_n == n && (rp & 1) == 0 && (reinterpret_cast<size_t>(R) & 15) == 0;
       const bool vecy = np_ == n && d.qry_n == n && !d.flip && (qp & 1) == 0 && (reinterpret_cast<size_t>(Q) & 15) == 0;
       auto load_cols = [&](const double *row, const int *kc, bool vec, bool on, double *out) {
+        if constexpr (CPT % 2 == 0) {
 #pragma unroll
-        for (int i = 0; i < CPT; i += 2) {
-          if (on && vec && c0 + i + 1 < np_) {
-            const double2 v = __ldg(reinterpret_cast<const double2 *>(row + c0 + i));
-            out[i] = v.x; out[i + 1] = v.y;
-          } else {
-            out[i] = on && c0 + i < np_ ? __ldg(row + kc[i]) : 0.0;
-            out[i + 1] = on && c0 + i + 1 < np_ ? __ldg(row + kc[i + 1]) : 0.0;
+          for (int i = 0; i < CPT; i += 2) {
+            if (on && vec && c0 + i + 1 < np_) {
+              const double2 v = __ldg(reinterpret_cast<const double2 *>(row + c0 + i));
+              out[i] = v.x; out[i + 1] = v.y;
+            } else {
+              out[i] = on && c0 + i < np_ ? __ldg(row + kc[i]) : 0.0;
+              out[i + 1] = on && c0 + i + 1 < np_ ? __ldg(row + kc[i + 1]) : 0.0;
+            }
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) out[i] = on && c0 + i < np_ ? __ldg(row + kc[i]) : 0.0;
         }
       };
       load_cols(R + (size_t)kr[0] * rp, kcr, vecx, true, nx);
@@ -534,8 +538,17 @@ int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const d
   }
   const int ncap = max_n < 32 ? 32 : max_n;
   // four adjacent columns per thread in the SSIM loop: a pair of <= 128 bins is one warp (no cross-warp step)
-  if (ncap <= 128) return launch<32, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-  if (ncap <= 256) return launch<64, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-  if (ncap <= 512) return launch<128, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (!p.compute_sn) {
+    // SSIM only (background comparisons, the dense one-vs-many batches of configs[0]): four adjacent columns
+    // per thread amortise the prefix shuffles; a pair of <= 128 bins is one warp (no cross-warp step)
+    if (ncap <= 128) return launch<32, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+    if (ncap <= 256) return launch<64, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+    if (ncap <= 512) return launch<128, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+    return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  }
+  // with SN the 7-row window phase wants a thread per column (measured: 573 us against 699 us on configs[1])
+  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
   return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
 }
