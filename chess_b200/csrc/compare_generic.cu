@@ -28,7 +28,8 @@
 
 namespace {
 
-constexpr int kRed = 192;  // doubles of reduction / scan scratch
+constexpr int kRed = 384;  // doubles of reduction / scan scratch (block reductions: 0..32, warp totals: 64..223,
+                           // warp offsets: 224..383)
 
 template <int BLOCK>
 __device__ __forceinline__ double block_sum(double v, double *red) {
@@ -108,8 +109,10 @@ __device__ __noinline__ double sn_window_twopass(const double *ring, int stride,
   return __ddiv_rn(fabs(avg), var);
 }
 
-template <int BLOCK, int CPT>
-__global__ void __launch_bounds__(BLOCK)
+// WITH_SN = false drops the SN phase from the instantiation (SSIM-only batches: background comparisons, the
+// dense one-vs-many batches of configs[0]); its registers then allow MINB CTAs of BLOCK threads per SM.
+template <int BLOCK, int CPT, bool WITH_SN, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 compare_generic_kernel(const double *__restrict__ ref_base, const double *__restrict__ qry_base,
                        const chess_pair *__restrict__ pairs, long long n_pairs, int ncap,
                        chess_params p, double *__restrict__ ssim_out, double *__restrict__ sn_out,
@@ -269,7 +272,8 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
       // load consecutive words (no bank conflicts at any CPT)
       const int PS = (ncap + CPT - 1) / CPT, PA = PS * CPT;
       double *pre = buf;            // [2][5][PA] inclusive prefix within the owning warp
-      double *wtot = red + 64;      // [2][5][8]    totals of the warps
+      double *wtot = red + 64;      // [2][5][16]   totals of the warps
+      double *woff = red + 224;     // [2][5][16]   sum of the warps left of a warp
       const int c0 = CPT * tid;
       double V[CPT][5];
 #pragma unroll
@@ -348,7 +352,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
           for (int k = 0; k < 5; ++k) {
             const double t = __shfl_up_sync(0xffffffffu, W[k], 1);
             E[k] = lane ? t : 0.0;                       // exclusive prefix of this thread within its warp
-            if (NW > 1 && lane == 31) wtot[(par * 5 + k) * 8 + warp] = W[k];
+            if (NW > 1 && lane == 31) wtot[(par * 5 + k) * 16 + warp] = W[k];
           }
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
@@ -360,38 +364,39 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
             }
           }
           __syncthreads();
-          // inclusive scan of the warp totals (lanes 0 .. NW-1 of every warp, redundantly)
-          double inc[5];
+          // warp 0 turns the warp totals into the offsets of the warps (exclusive scan); everybody reads them
+          // from shared memory after a second barrier (cheaper than every warp repeating the shuffle scan)
           if (NW > 1) {
+            if (warp == 0) {
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-              inc[k] = lane < NW ? wtot[(par * 5 + k) * 8 + lane] : 0.0;
+              for (int k = 0; k < 5; ++k) {
+                double t = lane < NW ? wtot[(par * 5 + k) * 16 + lane] : 0.0;
 #pragma unroll
-              for (int o = 1; o < NW; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, inc[k], o);
-                if (lane >= o) inc[k] += t;
+                for (int o = 1; o < NW; o <<= 1) {
+                  const double u = __shfl_up_sync(0xffffffffu, t, o);
+                  if (lane >= o) t += u;
+                }
+                const double ex = __shfl_up_sync(0xffffffffu, t, 1);
+                if (lane < NW) woff[(par * 5 + k) * 16 + lane] = lane ? ex : 0.0;
               }
-              const double t = __shfl_sync(0xffffffffu, inc[k], warp ? warp - 1 : 0);
-              E[k] += warp ? t : 0.0;                    // + the warps left of this one: prefix left of column c0
             }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 5; ++k) E[k] += woff[(par * 5 + k) * 16 + warp];   // prefix left of column c0
           }
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
             const int c = c0 + j;
             const int hi = min(c + win - 1, np_ - 1);
             const int whi = (hi / CPT) >> 5;             // warp that owns column hi
-            double h[5];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {                // shuffles outside the divergent branch below
-              h[k] = 0.0;
-              if (NW > 1) {
-                const double t = __shfl_sync(0xffffffffu, inc[k], whi ? whi - 1 : 0);
-                h[k] = whi ? t : 0.0;
-              }
-            }
             if (c < m) {
+              double h[5];
 #pragma unroll
-              for (int k = 0; k < 5; ++k) h[k] = (pre[(par * 5 + k) * PA + (hi % CPT) * PS + hi / CPT] + h[k]) - E[k];
+              for (int k = 0; k < 5; ++k) {
+                const double up = pre[(par * 5 + k) * PA + (hi % CPT) * PS + hi / CPT] +
+                                  (NW > 1 ? woff[(par * 5 + k) * 16 + whi] : 0.0);
+                h[k] = up - E[k];
+              }
               const double pxy = h[0] * h[1], pxx = h[0] * h[0], pyy = h[1] * h[1];
               const double a1 = 2.0 * pxy + c1s, b1 = pxx + pyy + c1s;
               const double a2 = 2.0 * cov_norm * (NP * h[4] - pxy) + c2s;
@@ -409,7 +414,7 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
 
     // ---- 6. SN
     double sn = qnan;
-    if (p.compute_sn) {
+    if (WITH_SN && p.compute_sn) {
       double *ring = buf;                 // 7 * ncap
       double *a1 = buf + 7 * (size_t)ncap; // np_+6, shifted by 3
       double *a2 = a1 + ncap + 6;
@@ -484,11 +489,11 @@ size_t generic_smem_bytes(int ncap) {
   return (bytes + 15) & ~size_t(15);
 }
 
-template <int BLOCK, int CPT>
+template <int BLOCK, int CPT, bool WITH_SN = true, int MINB = 1>
 int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const chess_pair *pairs,
            int64_t n_pairs, int ncap, const chess_params &p, double *ssim, double *sn,
            int32_t *status, cudaStream_t stream, bool retry_only, const int *retry_flag) {
-  auto kern = compare_generic_kernel<BLOCK, CPT>;
+  auto kern = compare_generic_kernel<BLOCK, CPT, WITH_SN, MINB>;
   const size_t smem = generic_smem_bytes(ncap);
   if ((int)smem > ctx->max_smem_optin) {
     ctx->err = "compare_generic: shared memory demand exceeds the device limit";
@@ -539,15 +544,19 @@ int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const d
   const int ncap = max_n < 32 ? 32 : max_n;
   // four adjacent columns per thread in the SSIM loop: a pair of <= 128 bins is one warp (no cross-warp step)
   if (!p.compute_sn) {
-    // SSIM only (background comparisons, the dense one-vs-many batches of configs[0]): four adjacent columns
-    // per thread amortise the prefix shuffles; a pair of <= 128 bins is one warp (no cross-warp step)
-    if (ncap <= 128) return launch<32, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-    if (ncap <= 256) return launch<64, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-    if (ncap <= 512) return launch<128, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
-    return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+    // SSIM only (background comparisons, the dense one-vs-many batches of configs[0]): adjacent columns per
+    // thread amortise the prefix shuffles; without the SN phase the kernel fits 16 warps per SM
+#define CHESS_GEN_ARGS ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag
+    // measured on the dense one-vs-many batches (profiles/r01_config0_*.txt): one warp per pair up to 128 bins,
+    // two columns per thread and 16 warps per SM above
+    if (ncap <= 128) return launch<32, 4, false, 1>(CHESS_GEN_ARGS);
+    if (ncap <= 256) return launch<128, 2, false, 4>(CHESS_GEN_ARGS);
+    if (ncap <= 512) return launch<256, 2, false, 2>(CHESS_GEN_ARGS);
+    return launch<512, 2, false, 1>(CHESS_GEN_ARGS);
+#undef CHESS_GEN_ARGS
   }
   // with SN the 7-row window phase wants a thread per column (measured: 573 us against 699 us on configs[1])
-  if (ncap <= 128) return launch<128, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
+  if (ncap <= 128) return launch<128, 1, true, 3>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
   if (ncap <= 256) return launch<256, 1>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
   if (ncap <= 512) return launch<256, 2>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
   return launch<256, 4>(ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag);
