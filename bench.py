@@ -22,6 +22,9 @@ Numbers on the JSON line
   cpu_baseline  the CPU oracle (reference algorithm restated, oracle/) with a
              multiprocessing pool on this box's cores, on a bounded sample.
 
+  synthetic_one_vs_many  (N = 1 only) BASELINE configs[0]: one dense reference against truth + 1000 decoys
+             (utils/run_synthetic_test.py), SSIM only, per window of the script; device-resident and e2e.
+
   genome_wide  (N = 1 only) the same measurements for BASELINE configs[2] -- hg38 at 10 kb, ~100k pairs
              of 2 Mb (201 bins), the workload the north-star target is quoted on -- 5 timed steps.
 
@@ -68,6 +71,8 @@ def parse_args():
                     help="skip the extra configs[2] (hg38 @ 10 kb, ~100k pairs) measurement at N=1")
     ap.add_argument("--no-ingest", action="store_true",
                     help="skip the extra sparse-text ingest measurement (8f-1) at N=1")
+    ap.add_argument("--no-synthetic", action="store_true",
+                    help="skip the extra configs[0] (dense one-vs-many synthetic comparison) measurement at N=1")
     ap.add_argument("--no-background", action="store_true",
                     help="skip the extra --background-query measurement (a-14) at N=1")
     ap.add_argument("--kernel", type=int, default=0,
@@ -488,6 +493,11 @@ def measure(args, rank, world, local_rank, dist):
             line["ingest"] = measure_ingest(local_rank, ref)
         except Exception as exc:
             line["ingest"] = {"error": repr(exc)}
+    if world == 1 and args.workload == "chr2_25kb" and not args.no_synthetic:
+        try:
+            line["synthetic_one_vs_many"] = measure_synthetic(local_rank)
+        except Exception as exc:
+            line["synthetic_one_vs_many"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(genome, ref, qry, pairs, args, re_, qe, h_ssim, h_sn)
     re_.drop_device_copies()
@@ -566,6 +576,81 @@ def measure_background(args, local_rank, genome, regions, trees, re_, qe, pairs,
                     "host_region_list_s": host_prep_s},
             "whole_run_estimate_s": len(pairs) * len(bf) / (n_cmp / dev_s),
             "finite_z": int(np.isfinite(z).sum()), "device_call_matches_engine": same}
+
+
+def measure_synthetic(local_rank, n=100, pool=1000):
+    """BASELINE configs[0] (utils/run_synthetic_test.py:97-121): one dense reference against its truth and
+    `pool` decoys, SSIM only, data_range 2.0, per window of the script.  `device`: the pool is resident, one
+    chess_compare_batch launch per window, CUDA events.  `e2e`: chess_b200.synthetic_test.OneVsMany from
+    host matrices (one upload of the pool, then every window of the script with results back on the host)."""
+    import torch
+    from chess_b200 import synth, _native
+    from chess_b200 import synthetic_test as S
+    from chess_b200.engine import get_context, PAIR_DTYPE, _ptr, _stream_ptr, check
+    from oracle import chess_oracle as O
+    rng = np.random.default_rng(0)
+    base = synth.dense_decay(n)
+    feat = synth.dense_features(n, rng)
+    ref = synth.dense_oe(synth.dense_noisy(base + feat, rng))
+    queries = [synth.dense_oe(synth.dense_noisy(base + (feat if k == 0 else synth.dense_features(n, rng)), rng))
+               for k in range(pool + 1)]
+    P = len(queries)
+    dev = torch.device("cuda", local_rank)
+    ctx = get_context(local_rank)
+    with torch.cuda.device(dev):
+        d_ref = torch.from_numpy(ref.ravel().copy()).to(dev)
+        d_pool = torch.from_numpy(np.concatenate([q.ravel() for q in queries])).to(dev)
+        tab = np.zeros(P, dtype=PAIR_DTYPE)
+        for k in range(P):
+            tab[k] = (0, k * n * n, n, n, n, n, 0, 0)
+        d_tab = torch.from_numpy(tab.view(np.uint8)).to(dev)
+        ssim = torch.empty(P, dtype=torch.float64, device=dev)
+        sn = torch.empty(P, dtype=torch.float64, device=dev)
+        status = torch.empty(P, dtype=torch.int32, device=dev)
+        stream = _stream_ptr(dev)
+        peak, _ = measured_peak()
+        alg = P * (2.0 * n * n * 8 + 24)
+        rows, launches = [], 0
+        for rel in S.distinct_windows(n):
+            win = S.window_size(n, rel)
+            prm = _native.make_params(absolute_window_size=win, min_bins=0, keep_unmappable_bins=True,
+                                      mappability_cutoff=0.0, compute_sn=False, data_range=2.0)
+            best = None
+            for rep in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                check(_native.lib.chess_compare_batch(ctx.handle, _ptr(d_ref), _ptr(d_pool), _ptr(d_tab), P, n,
+                                                      C.byref(prm), _ptr(ssim), _ptr(sn), _ptr(status), stream),
+                      ctx.handle, "chess_compare_batch")
+                e1.record()
+                torch.cuda.synchronize()
+                launches += 1
+                dt = e0.elapsed_time(e1) * 1e-3
+                best = dt if rep and (best is None or dt < best) else best
+            rows.append({"window": win, "pairs_per_s": P / best, "roofline_frac": alg / best / (peak * 1e9)})
+        rel = 0.1
+        rels = S.distinct_windows(n)
+        t0 = time.perf_counter()
+        batch = S.OneVsMany(ref, queries[0], queries[1:], device=local_rank)
+        for r_ in rels:
+            out = batch.run(r_)
+            if r_ == rel:
+                truth, control, pval, z = out
+        e2e_s = time.perf_counter() - t0
+        k = 8
+        t0 = time.perf_counter()
+        want = np.array([O.synthetic_compare_matrices(ref, q, rel) for q in queries[1:1 + k]])
+        cpu_s = (time.perf_counter() - t0) / k
+        dev_rel = float(np.max(np.abs(control[:k] - want) / np.abs(want)))
+    return {"what": "configs[0]: one dense O/E reference vs truth + %d decoys, %d bins, SSIM only, data_range 2.0 "
+                    "(utils/run_synthetic_test.py:97-121), generic kernel" % (pool, n),
+            "pairs_per_launch": P, "device": rows, "gpu_launches": launches,
+            "e2e": {"windows": len(rels), "pairs_per_s": P * len(rels) / e2e_s, "seconds": e2e_s,
+                    "h2d_bytes": int((P + 1) * n * n * 8), "d2h_bytes": int(P * 8 * len(rels)),
+                    "call": "chess_b200.synthetic_test.OneVsMany (host matrices uploaded once; per window of the "
+                            "script: truth, controls, p, z back on the host)",
+                    "p_window_9": pval, "z_window_9": z},
+            "cpu_oracle_1_core_pairs_per_s": 1.0 / cpu_s, "max_rel_dev_gpu_vs_cpu": dev_rel}
 
 
 def measure_ingest(local_rank, sample):

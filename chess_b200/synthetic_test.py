@@ -14,9 +14,14 @@ without `data_range`; for float images that function assumes the range of the
 dtype, -1 .. 1, i.e. 2.0.  That is the default here; `data_range=None` takes
 max - min of the pair as `chess sim` does (chess/sim.py:368-374).
 """
-import numpy as np
+import ctypes as C
 
-from .engine import compare_dense_pairs
+import numpy as np
+import torch
+
+from . import _native
+from ._native import lib, check
+from .engine import compare_dense_pairs, get_context, visible_devices, PAIR_DTYPE, _ptr, _stream_ptr
 
 REL_WINDOWS = (0.01, 0.05, 0.1, 0.2, 0.4, 0.5, 0.6, 0.8, 1)   # run_synthetic_test.py:97
 
@@ -69,3 +74,53 @@ def truth_and_controls(reference, query, pool, rel_window, data_range=2.0, devic
     allv = np.concatenate([control, [truth]])
     z = float((truth - allv.mean()) / allv.std())
     return truth, control, p, z
+
+
+class OneVsMany(object):
+    """One reference against its truth and a pool of decoys, resident on the device.
+
+    `run_test` (run_synthetic_test.py:97-121) compares the same reference with the same pool once per relative
+    window; here the matrices are uploaded ONCE and every window is one launch on the resident batch
+    (equal sizes only; `truth_and_controls` handles the general case).
+    """
+
+    def __init__(self, reference, query, pool, device=None):
+        self.device = visible_devices()[0] if device is None else int(device)
+        self.n = int(reference.shape[0])
+        mats = [query] + list(pool)
+        if any(m.shape != (self.n, self.n) for m in [reference] + mats):
+            raise ValueError("OneVsMany expects square matrices of one size")
+        self.n_pool = len(pool)
+        dev = torch.device("cuda", self.device)
+        self.ctx = get_context(self.device)
+        n2 = self.n * self.n
+        with torch.cuda.device(dev):
+            self.d_ref = torch.from_numpy(np.ascontiguousarray(reference, dtype=np.float64).ravel()).to(dev)
+            self.d_pool = torch.empty(len(mats) * n2, dtype=torch.float64, device=dev)
+            for k, m in enumerate(mats):
+                self.d_pool[k * n2:(k + 1) * n2] = torch.from_numpy(
+                    np.ascontiguousarray(m, dtype=np.float64).ravel()).to(dev, non_blocking=True)
+            tab = np.zeros(len(mats), dtype=PAIR_DTYPE)
+            for k in range(len(mats)):
+                tab[k] = (0, k * n2, self.n, self.n, self.n, self.n, 0, 0)
+            self.d_tab = torch.from_numpy(tab.view(np.uint8)).to(dev)
+            self.d_res = torch.empty(len(mats) * 5, dtype=torch.float32, device=dev)   # ssim f64, sn f64, status i32
+        self.P = len(mats)
+
+    def run(self, rel_window, data_range=2.0):
+        """(truth_ssim, control_ssim, p, z) for one relative window (run_synthetic_test.py:105-115)."""
+        dev = torch.device("cuda", self.device)
+        P = self.P
+        p = _native.make_params(**_params(self.n, rel_window, data_range))
+        base = self.d_res.data_ptr()
+        with torch.cuda.device(dev):
+            check(lib.chess_compare_batch(self.ctx.handle, _ptr(self.d_ref), _ptr(self.d_pool), _ptr(self.d_tab), P,
+                                          self.n, C.byref(p), C.c_void_p(base), C.c_void_p(base + 8 * P),
+                                          C.c_void_p(base + 16 * P), _stream_ptr(dev)),
+                  self.ctx.handle, "chess_compare_batch")
+            ssim = self.d_res[:2 * P].view(torch.float64).cpu().numpy()
+        truth, control = float(ssim[0]), ssim[1:]
+        pval = float(np.sum(control >= truth)) / max(self.n_pool, 1)
+        allv = np.concatenate([control, [truth]])
+        z = float((truth - allv.mean()) / allv.std())
+        return truth, control, pval, z

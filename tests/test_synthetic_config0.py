@@ -79,6 +79,12 @@ def test_one_vs_many_against_oracle(n, n_pool, rels):
             for a, b in zip(co, oco):
                 assert close(a, b, RTOL), (n, t, rel, a, b)
             assert p == op and close(z, oz, 1e-5), (n, t, rel, p, op, z, oz)
+    # the resident form: one upload, one launch per window, identical numbers
+    batch = S.OneVsMany(ref[2], truth[2], [q[2] for q in pool])
+    for rel in rels[:2]:
+        tr, co, p, z = batch.run(rel)
+        tr2, co2, p2, z2 = S.truth_and_controls(ref[2], truth[2], [q[2] for q in pool], rel)
+        assert tr == tr2 and np.array_equal(co, co2) and p == p2 and z == z2
     # the chess sim rule for the data range, and a single pair of unequal sizes
     tr, co, _, _ = S.truth_and_controls(ref[1], truth[1], [q[1] for q in pool[:2]], 0.2, data_range=None)
     lo = min(ref[1].min(), truth[1].min())
