@@ -61,7 +61,7 @@ PAIR_DTYPE = np.dtype([("ref_off", "<i8"), ("qry_off", "<i8"), ("ref_pitch", "<i
 assert PAIR_DTYPE.itemsize == C.sizeof(chess_pair) == 40
 
 PAIR_OK, PAIR_NOT_FOUND, PAIR_TOO_SMALL, PAIR_UNMAPPABLE, PAIR_WINDOW_EXCEEDS = range(5)
-FLAG_SYMMETRIC, FLAG_EQUAL_SIZES = 1, 2
+FLAG_SYMMETRIC, FLAG_EQUAL_SIZES, FLAG_MOSTLY_EQUAL_SIZES = 1, 2, 4
 
 _vp, _i32, _i64, _dbl, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_size_t
 _PP = C.POINTER(chess_params)

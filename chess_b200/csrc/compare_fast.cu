@@ -545,7 +545,8 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   const bool windowed = p.abs_window > 0 && H >= 1 && H <= 5 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
   // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
-  if (!(r1 || windowed) || !plain_default || max_n > 1024 || !(p.flags & CHESS_FLAG_EQUAL_SIZES) || !ref->nd_lo ||
+  if (!(r1 || windowed) || !plain_default || max_n > 1024 ||
+      !(p.flags & (CHESS_FLAG_EQUAL_SIZES | CHESS_FLAG_MOSTLY_EQUAL_SIZES)) || !ref->nd_lo ||
       !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
     return CHESS_OK;
   // column-strip width: the narrowest strip that holds the matrix in one block; wider matrices are

@@ -136,8 +136,28 @@ compare_generic_kernel(const double *__restrict__ ref_base, const double *__rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double qnan = CUDART_NAN;
 
-  for (long long pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
-    if (retry_only && status_out[pi] != CHESS_PAIR_RETRY) continue;  // uniform per CTA
+  // Pairs of this CTA.  Normal pass: blockIdx.x, + gridDim.x, ...  Retry pass: the CTAs scan the status
+  // array 32 pairs at a time (one coalesced load and a ballot per group, identical in every warp of the
+  // CTA) and walk only into the groups that hold a RETRY mark -- a 65 536-pair chunk with a handful of
+  // marks costs microseconds, not the millisecond that one status load per pair and CTA did.
+  long long group = blockIdx.x, cur_base = 0;
+  unsigned pending = 0;
+  long long pi = (long long)blockIdx.x - (long long)gridDim.x;
+  while (true) {
+    if (retry_only) {
+      while (pending == 0 && group * 32 < n_pairs) {
+        cur_base = group * 32;
+        const long long q = cur_base + lane;
+        pending = __ballot_sync(0xffffffffu, q < n_pairs && status_out[q] == CHESS_PAIR_RETRY);
+        group += gridDim.x;
+      }
+      if (pending == 0) break;
+      pi = cur_base + (__ffs(pending) - 1);
+      pending &= pending - 1;
+    } else {
+      pi += gridDim.x;
+      if (pi >= n_pairs) break;
+    }
     const chess_pair d = pairs[pi];
     int status = CHESS_PAIR_OK;
     if (d.ref_n <= 0 || d.qry_n <= 0) status = CHESS_PAIR_NOT_FOUND;
@@ -507,7 +527,11 @@ int launch(chess_ctx *ctx, const double *ref_base, const double *qry_base, const
   if (grid > n_pairs) grid = n_pairs;
   // the retry pass after a tuned kernel normally has nothing to do (it returns on the flag) and at
   // most a handful of pairs otherwise: a few CTAs keep its launch cost down
-  if (retry_flag != nullptr && grid > 16) grid = 16;
+  if (retry_flag != nullptr) {
+    long long want = (n_pairs + 255) / 256;   // 8 status groups per CTA
+    if (want < 16) want = 16;
+    if (grid > want) grid = want;
+  }
   if (retry_flag != nullptr) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

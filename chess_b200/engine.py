@@ -287,8 +287,11 @@ class CompareEngine(object):
         max_n = int(max(ref_n.max(), qry_n.max(), 1))
         # the band is symmetric by construction; equal sizes let the kernels skip the resize path
         flags = _native.FLAG_SYMMETRIC
-        if bool(np.all((ref_n == qry_n) | (ref_n <= 0) | (qry_n <= 0))):
+        equal = (ref_n == qry_n) | (ref_n <= 0) | (qry_n <= 0)
+        if bool(np.all(equal)):
             flags |= _native.FLAG_EQUAL_SIZES
+        elif equal.mean() >= 0.9:
+            flags |= _native.FLAG_MOSTLY_EQUAL_SIZES
         p = _native.make_params(default_value=default_value, flags=flags, **params)
         ndev = min(len(self.devices), total)
         bounds = shard_bounds(total, ndev)
@@ -363,6 +366,15 @@ class CompareEngine(object):
         sizes = np.unique(np.concatenate([ref_n[ref_n > 0], bg_n[bg_n > 0]]))
         if len(sizes) <= 1:
             flags |= _native.FLAG_EQUAL_SIZES
+        elif len(bg_n):
+            # fraction of the pair x region grid with equal sizes (regions of one length in bp differ by a bin
+            # where a chromosome ends): the work-item kernels take those, the retry pass the rest
+            rs, rc = np.unique(ref_n, return_counts=True)
+            bs, bc = np.unique(bg_n, return_counts=True)
+            same = sum(int(c) * int(bc[np.searchsorted(bs, v)]) for v, c in zip(rs, rc)
+                       if v > 0 and v in bs)
+            if same >= 0.9 * len(ref_n) * len(bg_n):
+                flags |= _native.FLAG_MOSTLY_EQUAL_SIZES
         params.pop("compute_sn", None)
         p = _native.make_params(default_value=default_value, flags=flags, compute_sn=False, **params)
         ndev = min(len(self.devices), total)

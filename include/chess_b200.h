@@ -103,6 +103,10 @@ typedef struct chess_params {
  * chess/sim.py:323-329).                                                      */
 #define CHESS_FLAG_SYMMETRIC 1
 #define CHESS_FLAG_EQUAL_SIZES 2
+/* MOSTLY_EQUAL_SIZES: nearly all pairs have ref_n == qry_n (e.g. background regions of one length in bp
+ * whose last bin is shorter at a chromosome end): the work-item kernels are worth launching, the few unequal
+ * pairs take the resize path in the retry pass.  A hint like the others: results do not depend on it.       */
+#define CHESS_FLAG_MOSTLY_EQUAL_SIZES 4
 
 /* ---- context ------------------------------------------------------------ */
 int chess_abi_version(void);

@@ -446,6 +446,31 @@ def test_tuned_kernels_agree_with_generic_kernel(cb, chr2_like):
                 np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
 
 
+def test_mostly_equal_sizes_take_the_tuned_kernels(cb, chr2_like):
+    """A batch in which a few pairs have regions of different sizes (resize path, sim.py:323-329) still runs on
+    the work-item kernels (CHESS_FLAG_MOSTLY_EQUAL_SIZES); the unequal pairs go through the retry pass.
+    Same numbers as the generic kernel on the whole batch, and the retry pass finds marks anywhere in a batch."""
+    genome, regions, trees, re_, qe, pairs, _, _ = chr2_like
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    mixed = list(pairs)
+    for k in (0, 33, 34, len(mixed) // 2, len(mixed) - 1):       # query region 10 bins longer / shorter
+        pid, r, q = mixed[k]
+        grow = 250000 if q.end + 250000 < 2400 * 25000 else -250000
+        mixed[k] = (pid, r, cb.GenomicRegion(chromosome=q.chromosome, start=q.start, end=q.end + grow, strand=q.strand))
+    for kw in (dict(), dict(absolute_window_size=7), dict(compute_sn=False)):
+        gen = eng.compare(mixed, kernel=1, **kw)
+        fast = eng.compare(mixed, **kw)
+        assert np.array_equal(fast[3], gen[3])
+        np.testing.assert_allclose(fast[1], gen[1], rtol=1e-9, atol=0, equal_nan=True)
+        np.testing.assert_allclose(fast[2], gen[2], rtol=1e-9, atol=0, equal_nan=True)
+        same = eng.compare(pairs, **kw)
+        keep = np.ones(len(pairs), dtype=bool)
+        keep[[0, 33, 34, len(mixed) // 2, len(mixed) - 1]] = False
+        # the equal pairs: the same numbers as in the all-equal batch (a wider band and strip layout, so not bit for bit)
+        np.testing.assert_allclose(fast[1][keep], same[1][keep], rtol=1e-11, atol=0, equal_nan=True)
+    assert np.isfinite(fast[1][33]) and fast[1][33] != same[1][33]
+
+
 def test_band_kernels_coincidentally_masked_bins(cb):
     """A bin whose entries are not all default but sum to exactly n is masked by the reference
     (np.sum(m, 0) == n, chess/sim.py:82-85).  The work-item kernel predicts masks from
