@@ -567,7 +567,10 @@ int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const d
   }
   const int ncap = max_n < 32 ? 32 : max_n;
   // four adjacent columns per thread in the SSIM loop: a pair of <= 128 bins is one warp (no cross-warp step)
-  if (!p.compute_sn) {
+  // a retry pass holds a handful of pairs: what counts is the latency of one pair, so small matrices get a
+  // thread per column (four warps) instead of one warp per pair
+  const bool few_pairs = retry_only && ncap <= 128;
+  if (!p.compute_sn && !few_pairs) {
     // SSIM only (background comparisons, the dense one-vs-many batches of configs[0]): adjacent columns per
     // thread amortise the prefix shuffles; without the SN phase the kernel fits 16 warps per SM
 #define CHESS_GEN_ARGS ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag
