@@ -478,7 +478,9 @@ def measure(args, rank, world, local_rank, dist):
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pairs/s",
                 "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_pairs * 28),
-                "call": "chess_sim_band_batch_host (host pair table in; ssim, SN, status, z_ssim out)"},
+                "call": "chess_sim_band_batch_host (host pair table in; ssim, SN, status, z_ssim out to host arrays; up to 8192 "
+                        "pairs the kernels read the table from / write the results to the pinned staging buffer over "
+                        "PCIe, larger batches use one DMA each way)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
