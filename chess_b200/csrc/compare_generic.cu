@@ -576,6 +576,9 @@ int chess_launch_compare_generic(chess_ctx *ctx, const double *ref_base, const d
 #define CHESS_GEN_ARGS ctx, ref_base, qry_base, pairs, n_pairs, ncap, p, ssim, sn, status, stream, retry_only, retry_flag
     // measured on the dense one-vs-many batches (profiles/r01_config0_*.txt): one warp per pair up to 128 bins,
     // two columns per thread and 16 warps per SM above
+    // (more than a wave of them: the 168-register build, 12 warps per SM; a single wave is bound by the
+    // latency of one warp, where the unconstrained build is faster: 0.198 against 0.231 ms at 1 001 pairs)
+    if (ncap <= 128 && n_pairs > 9LL * ctx->sm_count) return launch<32, 4, false, 12>(CHESS_GEN_ARGS);
     if (ncap <= 128) return launch<32, 4, false, 1>(CHESS_GEN_ARGS);
     if (ncap <= 256) return launch<128, 2, false, 4>(CHESS_GEN_ARGS);
     if (ncap <= 512) return launch<256, 2, false, 2>(CHESS_GEN_ARGS);

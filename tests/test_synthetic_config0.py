@@ -104,3 +104,21 @@ def test_fixed_data_range_is_rejected_when_negative():
     with pytest.raises(Exception):
         S.compare_matrices(a, a, 0.5, data_range=-1.0)
     assert S.compare_matrices(a, a, 0.5) == 1.0
+
+
+@pytest.mark.gpu
+def test_large_batch_uses_the_same_arithmetic():
+    """More than a wave of pairs switches the one-warp kernel to its 12-warps-per-SM build: same code, so the
+    numbers of a pair do not depend on the batch it is in; a few are checked against the oracle."""
+    from chess_b200 import synthetic_test as S
+    n = 40
+    rng = np.random.default_rng(5)
+    base = synth.dense_decay(n)
+    ref = synth.dense_oe(synth.dense_noisy(base + synth.dense_features(n, rng), rng))
+    pool = [synth.dense_oe(synth.dense_noisy(base + synth.dense_features(n, rng), rng)) for _ in range(1500)]
+    for rel in (0.2, 0.5):
+        _, big, _, _ = S.truth_and_controls(ref, pool[0], pool, rel)
+        _, small, _, _ = S.truth_and_controls(ref, pool[0], pool[:20], rel)
+        assert np.array_equal(big[:20], small)
+        for k in (0, 7, 1499):
+            assert close(big[k], O.synthetic_compare_matrices(ref, pool[k], rel), RTOL)
