@@ -28,6 +28,22 @@ def _load():
             raise ImportError(
                 "chess_b200: native library {} is missing and could not be built ({}). "
                 "Run `python -m chess_b200.build`; there is no CPU fallback.".format(LIB_PATH, exc))
+        # an older library is there.  Using it is only right when it was built from these very sources
+        # (a box without nvcc running the shipped .so); otherwise results would come from code that is not
+        # the checked-in source, so refuse unless the caller explicitly accepts the stale library.
+        stale = True
+        try:
+            with open(LIB_PATH + ".stamp") as fh:
+                stale = fh.read().strip() != _build._stamp()
+        except Exception:
+            pass
+        if stale:
+            if os.environ.get("CHESS_B200_ALLOW_STALE_LIB") != "1":
+                raise ImportError(
+                    "chess_b200: the sources changed since {} was built and the rebuild failed ({}). Fix the "
+                    "build, or set CHESS_B200_ALLOW_STALE_LIB=1 to load the stale library.".format(LIB_PATH, exc))
+            import warnings
+            warnings.warn("chess_b200: loading a STALE {} (rebuild failed: {})".format(LIB_PATH, exc))
     return C.CDLL(LIB_PATH)
 
 

@@ -24,6 +24,7 @@ from ._native import PAIR_DTYPE, lib, check
 from .distributed import shard_bounds
 
 _contexts = {}
+MAX_BINS = 1024   # largest region, in bins, the comparison kernels take (csrc/compare_generic.cu)
 
 
 def get_context(device=0):
@@ -69,6 +70,24 @@ class DeviceContacts(object):
         swap = src > sink
         if swap.any():
             src, sink = np.where(swap, sink, src), np.where(swap, src, sink)
+        if len(src) and int(src.min()) < 0:
+            raise ValueError("negative contact index")
+        if len(src) > 1:
+            # a (source, sink) listed more than once: the reference's dict of dicts keeps the LAST occurrence
+            # in input order (chess/helpers.py:353-356); keep exactly that one, so that the band scatter has
+            # one writer per cell (deterministic, and both mirror cells agree)
+            key = src * (int(sink.max()) + 1) + sink
+            if bool(np.all(key[1:] > key[:-1])):      # sorted input (the usual dump order): nothing repeats
+                dup = np.zeros(0, dtype=bool)
+            else:
+                order = np.argsort(key, kind="stable")
+                ks = key[order]
+                dup = ks[1:] == ks[:-1]
+            if dup.any():
+                last = np.ones(len(ks), dtype=bool)
+                last[:-1] = ~dup
+                keep = np.sort(order[last])
+                src, sink, self.value = src[keep], sink[keep], self.value[keep]
         self.src, self.sink = src, sink
         hi = int(sink.max()) + 1 if len(sink) else 0
         self.n_bins = int(n_bins) if n_bins is not None else hi
@@ -79,6 +98,28 @@ class DeviceContacts(object):
         self._index = {}   # device -> (nd_lo, nd_hi, pmax, pmin) tensors for the current band
         self._coo = {}     # device -> (src32, sink32, value) tensors
         self._csr = None
+
+    def ensure_bins(self, n_bins):
+        """Make the store cover at least ``n_bins`` bins.  Bins after the last one with a contact
+        (chrY, chrM, telomeric or unplaced bins are routinely empty) hold the fill value like every
+        absent cell (chess/helpers.py:297); a store sized by its largest contact index alone would
+        leave regions that reach into them outside every per-sample buffer."""
+        n_bins = int(n_bins)
+        if n_bins > self.n_bins:
+            self.n_bins = n_bins
+            self._bands.clear()
+            self._index.clear()
+            self._csr = None
+
+    def check_span(self, first, n, what="region"):
+        """Raise unless every span [first, first + n) with n > 0 lies inside the store."""
+        first = np.asarray(first, dtype=np.int64)
+        n = np.asarray(n, dtype=np.int64)
+        live = n > 0
+        if live.any() and (int(first[live].min()) < 0 or int((first[live] + n[live]).max()) > self.n_bins):
+            raise ValueError("{} bins [{}, {}) lie outside the contact store of {} bins: the regions file "
+                             "does not match the contact matrix".format(
+                                 what, int(first[live].min()), int((first[live] + n[live]).max()), self.n_bins))
 
     # -- dict-like view (compatibility with code indexing the reference's dict)
     def _rows(self):
@@ -182,6 +223,7 @@ class DeviceContacts(object):
     def submatrix(self, start_ix, n, default_weight=None, device=None):
         """Dense n x n numpy tile starting at bin ``start_ix`` (device gather + D2H)."""
         device = visible_devices()[0] if device is None else int(device)
+        self.check_span([start_ix], [n])
         W, band = self.band_on(device, n, default_weight)
         ctx = get_context(device)
         dev = torch.device("cuda", device)
@@ -193,12 +235,30 @@ class DeviceContacts(object):
         return out.cpu().numpy()
 
 
-def as_device_contacts(edges):
-    """Accept a DeviceContacts or a ``{src: {sink: w}}`` mapping (uploaded as is)."""
+def index_bins(region_index):
+    """Number of bins a region index addresses (largest ``ix`` + 1); None when it cannot tell."""
+    try:
+        if isinstance(region_index, dict):
+            tops = [int(ix.ixs.max()) for ix in region_index.values() if len(ix)]
+        else:
+            tops = [int(r.ix) for r in region_index if r.ix is not None]
+        return max(tops) + 1 if tops else None
+    except (AttributeError, TypeError, ValueError):
+        return None
+
+
+def as_device_contacts(edges, n_bins=None):
+    """Accept a DeviceContacts or a ``{src: {sink: w}}`` mapping (uploaded as is).
+    ``n_bins``: the number of bins of the regions the store goes with (bins after the
+    last contact exist and hold the default value)."""
     if isinstance(edges, DeviceContacts):
+        if n_bins is not None:
+            edges.ensure_bins(n_bins)
         return edges
     cached = getattr(edges, "_chess_b200_contacts", None)
     if cached is not None:
+        if n_bins is not None:
+            cached.ensure_bins(n_bins)
         return cached
     src, sink, val = [], [], []
     for a, row in edges.items():
@@ -208,6 +268,8 @@ def as_device_contacts(edges):
             val.append(w)
     contacts = DeviceContacts(np.asarray(src, dtype=np.int64), np.asarray(sink, dtype=np.int64),
                               np.asarray(val, dtype=np.float64))
+    if n_bins is not None:
+        contacts.ensure_bins(n_bins)
     try:
         edges._chess_b200_contacts = contacts
     except AttributeError:
@@ -263,8 +325,8 @@ class CompareEngine(object):
     """
 
     def __init__(self, reference_edges, reference_regions, query_edges, query_regions, devices=None):
-        self.ref = as_device_contacts(reference_edges)
-        self.qry = as_device_contacts(query_edges)
+        self.ref = as_device_contacts(reference_edges, index_bins(reference_regions))
+        self.qry = as_device_contacts(query_edges, index_bins(query_regions))
         self.ref_index = reference_regions
         self.qry_index = query_regions
         self.devices = list(devices) if devices is not None else visible_devices()[:1]
@@ -284,6 +346,8 @@ class CompareEngine(object):
         status = np.zeros(total, dtype=np.int32)
         if total == 0:
             return ssim, sn, status
+        self.ref.check_span(ref_first, ref_n, "reference region")
+        self.qry.check_span(qry_first, qry_n, "query region")
         max_n = int(max(ref_n.max(), qry_n.max(), 1))
         # the band is symmetric by construction; equal sizes let the kernels skip the resize path
         flags = _native.FLAG_SYMMETRIC
@@ -361,6 +425,10 @@ class CompareEngine(object):
         p_bg = np.full(total, np.nan)
         if total == 0:
             return z_bg, p_bg
+        self.ref.check_span(ref_first, ref_n, "reference region")
+        self.qry.check_span(bg_first, bg_n, "background region")
+        if own is not None:
+            self.qry.check_span(own[0], own[1], "query region")
         max_n = int(max(ref_n.max(), bg_n.max() if len(bg_n) else 1, 1))
         flags = _native.FLAG_SYMMETRIC
         sizes = np.unique(np.concatenate([ref_n[ref_n > 0], bg_n[bg_n > 0]]))
@@ -434,6 +502,12 @@ class CompareEngine(object):
             raise TypeError("union1d() missing 2 required positional arguments: 'ar1' and 'ar2'")
         rf, rn = region_spans(self.ref_index, [p[1] for p in pairs])
         qf, qn = region_spans(self.qry_index, [p[2] for p in pairs])
+        big = np.nonzero((rn > MAX_BINS) | (qn > MAX_BINS))[0]
+        if len(big):
+            k = int(big[0])
+            raise ValueError("region pair {} ({} / {}) spans {} bins; the comparison kernels handle at most {} bins "
+                             "per region ({} such pair(s) in this run): use smaller regions or a larger bin size"
+                             .format(ids[k], pairs[k][1], pairs[k][2], int(max(rn[k], qn[k])), MAX_BINS, len(big)))
         flip = np.array([1 if p[1].strand != p[2].strand else 0 for p in pairs], dtype=np.int32)
         ssim, sn, status = self.compare_spans(rf, rn, qf, qn, flip, default_value=default_value,
                                               compute_sn=compute_sn, **params)

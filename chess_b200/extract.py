@@ -22,7 +22,8 @@ def log_ratio_stage(reference_edges, reference_regions, query_edges, query_regio
     import torch
     from . import _native
     from ._native import lib, check
-    from .engine import as_device_contacts, build_pair_table, get_context, region_spans, visible_devices
+    from .engine import (as_device_contacts, build_pair_table, get_context, index_bins, region_spans,
+                         visible_devices)
 
     pairs = list(pairs)
     if not pairs:
@@ -30,9 +31,12 @@ def log_ratio_stage(reference_edges, reference_regions, query_edges, query_regio
     device = visible_devices()[0] if device is None else int(device)
     ctx = get_context(device)
     dev = torch.device("cuda", device)
-    ref, qry = as_device_contacts(reference_edges), as_device_contacts(query_edges)
+    ref = as_device_contacts(reference_edges, index_bins(reference_regions))
+    qry = as_device_contacts(query_edges, index_bins(query_regions))
     rf, rn = region_spans(reference_regions, [p[1] for p in pairs])
     qf, qn = region_spans(query_regions, [p[2] for p in pairs])
+    ref.check_span(rf, rn, "reference region")
+    qry.check_span(qf, qn, "query region")
     max_n = int(max(rn.max(), qn.max(), 1))
     ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     out = []

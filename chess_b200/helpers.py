@@ -257,9 +257,9 @@ def sub_matrix_from_edges_dict(edges, regions, region, default_weight=0.0):
     produced by a gather kernel from the device-resident band whose absent
     cells hold ``default_weight``.
     """
-    from .engine import as_device_contacts
+    from .engine import as_device_contacts, index_bins
     sr, start_ix, end_ix = sub_regions(regions, region)
-    contacts = as_device_contacts(edges)
+    contacts = as_device_contacts(edges, index_bins(regions))
     return contacts.submatrix(start_ix, end_ix - start_ix + 1, default_weight), sr
 
 
@@ -326,32 +326,43 @@ def load_sparse_matrix(file_name, ix_converter=None, sep="\t"):
     return list(edges_from_sparse_matrix(file_name, ix_converter, sep))
 
 
-def edges_dict_from_sparse(edges):
+def edges_dict_from_sparse(edges, n_bins=None):
     """Edges store from (source, sink, weight) triples; chess/helpers.py:342-356.
 
     Returns a :class:`DeviceContacts` (device-resident), which answers
-    ``store[source][sink]`` like the reference's dict of dicts.
+    ``store[source][sink]`` like the reference's dict of dicts.  ``n_bins`` (not in
+    the reference signature) = number of regions the matrix goes with: bins after
+    the last contact exist and read as the default value.
     """
     from .engine import DeviceContacts
     if isinstance(edges, tuple) and len(edges) == 3 and isinstance(edges[0], np.ndarray):
-        return DeviceContacts(*edges)
+        return DeviceContacts(*edges, n_bins=n_bins)
     triples = list(edges)
     if triples:
         a, b, w = zip(*triples)
     else:
         a, b, w = (), (), ()
     return DeviceContacts(np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64),
-                          np.asarray(w, dtype=np.float64))
+                          np.asarray(w, dtype=np.float64), n_bins=n_bins)
+
+
+def _fanc_bins(hic):
+    try:
+        return len(hic.regions)
+    except TypeError:
+        return sum(1 for _ in hic.regions)
 
 
 def edges_dict_from_fanc(hic):
     """chess/helpers.py:359-373 (needs the third-party fanc object)."""
-    return edges_dict_from_sparse((e.source, e.sink, e.weight) for e in hic.edges(lazy=True))
+    return edges_dict_from_sparse(((e.source, e.sink, e.weight) for e in hic.edges(lazy=True)),
+                                  n_bins=_fanc_bins(hic))
 
 
 def oe_edges_dict_from_fanc(hic):
     """chess/helpers.py:376-391 (O/E computed inside fanc)."""
-    return edges_dict_from_sparse((e.source, e.sink, e.weight) for e in hic.edges(oe=True, lazy=True))
+    return edges_dict_from_sparse(((e.source, e.sink, e.weight) for e in hic.edges(oe=True, lazy=True)),
+                                  n_bins=_fanc_bins(hic))
 
 
 def load_matrix(file_name, size=None, sep=None, ix_converter=None, is_oe=False):
@@ -481,7 +492,7 @@ def load_oe_contacts(matrix_file, regions_file=None):
             assert regions_file is not None
             regions, ix_converter, _ = load_regions(regions_file)
             region_trees = region_interval_trees(regions)
-            edges = edges_dict_from_sparse(_parse_sparse(matrix_file, ix_converter))
+            edges = edges_dict_from_sparse(_parse_sparse(matrix_file, ix_converter), n_bins=len(regions))
         except AssertionError:
             raise ValueError
     return edges, region_trees, regions

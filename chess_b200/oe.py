@@ -75,6 +75,14 @@ def _device_expected(regions, triples, device=None, want_oe=False, apply_log2=Fa
     device = visible_devices()[0] if device is None else int(device)
     layout = _Layout(regions)
     a, b, w = triples
+    # the kernels index marginals, chromosome table and expected values with these: a matrix that does not
+    # go with the regions file must fail here, as it does in the reference (marginals[source], oe.py:107)
+    if layout.n_bins >= 2 ** 31:
+        raise ValueError("more than 2^31 - 1 regions are not supported")
+    if len(a) and (int(min(a.min(), b.min())) < 0 or int(max(a.max(), b.max())) >= layout.n_bins):
+        raise IndexError("matrix index {} is out of bounds for {} regions: the sparse matrix does not match "
+                         "the regions file".format(int(max(a.max(), b.max())) if int(min(a.min(), b.min())) >= 0
+                                                   else int(min(a.min(), b.min())), layout.n_bins))
     ctx = get_context(device)
     dev = torch.device("cuda", device)
     n = layout.n_bins
@@ -174,6 +182,9 @@ def _oe_generator(sparse_matrix, ix_to_chromosome, intra_expected, inter_expecte
         except ZeroDivisionError:
             oe = 1
         if log:
+            # NB deliberate bug-compatibility: chess/oe.py:163-166 has no `else`, so log=True yields every edge
+            # twice (log2 value, then the plain value).  No caller sets it (oe.py:181); the device path
+            # (`observed_expected_arrays(apply_log2=True)`) yields each edge once, log2 only.
             yield source, sink, np.log2(oe)
         yield source, sink, oe
 

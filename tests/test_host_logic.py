@@ -125,3 +125,81 @@ def test_synthetic_generator_is_seeded():
     assert (a[0] <= a[1]).all() and a[1].max() < g.n_bins and (a[2] > 0).all()
     pairs = synth.sliding_pairs(g, 400000, 100000)
     assert len(pairs) == (3000000 - 400000) // 100000 + 1 + (2000000 - 400000) // 100000 + 1
+
+
+def test_contact_store_covers_every_region_bin(toy, tmp_path):
+    """Bins after the last bin with a contact (chrY, chrM, telomeres) exist: the store built on the
+    --oe-input path must span the whole regions file, not just max(sink) + 1; a region outside it is an
+    error, not an out-of-bounds read."""
+    from chess_b200.engine import DeviceContacts, as_device_contacts, index_bins
+    from chess_b200.helpers import GenomicRegion, edges_dict_from_sparse, region_interval_trees
+    regions = [GenomicRegion(chromosome="c", start=k * 10, end=k * 10 + 10, ix=k) for k in range(100)]
+    trees = region_interval_trees(regions)
+    assert index_bins(trees) == 100 and index_bins(regions) == 100
+    a = np.arange(0, 59)
+    store = edges_dict_from_sparse((a, a + 1, np.ones(59)), n_bins=len(regions))
+    assert store.n_bins == 100
+    short = DeviceContacts(a, a + 1, np.ones(59))
+    assert short.n_bins == 60
+    with pytest.raises(ValueError, match="outside the contact store"):
+        short.check_span([50], [41])
+    assert as_device_contacts(short, index_bins(trees)).n_bins == 100
+    short.check_span([50], [41])
+    short.check_span([-1, 95], [0, 5])          # n = 0 marks "region not found": ignored
+    with pytest.raises(ValueError):
+        short.check_span([95], [6])
+    d = as_device_contacts({0: {1: 2.0}, 1: {1: 3.0}}, 7)
+    assert d.n_bins == 7 and d[0] == {1: 2.0}
+    # load_oe_contacts passes the number of regions
+    bed = tmp_path / "r.bed"
+    bed.write_text("".join("c\t%d\t%d\n" % (k * 10, k * 10 + 10) for k in range(30)))
+    mat = tmp_path / "m.sparse"
+    mat.write_text("0\t1\t1.5\n3\t4\t0.5\n")
+    import torch
+    if not torch.cuda.is_available():      # file parsing alone works without a GPU
+        from chess_b200.helpers import load_oe_contacts
+        edges, _, regs = load_oe_contacts(str(mat), str(bed))
+        assert edges.n_bins == len(regs) == 30
+
+
+def test_duplicate_contacts_keep_the_last_occurrence():
+    """chess/helpers.py:353-356: edges_d[source][sink] = weight -- a later line overwrites an earlier
+    one, and (i, j) / (j, i) are the same cell after canonicalisation."""
+    from chess_b200.engine import DeviceContacts
+    src = np.array([0, 1, 2, 1, 0, 5, 2])
+    snk = np.array([1, 2, 1, 2, 1, 5, 2])
+    val = np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0])
+    d = DeviceContacts(src, snk, val)
+    ref = {}
+    for a, b, w in zip(src, snk, val):
+        ref.setdefault(min(a, b), {})[max(a, b)] = w
+    got = {int(a): d[int(a)] for a in set(d.src.tolist())}
+    assert got == {int(k): {int(j): float(w) for j, w in row.items()} for k, row in ref.items()}
+    assert len(d.value) == sum(len(r) for r in ref.values())
+    # sorted, duplicate-free input is untouched (and takes the O(n) path)
+    e = DeviceContacts(np.array([0, 0, 1]), np.array([0, 2, 1]), np.array([1.0, 2.0, 3.0]))
+    assert e.value.tolist() == [1.0, 2.0, 3.0]
+    # oracle agrees (edges_from_sparse_matrix canonicalises before the dict is built, helpers.py:332-335)
+    lo, hi = np.minimum(src, snk), np.maximum(src, snk)
+    assert O.edges_dict(zip(lo.tolist(), hi.tolist(), val.tolist())) == \
+        {int(k): {int(j): float(w) for j, w in row.items()} for k, row in ref.items()}
+
+
+def test_oversized_and_mismatched_inputs_fail_with_a_clear_message():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("host-side validation is exercised on the CPU box")
+    from chess_b200.helpers import GenomicRegion
+    from chess_b200 import oe
+    regions = [GenomicRegion(chromosome="c", start=k * 10, end=k * 10 + 10, ix=k) for k in range(10)]
+    # index validation happens before any device work
+    import chess_b200.oe as oemod
+    orig = oemod.visible_devices
+    oemod.visible_devices = lambda: [0]
+    try:
+        with pytest.raises(IndexError, match="does not match the regions file"):
+            oe._device_expected(regions, (np.array([0, 3]), np.array([1, 12]), np.array([1.0, 2.0])))
+        with pytest.raises(IndexError):
+            oe._device_expected(regions, (np.array([-1]), np.array([1]), np.array([1.0])))
+    finally:
+        oemod.visible_devices = orig

@@ -169,3 +169,28 @@ def test_window_rule():
     assert O.window_rule(80, absolute_window_size=8) == 7
     assert O.window_rule(80, absolute_window_size=1) == 3
     assert O.window_rule(30, relative_window_size=0.01) == 3
+
+
+def test_extract_head_oracle_matches_reference_golden(toy):
+    """oracle.log_ratio_stage against what the reference's own extract_structures handed to its first
+    denoise_bilateral calls (tests/golden/make_golden_extract.py): bit for bit (same numpy)."""
+    import os
+    from tests.conftest import GOLDEN_DIR
+    gold = np.load(os.path.join(GOLDEN_DIR, "extract_golden.npz"))
+    trees, edges = [], []
+    for tag in ("ref", "qry"):
+        regions, conv, _ = O.load_regions(toy(tag + ".bed"))
+        trees.append(O.region_trees(regions))
+        edges.append(O.edges_dict(O.iter_sparse(toy(tag + ".oe.sparse"), conv)))
+    pairs, _ = O.load_pairs_for_chroms(toy("pairs.bedpe"), set(trees[0]) | set(trees[1]))
+    assert [p[0] for p in pairs] == gold["all_ids"].tolist()
+    have = set(gold["ids"].tolist())
+    for pair in pairs:
+        pid = pair[0]
+        if pid not in have:
+            with pytest.raises(ValueError):
+                O.log_ratio_stage(edges[0], trees[0], edges[1], trees[1], pair)
+            continue
+        pos, neg, std, mp, mn = O.log_ratio_stage(edges[0], trees[0], edges[1], trees[1], pair)
+        assert np.array_equal(pos, gold["pos_" + pid]) and np.array_equal(neg, gold["neg_" + pid])
+        assert [std, mp, mn] == gold["stats_" + pid].tolist()
