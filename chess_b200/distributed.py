@@ -31,31 +31,58 @@ def my_shard(total, rank, world):
     return int(b[rank]), int(b[rank + 1])
 
 
-def gather_to_rank0(local_arrays, total, rank, world, dist=None):
+def gather_to_rank0(local_arrays, total, rank, world, dist=None, group=None, device=None):
     """Concatenate per-rank result arrays in rank (= pair) order on rank 0.
 
-    ``local_arrays`` is a tuple of 1-D numpy arrays covering this rank's shard.
-    Returns the full arrays on rank 0 and ``None`` elsewhere.
+    ``local_arrays`` is a tuple of 1-D numpy arrays covering this rank's shard
+    (``shard_bounds(total, world)``).  All arrays travel in ONE collective: each
+    rank packs its arrays back to back into a byte buffer padded to the longest
+    shard (20 bytes per pair for ssim, SN and status), rank 0 unpacks.  ``group``
+    selects the process group (a gloo group for host buffers when the default
+    group is NCCL); with ``device`` the buffer is staged through that device
+    instead (NCCL groups).  Returns the full arrays on rank 0, ``None`` elsewhere.
     """
     if world == 1 or dist is None:
         return tuple(np.asarray(a) for a in local_arrays)
     import torch
     bounds = shard_bounds(total, world)
     longest = int(np.max(np.diff(bounds)))
-    out = []
-    for arr in local_arrays:
-        arr = np.ascontiguousarray(arr)
-        pad = np.zeros(longest, dtype=arr.dtype)
-        pad[:len(arr)] = arr
-        t = torch.from_numpy(pad)
-        bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, gather_list=bucket, dst=0)
-        if rank == 0:
-            full = np.empty(total, dtype=arr.dtype)
-            for k in range(world):
-                full[bounds[k]:bounds[k + 1]] = bucket[k].numpy()[:bounds[k + 1] - bounds[k]]
-            out.append(full)
-    return tuple(out) if rank == 0 else None
+    arrays = [np.ascontiguousarray(a) for a in local_arrays]
+    sizes = [a.dtype.itemsize for a in arrays]
+    buf = np.zeros(longest * sum(sizes), dtype=np.uint8)
+    off = 0
+    for a, size in zip(arrays, sizes):
+        buf[off:off + a.nbytes] = a.view(np.uint8)
+        off += longest * size
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, gather_list=bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = [np.empty(total, dtype=a.dtype) for a in arrays]
+    for k in range(world):
+        part = bucket[k].cpu().numpy() if device is not None else bucket[k].numpy()
+        n = int(bounds[k + 1] - bounds[k])
+        off = 0
+        for full, size in zip(out, sizes):
+            full[bounds[k]:bounds[k + 1]] = part[off:off + n * size].view(full.dtype)
+            off += longest * size
+    return tuple(out)
+
+
+def run_zscores(ssim):
+    """z_ssim over the whole run from the gathered ssim values (bin/chess:228-233): nanmean / nanstd
+    (ddof 0) over the non-NaN entries, NaN kept.  Rank 0 calls this after `gather_to_rank0`."""
+    ssim = np.asarray(ssim, dtype=np.float64)
+    z = np.full(len(ssim), np.nan)
+    ok = ~np.isnan(ssim)
+    if ok.any():
+        with np.errstate(invalid="ignore", divide="ignore"):
+            valid = ssim[ok]
+            z[ok] = (valid - valid.mean()) / valid.std()
+    return z
 
 
 def max_over_ranks(value, world, dist=None, device=None):

@@ -9,6 +9,9 @@ with a zero count are absent from the sparse output (their fraction rises with
 distance), and runs of bins are unmappable (no entries at all).
 
 Used by tests/ and bench.py; everything is vectorised numpy on the host.
+The module imports nothing of the package at import time, so bench.py's CPU
+reference arm can load it by file path without mapping the CUDA library;
+functions that make region objects take the class to use (`region_cls`).
 """
 import os
 
@@ -40,8 +43,10 @@ class Genome(object):
         self.bin_size = int(bin_size)
         self.lengths_bp = dict(chroms_bp) if chroms_bp else {c: int(n) * bin_size for c, n in chrom_bins}
 
-    def regions(self):
-        from .helpers import GenomicRegion
+    def regions(self, region_cls=None):
+        if region_cls is None:
+            from .helpers import GenomicRegion as region_cls
+        GenomicRegion = region_cls
         out = []
         for c, name in enumerate(self.names):
             for k in range(int(self.sizes[c])):
@@ -122,10 +127,17 @@ def write_sparse(path, src, sink, w):
     frame.to_csv(path, sep="\t", header=False, index=False, float_format="%.17g")
 
 
-def sliding_pairs(genome, window_bp, step_bp, chroms=None, strand_query="+"):
+def count_sliding_pairs(chroms_bp, window_bp, step_bp):
+    """Number of pairs `sliding_pairs` makes for these chromosome lengths."""
+    return int(sum(len(range(0, length - window_bp + 1, step_bp)) for _, length in chroms_bp))
+
+
+def sliding_pairs(genome, window_bp, step_bp, chroms=None, strand_query="+", region_cls=None):
     """[(ID, reference_region, query_region)] sliding windows, same locus both sides
     (the layout `chess pairs` emits, bin/chess:444-458)."""
-    from .helpers import GenomicRegion
+    if region_cls is None:
+        from .helpers import GenomicRegion as region_cls
+    GenomicRegion = region_cls
     out, pid = [], 0
     for name in genome.names:
         if chroms is not None and name not in chroms:

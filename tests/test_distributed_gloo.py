@@ -37,13 +37,29 @@ def _worker(rank, world, port, total, out_path):
     sn = idx * 0.5
     status = (idx % 17 == 0).astype(np.int32) * 3
     got = gather_to_rank0((ssim, sn, status), total, rank, world, dist)
+    # the same through an explicit (second) gloo group, as bench.py does beside an NCCL default group
+    again = gather_to_rank0((ssim, sn, status), total, rank, world, dist, group=dist.new_group(backend="gloo"))
     slowest = max_over_ranks(1.0 + rank, world, dist)
     if rank == 0:
-        np.savez(out_path, ssim=got[0], sn=got[1], status=got[2], slowest=slowest)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, again))
+        from chess_b200.distributed import run_zscores
+        np.savez(out_path, ssim=got[0], sn=got[1], status=got[2], slowest=slowest, z=run_zscores(got[0]))
     else:
         assert got is None
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_odd_total_three_ranks(tmp_path):
+    """Shards of unequal length (padding of the packed buffer) and a rank with an empty shard."""
+    for total, world in ((7, 3), (2, 3)):
+        out = str(tmp_path / ("g%d.npz" % total))
+        mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
+        got = np.load(out)
+        idx = np.arange(total)
+        want = np.sin(idx * 0.37)
+        want[idx % 17 == 0] = np.nan
+        assert np.array_equal(got["ssim"], want, equal_nan=True) and np.array_equal(got["sn"], idx * 0.5)
 
 
 def test_two_rank_gather_matches_single_process(tmp_path):
@@ -58,3 +74,7 @@ def test_two_rank_gather_matches_single_process(tmp_path):
     assert np.array_equal(got["sn"], idx * 0.5)
     assert np.array_equal(got["status"], (idx % 17 == 0).astype(np.int32) * 3)
     assert float(got["slowest"]) == 2.0
+    ok = ~np.isnan(want)                                          # bin/chess:228-233 on the gathered values
+    zw = np.full(total, np.nan)
+    zw[ok] = (want[ok] - np.nanmean(want)) / np.nanstd(want)
+    assert np.allclose(got["z"], zw, rtol=1e-12, atol=0, equal_nan=True)

@@ -24,7 +24,7 @@ def main():
     args = ap.parse_args()
     import bench
     from chess_b200.cli import Chess
-    genome, ref, qry, pairs = bench.make_workload(0)
+    genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(["--workload", "chr2_25kb"])))
     tmp = tempfile.mkdtemp()
     t0 = time.perf_counter()
     regions = genome.regions()

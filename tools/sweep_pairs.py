@@ -30,7 +30,8 @@ def main():
     from chess_b200.engine import get_context, region_spans, build_pair_table
 
     dev = torch.device("cuda", 0)
-    genome, ref, qry, pairs = bench.make_workload(0, "chr2_25kb", 1, args.bin_size, args.window_bp)
+    genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(
+        ["--workload", "chr2_25kb", "--bin-size", str(args.bin_size), "--window-bp", str(args.window_bp)])))
     regions = genome.regions()
     trees = cb.region_interval_trees(regions)
     p = _native.make_params(compute_sn=True, kernel=0, flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES,
