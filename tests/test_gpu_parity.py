@@ -647,7 +647,7 @@ def test_zscore_kernel(cb):
 def test_full_size_chr2_properties(cb):
     """BASELINE configs[1] at full size (9 688 bins, 2 402 pairs): size-independent properties."""
     import bench
-    genome, ref, qry, pairs = bench.make_workload(0)
+    genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(["--workload", "chr2_25kb"])))
     assert genome.n_bins == 9688 and len(pairs) == 2402
     regions = genome.regions()
     trees = cb.region_interval_trees(regions)

@@ -277,3 +277,52 @@ def test_mismatched_matrix_is_rejected_before_any_launch(cb):
     huge = cb.GenomicRegion(chromosome="c", start=1, end=11000000, strand="+")
     with pytest.raises(ValueError, match="at most 1024 bins"):
         eng.compare([("huge", huge, huge)])
+
+
+def test_full_size_hg38_properties(cb):
+    """BASELINE configs[2] at full size (hg38 @ 10 kb, 101 354 pairs of 201 bins): size-independent properties
+    of the kernels the north-star number is quoted on."""
+    import bench
+    w = bench.workload_spec(bench.parse_args([]))
+    assert w["name"] == "hg38_10kb" and w["pairs"] == 101354
+    genome, ref, qry, pairs = bench.make_workload(w)
+    assert len(pairs) == w["pairs"] and genome.n_bins == w["n_bins"]
+    regions = genome.regions()
+    trees = cb.region_interval_trees(regions)
+    re_ = cb.observed_expected_arrays(regions, ref)
+    qe = cb.observed_expected_arrays(regions, qry)
+    fwd = cb.CompareEngine(re_, trees, qe, trees)
+    rev = cb.CompareEngine(qe, trees, re_, trees)
+    for kw in (dict(), dict(absolute_window_size=7)):
+        ids, s, sn, st = fwd.compare(pairs, **kw)
+        assert ids == [p[0] for p in pairs] and (st == 0).sum() > 95000
+        # SSIM and SN are symmetric in (reference, query)
+        _, s_r, sn_r, st_r = rev.compare(pairs, **kw)
+        assert np.array_equal(st, st_r)
+        np.testing.assert_allclose(s, s_r, rtol=1e-10, equal_nan=True)
+        np.testing.assert_allclose(sn, sn_r, rtol=1e-9, equal_nan=True)
+        # results do not depend on how the pair list is cut into launches (1 / 2 / 4 / 8 GPUs cut it like this)
+        from chess_b200.distributed import shard_bounds
+        for world in (2, 8):
+            b = shard_bounds(len(pairs), world)
+            cut = [fwd.compare(pairs[b[k]:b[k + 1]], **kw) for k in range(world)]
+            assert np.concatenate([c[1] for c in cut]).tobytes() == s.tobytes()
+            assert np.concatenate([c[2] for c in cut]).tobytes() == sn.tobytes()
+        # SSIM is bounded, SN non-negative, failures are NaN in both columns
+        ok = st == 0
+        assert np.all(np.abs(s[ok]) <= 1.0 + 1e-12) and np.all(sn[ok] >= 0)
+        assert np.all(np.isnan(s[~ok])) and np.all(np.isnan(sn[~ok]))
+        # a sample against the generic kernel (a different implementation of the same function)
+        pick = pairs[::977]
+        a = fwd.compare(pick, **kw)
+        g = fwd.compare(pick, kernel=1, **kw)
+        assert np.array_equal(a[3], g[3])
+        np.testing.assert_allclose(a[1], g[1], rtol=1e-9, equal_nan=True)
+        np.testing.assert_allclose(a[2], g[2], rtol=1e-8, equal_nan=True)
+        assert np.array_equal(a[1], s[::977], equal_nan=True)      # and a pair's bits do not depend on its batch
+    # a matrix against itself
+    ids, s, sn, st = cb.CompareEngine(re_, trees, re_, trees).compare(pairs[::50])
+    ok = st == 0
+    assert np.all(np.abs(s[ok] - 1.0) < 1e-12) and np.all(np.isnan(sn[ok]))
+    re_.drop_device_copies()
+    qe.drop_device_copies()
