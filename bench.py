@@ -90,6 +90,8 @@ def parse_args(argv=None):
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child pass that measures DRAM traffic")
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 auto, 1 force the generic kernel, 2 the CTA-per-pair tuned kernel, 3 full-square items")
+    ap.add_argument("--sweep-windows", default=",".join(WINDOWS),
+                    help="sweep workload: comma-separated subset of the windows (development runs)")
     ap.add_argument("--probe-kernel", action="store_true",
                     help="internal: set the workload up, launch the compare kernel three times, exit (run under ncu)")
     return ap.parse_args(argv)
@@ -950,7 +952,7 @@ def measure_sweep(args, R, w):
         res.re_._bands.clear(), res.re_._index.clear(), res.qe._bands.clear(), res.qe._index.clear()
         res.rw, res.rband, res.rsample = res.re_.sample_on(R.local_rank, res.max_n)
         res.qw, res.qband, res.qsample = res.qe.sample_on(R.local_rank, res.max_n)
-        for win in WINDOWS:
+        for win in [x for x in WINDOWS if x in args.sweep_windows.split(",")]:
             a = copy.copy(args)
             a.window = win
             line = measure_pairs(a, R, wc, res=res, steps=steps, warmup=3, want_cpu=False, want_traffic=False)

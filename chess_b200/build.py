@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchess_b200.so")
 SOURCES = ["api.cu", "oe.cu", "compare_generic.cu", "compare_fast.cu", "background.cu", "ingest.cu", "extract.cu",
            "items_h0.cu", "items_tri.cu", "items_blk.cu", "items_blkw.cu", "items_tri7.cu", "items_triw.cu", "items_h1.cu", "items_h2.cu", "items_h3.cu"]
-HEADERS = ["common.cuh", "compare_kernels.cuh", "compare_tri.cuh", "compare_blk.cuh", "compare_blk7.cuh", "compare_blkw.cuh", "compare_tri7.cuh", "compare_triw.cuh", "parse_number.cuh", "pow5_table.inc", os.path.join("..", "..", "include", "chess_b200.h")]
+HEADERS = ["common.cuh", "compare_kernels.cuh", "compare_tri.cuh", "tri_rows.cuh", "compare_blk.cuh", "compare_blk7.cuh", "compare_blkw.cuh", "compare_tri7.cuh", "compare_triw.cuh", "parse_number.cuh", "pow5_table.inc", os.path.join("..", "..", "include", "chess_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["--shared", "-cudart", "static"]

@@ -71,186 +71,20 @@ compare_win7_tri_kernel(chess_item_args a) {
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
 
-    // ---- this item's lanes: rows [lo, hi), first column cbase
+    // ---- the parts of this item (tri_rows.cuh: bands cut at multiples of G, lane-uniform weights)
     int B1, B2, L1, L2;
-    tri_split(np_, G, B1, B2, L1, L2);
+    tri_split_aligned(np_, G, B1, B2, L1, L2);
     double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
     bool overflow = false;
+    const double c1 = C1 * 2401.0, c2 = C2 * 2401.0;
     for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
-    if (PAIR && part == 1) {
-      if (lane == 0) *susp_n = 0;
-      __syncwarp();
-    }
-    int lo = 0, hi = 0, cbase = 1 << 20;
-    if (part == 0) {
-      lo = 0; hi = B1; cbase = G * lane;
-    } else if (lane < L1) {
-      lo = B1; hi = B2; cbase = B1 - 3 + G * lane;
-    } else if (lane > L1 && lane <= L1 + L2) {
-      lo = B2; hi = np_; cbase = B2 - 3 + G * (lane - L1 - 1);
-    }
+    if (lane == 0) *susp_n = 0;
+    __syncwarp();
+    const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, 3);
     const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
-    unsigned xo[G], yo[G];
-    bool valid[G];
-    double wc[G];   // column weight: 0 halo / missing, 1 inside the band's diagonal block, 2 right of it
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c = cbase + g;
-      valid[g] = c < np_;
-      wc[g] = (!valid[g] || c < lo) ? 0.0 : (c < hi ? 1.0 : 2.0);
-      const int kc = valid[g] ? (int)kmap[c] : 0;
-      xo[g] = (unsigned)kc;
-      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
-    }
-
     if (rows_max > 0) {
-      const int first = part == 0 ? 0 : max(lo - 3, 0);          // idle lanes have lo = 0
-      const int t_emit0 = part == 0 ? 3 : 6;                      // first iteration with a complete window
-      const int T = rows_max + (part == 0 ? 3 : 6);
-      const double inv_np = 1.0 / 49.0;
-      const double cov_norm = 49.0 / 48.0;
-      double ccnt[G], wss[G];
-      double Vx[G], Vy[G], Vq[G], Vxy[G];
-      unsigned hist[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int c = cbase + g;
-        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-        wss[g] = (c >= 3 && c <= np_ - 4) ? wc[g] : 0.0;          // SSIM windows need 3 columns either side
-        Vx[g] = Vy[g] = Vq[g] = Vxy[g] = 0.0;
-        hist[g] = 0u;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
-      }
-      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-      int slot = 0;
-      double xn[G], yn[G];
-      auto fetch = [&](int row) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
-        if (row < np_) {
-          const unsigned kr = (unsigned)kmap[row];
-          const unsigned ro = kr * (unsigned)rp;
-          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
-          }
-        }
-      };
-      int row = first;
-      fetch(row);
-      for (int t = 0; t < T; ++t, ++row) {
-        double x[G], y[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
-        if (t + 1 < T) fetch(row + 1);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          double *cell = myring + ((slot * G + g) * 2) * 32;   // the slot being overwritten holds row - 7
-          const double xold = cell[0], yold = cell[32];
-          cell[0] = x[g];
-          cell[32] = y[g];
-          Vx[g] += x[g]; Vx[g] -= xold;
-          Vy[g] += y[g]; Vy[g] -= yold;
-          Vq[g] = fma(x[g], x[g], fma(y[g], y[g], Vq[g]));
-          Vq[g] = fma(-xold, xold, fma(-yold, yold, Vq[g]));
-          Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xold, yold, Vxy[g]);
-          hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
-          if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
-        }
-        slot = slot == 6 ? 0 : slot + 1;
-        if (slot == 0) {
-          // the ring has just wrapped: rebuild the four column sums from its seven rows.  A running sum keeps the
-          // rounding of every value that ever passed through it; rebuilt once per window height it is exact to a
-          // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            double vq = 0.0, vxy = 0.0;   // the quadratic sums only: errors in sum x, sum y enter linearly
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-              const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
-              vq = fma(xk, xk, fma(yk, yk, vq));
-              vxy = fma(xk, yk, vxy);
-            }
-            Vq[g] = vq; Vxy[g] = vxy;
-            if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
-          }
-        }
-
-        if (t >= t_emit0) {
-          const int rc = row - 3;   // centre row of the SSIM window and SN pixel row
-          const bool emit_row = rc >= lo && rc < hi;
-          const bool ssim_row = emit_row && rc >= 3 && rc <= np_ - 4;
-          double W4[4][G];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vq : Vxy;
-            double P[G + 1];
-            P[0] = 0.0; P[1] = V[0];
-#pragma unroll
-            for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
-            double up[3], dn[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
-              up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
-              dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int a0 = g - 3 < 0 ? 0 : g - 3;
-              const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
-              double w = a0 == 0 ? P[b0 + 1] : P[b0 + 1] - P[a0];
-              if (g - 3 < 0) w += up[2 - g];
-              if (g + 3 > G - 1) w += dn[g + 3 - G];
-              W4[q][g] = w;
-            }
-          }
-          const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-          unsigned suspect = 0u;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            {
-              const double ux = W4[0][g] * inv_np, uy = W4[1][g] * inv_np;
-              const double uq = W4[2][g] * inv_np, uxy = W4[3][g] * inv_np;
-              const double m2s = fma(ux, ux, uy * uy);                  // ux^2 + uy^2
-              const double vsum = cov_norm * (uq - m2s);                // vx + vy
-              const double vxy = cov_norm * fma(-ux, uy, uxy);
-              const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
-              const double B1s = m2s + C1, B2s = vsum + C2;
-              const double den = B1s * B2s;
-              const double num = A1 * A2;
-              double S = num * fast_rcp(den);
-              if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
-              if (ssim_row && wss[g] != 0.0) ss_sum = fma(wss[g], S, ss_sum);
-            }
-            if (with_sn) {
-              const double w1 = W4[0][g] - W4[1][g];
-              const double w2 = fma(-2.0, W4[3][g], W4[2][g]);
-              const bool own = emit_row & (wc[g] != 0.0);
-              const double cnt = rcnt * ccnt[g];
-              const double m2 = w2 * cnt;
-              const double den = fma(-w1, w1, m2);
-              // trusted: one-pass variance well conditioned AND the q - 2xy subtraction kept >= 10 digits
-              const bool good = own & (den > fma(m2, kVarGuard, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
-              const double gq = fabs(w1) * cnt * fast_rcp(den);
-              sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
-              sn_cnt += good ? wc[g] : 0.0;
-              if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
-            }
-          }
-          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (suspect & (1u << g)) {
-                const int e = atomicAdd(susp_n, 1);
-                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
-              }
-            }
-          }
-        }
-      }
+      tri_w7_part<G>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, part, rows_max, with_sn, c1, c2,
+                     susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();
         const int ns = *susp_n;
