@@ -303,6 +303,23 @@ __device__ __forceinline__ void tri_edge_row(const TriItem &it, int which, int l
   for (int k = 0; k < 5; ++k) rt[k] = warp_sum(t5[k]);
 }
 
+// Two records -> ssim, SN, status of the pair.  Deliberately not inlined: both ways a pair can run end here.
+__device__ __noinline__ void tri_r1_finish(const double *recs, int np_, int win, int m, const short *kmap,
+                                           const double *R, const double *Q, size_t rp, size_t qp, int n, int flip,
+                                           bool with_sn, double *ssim_out, double *sn_out, int *status_out) {
+  double t[5], row0[5], rowL[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    t[k] = recs[k] + recs[kTriRec + k];
+    row0[k] = recs[9 + k];
+    rowL[k] = recs[kTriRec + 9 + k];
+  }
+  const double mx = fmax(recs[5], recs[kTriRec + 5]), mn = fmin(recs[6], recs[kTriRec + 6]);
+  const double ss = recs[7] + recs[kTriRec + 7], sc = recs[8] + recs[kTriRec + 8];
+  finish_pair(t, mx, mn, ss, sc, row0, rowL, np_, win, m, kmap, R, Q, rp, qp, n, flip, with_sn, ssim_out, sn_out,
+              status_out);
+}
+
 // The first a.pair_items pairs of a launch are "pair items": one warp walks item A, then item B, with one
 // set-up, no record and no arrival counter.  The remaining pairs are two independent items each, which keeps
 // the tail of the grid short.  The launcher makes as many pairs as fill whole waves of warps pair items
@@ -314,8 +331,7 @@ __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2))
 compare_r1_tri_kernel(chess_item_args a) {
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
-  __shared__ double s_part[4][8];   // per warp: totals of the parts of the current pair item (seven doubles that
-                                    // would otherwise stay live through the second row loop)
+  __shared__ double s_rec[4][2 * kTriRec];   // per warp: the two records of the pair being finished
   extern __shared__ __align__(16) double ringbuf[];  // per warp: 7*G*32 doubles of d = x - y
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -367,73 +383,42 @@ compare_r1_tri_kernel(chess_item_args a) {
     const bool inloop_minmax = tri_extrema(a, it, lane, mflag, xmax, xmin);
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 
-    double P[7];
+    // every part ends in a record -- in shared memory for a pair item, in the scratch array for a half item --
+    // and ONE routine (tri_r1_finish, not inlined) turns two records into the result: a pair gives the same
+    // bits whichever way it ran
     bool overflow = false;
     for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
       double tot[7], vmax = -CUDART_INF, vmin = CUDART_INF;
       overflow |= !tri_r1_run_part<G, WITH_SN>(it, part, lane, kmap, myring, susp, susp_n, inloop_minmax, tot, vmax,
                                                vmin);
-      if (HYBRID) {
-        if (lane == 0) {
-          double *ptot = s_part[warp];
-#pragma unroll
-          for (int k = 0; k < 7; ++k) ptot[k] = part == part0 ? tot[k] : ptot[k] + tot[k];
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) P[k] = tot[k];
-      }
-      if (inloop_minmax) { xmax = fmax(xmax, vmax); xmin = fmin(xmin, vmin); }
-    }
-    if (HYBRID) {
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 7; ++k) P[k] = s_part[warp][k];
-    }
-
-    // first / last row totals for the 2x2 SSIM map (np even)
-    double rt0[5] = {0, 0, 0, 0, 0}, rtL[5] = {0, 0, 0, 0, 0};
-    if (m == 2) {
-      if (PAIR || part0 == 0) tri_edge_row(it, 0, lane, kmap, rt0);
-      if (PAIR || part0 == 1) tri_edge_row(it, 1, lane, kmap, rtL);
-    }
-
-    if (PAIR) {  // the whole pair was walked by this warp: verify the predicted masks and finish
-      bool bad = overflow || !tri_masks_hold(a, it, lane, kmap, mflag);
-      bad = __any_sync(0xffffffffu, bad);
+      double rt[5] = {0, 0, 0, 0, 0};     // first (part 0) / last (part 1) row totals for the 2x2 SSIM map (np even)
+      if (m == 2) tri_edge_row(it, part, lane, kmap, rt);
       if (lane == 0) {
-        if (bad) {
-          a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
-          atomicOr(a.retry_cur, 1);
-        } else {
-          finish_pair(P, xmax, xmin, P[5], P[6], rt0, rtL, np_, win, m, kmap, it.R, it.Q, it.rp, it.qp, it.n, it.flip,
-                      WITH_SN, a.ssim + pi, a.sn + pi, a.status + pi);
-        }
-      }
-      continue;
-    }
-
-    // ---- record of this item
-    double *rec = a.scratch + ((size_t)pi * 2 + part0) * kTriRec;
-    if (lane == 0) {
-      const double *rt = part0 == 0 ? rt0 : rtL;
-      rec[0] = P[0]; rec[1] = P[1]; rec[2] = P[2]; rec[3] = P[3]; rec[4] = P[4];
-      rec[5] = xmax; rec[6] = xmin; rec[7] = P[5]; rec[8] = P[6];
+        double *rec = PAIR ? s_rec[warp] + part * kTriRec : a.scratch + ((size_t)pi * 2 + part) * kTriRec;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) rec[9 + k] = rt[k];
-      rec[14] = overflow ? 1.0 : 0.0;
+        for (int k = 0; k < 5; ++k) rec[k] = tot[k];
+        rec[5] = inloop_minmax ? vmax : xmax; rec[6] = inloop_minmax ? vmin : xmin;
+        rec[7] = tot[5]; rec[8] = tot[6];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rec[9 + k] = rt[k];
+        rec[14] = overflow ? 1.0 : 0.0;
+      }
     }
-    __threadfence();
+    if (!PAIR) {
+      __threadfence();
+      __syncwarp();
+      int arrived = 0;
+      if (lane == 0) arrived = atomicAdd(a.done + pi, 1);
+      arrived = __shfl_sync(0xffffffffu, arrived, 0);
+      if (arrived != 1) continue;
+      // second item to arrive: fetch both records
+      __threadfence();
+      const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
+      s_rec[warp][lane] = __ldcg(recs + lane);
+    }
     __syncwarp();
-    int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(a.done + pi, 1);
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if (arrived != 1) continue;
-
-    // ---- second item to arrive: verify the predicted masks, combine, write the result
-    __threadfence();
-    const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
-    bool bad = __ldcg(recs + 14) != 0.0 || __ldcg(recs + kTriRec + 14) != 0.0;
+    // verify the predicted masks, combine, write the result
+    bool bad = s_rec[warp][14] != 0.0 || s_rec[warp][kTriRec + 14] != 0.0;
     bad |= !tri_masks_hold(a, it, lane, kmap, mflag);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
@@ -441,21 +426,12 @@ compare_r1_tri_kernel(chess_item_args a) {
         a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
         atomicOr(a.retry_cur, 1);
       } else {
-        double t[5], mx, mn, ss, sc;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) t[k] = __ldcg(recs + k) + __ldcg(recs + kTriRec + k);
-        mx = fmax(__ldcg(recs + 5), __ldcg(recs + kTriRec + 5));
-        mn = fmin(__ldcg(recs + 6), __ldcg(recs + kTriRec + 6));
-        ss = __ldcg(recs + 7) + __ldcg(recs + kTriRec + 7);
-        sc = __ldcg(recs + 8) + __ldcg(recs + kTriRec + 8);
-        double row0[5], rowL[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { row0[k] = __ldcg(recs + 9 + k); rowL[k] = __ldcg(recs + kTriRec + 9 + k); }
-        finish_pair(t, mx, mn, ss, sc, row0, rowL, np_, win, m, kmap, it.R, it.Q, it.rp, it.qp, it.n, it.flip, WITH_SN,
-                    a.ssim + pi, a.sn + pi, a.status + pi);
+        tri_r1_finish(s_rec[warp], np_, win, m, kmap, it.R, it.Q, it.rp, it.qp, it.n, it.flip, WITH_SN, a.ssim + pi,
+                      a.sn + pi, a.status + pi);
       }
-      a.done[pi] = 0;
+      if (!PAIR) a.done[pi] = 0;
     }
+    __syncwarp();
   }
 }
 

@@ -70,6 +70,15 @@ compare_win7_tri_kernel(chess_item_args a) {
     if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
+    if (!(C2 > 0.0)) {
+      // constant matrices (zero data range): the SSIM quotient degenerates to x / 0; the generic kernel evaluates
+      // it with a true division, as numpy does
+      if (part0 == 0 && lane == 0) {
+        a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
+        atomicOr(a.retry_cur, 1);
+      }
+      continue;
+    }
 
     // ---- the parts of this item (tri_rows.cuh: bands cut at multiples of G, lane-uniform weights)
     int B1, B2, L1, L2;

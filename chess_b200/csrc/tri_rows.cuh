@@ -49,6 +49,15 @@ __host__ __device__ __forceinline__ bool tri_split_aligned(int np_, int G, int &
   return true;
 }
 
+// A pointer as one 64-bit register value (an opaque move: keeps the two halves in an aligned register pair, which
+// IMAD.WIDE needs for its 64-bit addend -- computed piecewise, ptxas may leave them in unrelated registers and then
+// splits every address into a multiply and a 64-bit add).
+__device__ __forceinline__ const double *as_reg_pair(const double *p) {
+  unsigned long long v;
+  asm("mov.b64 %0, %1;" : "=l"(v) : "l"(p));
+  return reinterpret_cast<const double *>(v);
+}
+
 // One element of a matrix row: row base + 32-bit element offset as ONE IMAD.WIDE, then the load.  The loads
 // are volatile asm so that they stay where they are written (at the top of the iteration that precedes their
 // use); left to the compiler they sink towards their first use and the row they overwrite gets copied.
@@ -81,6 +90,8 @@ __device__ __forceinline__ void pin_before_loads(const double (&v)[G]) {
 __device__ __forceinline__ void pin_before_loads(double a, double b, double c, double d, double e) {
   asm volatile("" ::"d"(a), "d"(b), "d"(c), "d"(d), "d"(e));
 }
+// ... and stores written before it (the ring slots that take the current row) stay before it, too
+__device__ __forceinline__ void pin_stores_before_loads() { asm volatile("" ::: "memory"); }
 template <int G>
 __device__ __forceinline__ void pin_before_loads(const unsigned (&v)[G]) {
 #pragma unroll
@@ -181,8 +192,8 @@ __device__ __forceinline__ void tri_r1_part(const double *__restrict__ R, const 
     constexpr bool TAIL = decltype(tail_tag)::value;
     const bool vr = !TAIL || row < np_;
     const unsigned kr = (unsigned)kmap[TAIL ? (vr ? row : 0) : row];
-    const double *rowR = R + (size_t)(kr * rp);
-    const double *rowQ = Q + (size_t)((flip ? (unsigned)(n - 1) - kr : kr) * qp) + (flip ? n - 1 : 0);
+    const double *rowR = as_reg_pair(R + (size_t)(kr * rp));
+    const double *rowQ = as_reg_pair(Q + (size_t)((flip ? (unsigned)(n - 1) - kr : kr) * qp) + (flip ? n - 1 : 0));
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if (g < nv) {
@@ -378,8 +389,8 @@ __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const 
     constexpr bool TAIL = decltype(tail_tag)::value;
     const bool vr = !TAIL || row < np_;
     const unsigned kr = (unsigned)kmap[TAIL ? (vr ? row : 0) : row];
-    const double *rowR = R + (size_t)(kr * rp);
-    const double *rowQ = Q + (size_t)((flip ? (unsigned)(n - 1) - kr : kr) * qp) + (flip ? n - 1 : 0);
+    const double *rowR = as_reg_pair(R + (size_t)(kr * rp));
+    const double *rowQ = as_reg_pair(Q + (size_t)((flip ? (unsigned)(n - 1) - kr : kr) * qp) + (flip ? n - 1 : 0));
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if (g < nv) {
@@ -408,6 +419,7 @@ __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const 
     // the row is used up (ring, column sums, history): the next one travels while the rest of the iteration runs
     pin_before_loads<G>(Vx); pin_before_loads<G>(Vy); pin_before_loads<G>(Vq); pin_before_loads<G>(Vxy);
     pin_before_loads<G>(hist);
+    pin_stores_before_loads();
     if (t < t_main) fetch(row + 1, std::false_type());
     else if (t + 1 < T) fetch(row + 1, std::true_type());
 #pragma unroll
@@ -475,8 +487,7 @@ __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const 
             const double u = fma(49.0, W4[2][g], -s2);
             const double b2 = fma(cn, u, c2);
             const double num = a1 * a2, den = b1 * b2;
-            double S = num * fast_rcp(den);
-            if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
+            const double S = num * fast_rcp(den);   // den > 0: a zero data range never gets here (caller)
             if (ssmask & (1u << g)) ss_sum += S;
           }
         }
