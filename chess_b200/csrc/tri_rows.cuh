@@ -526,4 +526,236 @@ __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const 
   cnt_out = ln.wl * (double)sn_cnt;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// -a 3 / 5 / 9 / 11 (H = 1, 2, 4, 5): the SSIM window (2H+1 rows) and the SN window (7 rows) differ, so the
+// column sums are kept separately -- Vx, Vy, Vq = sum x^2 + y^2, Vxy over the last 2H+1 rows, Sd, Se over the
+// last 7 -- all fed from one ring of x and y that is max(2H+1, 7) rows deep.  Geometry, loads and fences as in
+// tri_r1_part; the bands carry a halo of max(H, 3) rows, and one whole lane of columns left of their block.
+template <int G, int H>
+__device__ __forceinline__ void tri_win_part(const double *__restrict__ R, const double *__restrict__ Q, unsigned rp,
+                                             unsigned qp, int n, int np_, int flip, const short *kmap,
+                                             double *myring, const TriLane &ln, int part, int rows_max,
+                                             bool with_sn, double c1, double c2, int *susp, int *susp_n,
+                                             double &ss_out, double &sn_out, double &cnt_out) {
+  static_assert(H >= 1 && H <= 5 && H != 3 && G >= H, "window 3 / 5 / 9 / 11");
+  constexpr int HALO = H > 3 ? H : 3;
+  constexpr int WIN = 2 * H + 1;
+  constexpr int D = WIN > 7 ? WIN : 7;          // ring depth in rows
+  const int lo = ln.lo, hi = ln.hi, cbase = ln.cbase;
+  const int t_own0 = part == 0 ? 0 : HALO;      // iteration of the band's first own row
+  const int T = rows_max + (part == 0 ? HALO : 2 * HALO);
+  int nv = np_ - cbase;
+  nv = nv < 0 ? 0 : (nv > G ? G : nv);
+  unsigned xo[G];
+  double ccnt[G];
+  const int ystep = flip ? -8 : 8;
+  unsigned ssmask = 0u;                         // columns whose SSIM window lies inside the matrix
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int c = cbase + g;
+    const int kc = g < nv ? (int)kmap[c] : 0;
+    xo[g] = (unsigned)kc;
+    ccnt[g] = g < nv ? (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1) : 0.0;
+    if (g < nv && c >= H && c <= np_ - 1 - H) ssmask |= 1u << g;
+  }
+  const unsigned ownmask = ln.wl > 0.0 ? ((1u << nv) - 1u) : 0u;
+  if (!(ln.wl > 0.0)) ssmask = 0u;
+
+  double ss_sum = 0.0, sn_sum = 0.0;
+  int sn_cnt = 0;
+  double Sd[G], Se[G], Vx[G], Vy[G], Vq[G], Vxy[G];
+  unsigned hist[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    Sd[g] = Se[g] = Vx[g] = Vy[g] = Vq[g] = Vxy[g] = 0.0;
+    hist[g] = 0u;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
+  }
+  const int up_lane = (threadIdx.x + 31) & 31, dn_lane = (threadIdx.x + 1) & 31;
+  int slot = 0;
+  double x[G], y[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { x[g] = 0.0; y[g] = 0.0; }
+  int t_tail = nv > 0 ? np_ - ln.first : (1 << 20);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t_tail = min(t_tail, __shfl_xor_sync(0xffffffffu, t_tail, o));
+  const int t_main = min(T, t_tail) - 1;
+  constexpr double NP = (double)(WIN * WIN);
+  constexpr double cn = NP / (NP - 1.0);
+
+  auto fetch = [&](int row, auto tail_tag) {
+    constexpr bool TAIL = decltype(tail_tag)::value;
+    const bool vr = !TAIL || row < np_;
+    const unsigned kr = (unsigned)kmap[TAIL ? (vr ? row : 0) : row];
+    const double *rowR = as_reg_pair(R + (size_t)(kr * rp));
+    const double *rowQ = as_reg_pair(Q + (size_t)((flip ? (unsigned)(n - 1) - kr : kr) * qp) + (flip ? n - 1 : 0));
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (g < nv) {
+        if (!TAIL || vr) { x[g] = ld_row(rowR, xo[g]); y[g] = ld_row_step(rowQ, xo[g], ystep); }
+        else { x[g] = 0.0; y[g] = 0.0; }
+      }
+    }
+  };
+
+  int row = ln.first;
+  if (T > 0) fetch(row, std::false_type());
+  for (int t = 0; t < T; ++t, ++row) {
+    // ring positions of the rows that leave the 7-row and the WIN-row windows
+    const int s7 = slot + D - 7 >= D ? slot - 7 : slot + D - 7;        // row - 7
+    const int sw = slot + D - WIN >= D ? slot - WIN : slot + D - WIN;  // row - WIN
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
+      const double xow = myring[((sw * G + g) * 2) * 32], yow = myring[((sw * G + g) * 2 + 1) * 32];
+      myring[((slot * G + g) * 2) * 32] = x[g];
+      myring[((slot * G + g) * 2 + 1) * 32] = y[g];
+      const double dv = x[g] - y[g], dold = xo7 - yo7;
+      Sd[g] += dv; Sd[g] -= dold;
+      Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
+      hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
+      Vx[g] += x[g]; Vx[g] -= xow;
+      Vy[g] += y[g]; Vy[g] -= yow;
+      Vq[g] = fma(x[g], x[g], fma(y[g], y[g], Vq[g]));
+      Vq[g] = fma(-xow, xow, fma(-yow, yow, Vq[g]));
+      Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
+    }
+    // the row is used up (ring, column sums, history): the next one travels while the rest of the iteration runs
+    pin_before_loads<G>(Sd); pin_before_loads<G>(Se); pin_before_loads<G>(Vx); pin_before_loads<G>(Vy);
+    pin_before_loads<G>(Vq); pin_before_loads<G>(Vxy); pin_before_loads<G>(hist);
+    pin_stores_before_loads();
+    if (t < t_main) fetch(row + 1, std::false_type());
+    else if (t + 1 < T) fetch(row + 1, std::true_type());
+#pragma unroll
+    for (int g = 0; g < G; ++g) Se[g] = hist[g] == 0u ? 0.0 : Se[g];   // seven equal rows: exactly 0
+    slot = slot == D - 1 ? 0 : slot + 1;
+    if (slot == 0) {
+      // the ring has just wrapped: rebuild the 7-row sums of d*d from its most recent seven rows (slots D-7 .. D-1)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int k = D - 7; k < D; ++k) {
+          const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
+          s2 = fma(dk, dk, s2);
+        }
+        Se[g] = hist[g] == 0u ? 0.0 : s2;
+      }
+    }
+
+    // ---- SSIM windows whose centre row is row - H
+    if (t >= t_own0 + H) {
+      const int rcs = row - H;
+      double W4[4][G];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vq : Vxy;
+        double P[G + 1], X[G];
+        P[0] = 0.0; P[1] = V[0];
+#pragma unroll
+        for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
+        X[G - 1] = V[G - 1];
+#pragma unroll
+        for (int g = G - 2; g >= 0; --g) X[g] = X[g + 1] + V[g];
+        double up[H], dn[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          up[j] = __shfl_sync(0xffffffffu, X[G - 1 - j < 0 ? 0 : G - 1 - j], up_lane);
+          dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int a0 = g - H < 0 ? 0 : g - H;
+          const int b0 = g + H > G - 1 ? G - 1 : g + H;
+          double w;
+          if (a0 == 0) w = P[b0 + 1];
+          else if (b0 == G - 1) w = X[a0];
+          else {            // the window lies inside the strip (H <= 2 only): its 2H+1 columns, added up
+            w = V[a0];
+#pragma unroll
+            for (int j = a0 + 1; j <= b0; ++j) w += V[j];
+          }
+          if (g - H < 0) w += up[H - 1 - g];
+          if (g + H > G - 1) w += dn[g + H - G];
+          W4[q][g] = w;
+        }
+      }
+      if (rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double wx = W4[0][g], wy = W4[1][g];
+          const double p = wx * wy;
+          const double s2 = fma(wx, wx, wy * wy);
+          const double a1 = fma(2.0, p, c1), b1 = s2 + c1;
+          const double tt = fma(NP, W4[3][g], -p);
+          const double a2 = fma(2.0 * cn, tt, c2);
+          const double u = fma(NP, W4[2][g], -s2);
+          const double b2 = fma(cn, u, c2);
+          const double S = (a1 * a2) * fast_rcp(b1 * b2);   // b1 b2 > 0: a zero data range never gets here (caller)
+          if (ssmask & (1u << g)) ss_sum += S;
+        }
+      }
+    }
+
+    // ---- SN pixels of row - 3
+    if (with_sn && t >= t_own0 + 3) {
+      const int rc = row - 3;
+      double P1[G + 1], P2[G + 1];
+      P1[0] = 0.0; P2[0] = 0.0;
+      P1[1] = Sd[0]; P2[1] = Se[0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
+      double X1[G], X2[G];
+      X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
+#pragma unroll
+      for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
+      double up1[3], up2[3], dn1[3], dn2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
+        const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
+        up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
+        up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
+        dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
+        dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
+      }
+      if (rc >= lo && rc < hi) {
+        const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
+        unsigned bad = 0u;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int a0 = g - 3 < 0 ? 0 : g - 3;
+          const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
+          double w1 = a0 == 0 ? P1[b0 + 1] : X1[a0];
+          double w2 = a0 == 0 ? P2[b0 + 1] : X2[a0];
+          if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
+          if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
+          const double cnt = rcnt * ccnt[g];
+          const double m2 = w2 * cnt;
+          const double den = fma(-w1, w1, m2);
+          const bool good = den > fma(m2, kVarGuard, 1e-290);
+          const double gq = fabs(w1) * cnt * fast_rcp(den);
+          if (good) { sn_sum += gq; sn_cnt += 1; }
+          if (!good && w2 != 0.0) bad |= 1u << g;
+        }
+        bad &= ownmask;
+        if (bad) {  // rare: exact recompute after the loop
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (bad & (1u << g)) {
+              const int e = atomicAdd(susp_n, 1);
+              if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
+            }
+          }
+        }
+      }
+    }
+  }
+  ss_out = ln.wl * ss_sum;
+  sn_out = ln.wl * sn_sum;
+  cnt_out = ln.wl * (double)sn_cnt;
+}
+
 }  // namespace
