@@ -96,6 +96,8 @@ SIGNATURES = {
     "chess_possible_contacts": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "chess_oe_values": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "chess_band_build": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _dbl, _vp, _vp]),
+    "chess_band_build_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _dbl, _vp, _vp]),
+    "chess_coo_check": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "chess_gather_submatrix": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
@@ -122,8 +124,8 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 # the struct layouts above follow include/chess_b200.h at this ABI version (chess_sample grew `rowpre` in 2,
-# chess_params grew `data_range` in 3)
-ABI_VERSION = 3
+# chess_params grew `data_range` in 3; 4 added chess_band_build_range and chess_coo_check)
+ABI_VERSION = 4
 if lib.chess_abi_version() != ABI_VERSION:
     raise ChessNativeError("libchess_b200.so has ABI version {}, this binding expects {}: rebuild with "
                            "python -m chess_b200.build".format(lib.chess_abi_version(), ABI_VERSION))

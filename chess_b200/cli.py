@@ -16,6 +16,34 @@ from . import commands
 
 logger = logging.getLogger('')
 
+# stage -> seconds of the last `run_sim` (development aid, tools/cli_e2e.py prints it)
+LAST_STAGES = {}
+
+
+class _StageClock(object):
+    """Wall-clock split of run_sim; every stage ends with a device synchronisation so that asynchronous GPU work is
+    charged to the stage that launched it."""
+
+    def __init__(self):
+        import time
+        self._time = time.perf_counter
+        self._t = self._time()
+        LAST_STAGES.clear()
+
+    def mark(self, name, sync=True):
+        if sync:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    for d in range(torch.cuda.device_count()):
+                        torch.cuda.synchronize(d)
+            except Exception:
+                pass
+        now = self._time()
+        LAST_STAGES[name] = LAST_STAGES.get(name, 0.0) + (now - self._t)
+        logger.debug("stage %s: %.3f s", name, now - self._t)
+        self._t = now
+
 
 
 class Chess(object):
@@ -135,13 +163,14 @@ class Chess(object):
 def _zscores(ssim):
     """z_ssim over the run; bin/chess:216-233 (nanmean / nanstd, ddof 0)."""
     import warnings
-    valid = [s for s in ssim if not np.isnan(s)]
+    ssim = np.asarray(ssim, dtype=np.float64)
+    valid = ssim[~np.isnan(ssim)]
     with warnings.catch_warnings(), np.errstate(invalid="ignore", divide="ignore"):
         warnings.simplefilter("ignore")
         mean, sd = np.nanmean(valid), np.nanstd(valid)
         z = np.full(len(ssim), np.nan)
         fin = np.isfinite(ssim)
-        z[fin] = (np.asarray(ssim)[fin] - mean) / sd
+        z[fin] = (ssim[fin] - mean) / sd
     return z
 
 
@@ -165,10 +194,51 @@ def _background_regions_from_query(query_regions, query_region, limit_background
     return out
 
 
+def _float_column(values):
+    """Every value as '{}'.format(np.float64(v)) writes it (numpy prints float64 like Python prints float: shortest
+    round-trip digits, exponent form below 1e-4 and from 1e16; tests/test_host_logic.py compares the two)."""
+    return list(map(repr, np.asarray(values, dtype=np.float64).tolist()))
+
+
+def _background_spans_from_query(query_regions, query_trees, query_region, limit_background):
+    """bin/chess:272-298 as columns: every query bin start x {+, -} with the size of `query_region`, kept where it
+    ends inside its chromosome, optionally on the pair's chromosome only -> (first_bin, n_bins, strand code)
+    of every background region, in the reference's order.  No region objects are made."""
+    from .engine import region_spans
+    from .helpers import RegionTable
+    if not isinstance(query_regions, RegionTable):
+        regs = _background_regions_from_query(query_regions, query_region, limit_background)
+        bf, bn = region_spans(query_trees, regs)
+        return bf, bn, np.array([0 if r.strand == '+' else 1 for r in regs], dtype=np.int32)
+    t = query_regions
+    size = query_region.end - query_region.start
+    ends = np.zeros(len(t.chrom_names), dtype=np.int64)
+    np.maximum.at(ends, t.chrom_codes, t.ends)
+    keep = t.starts + size <= ends[t.chrom_codes]
+    if limit_background:
+        if query_region.chromosome not in t.chrom_names:
+            keep[:] = False
+        else:
+            keep &= t.chrom_codes == t.chrom_names.index(query_region.chromosome)
+    rows = np.flatnonzero(keep)
+    first = np.full(len(rows), -1, dtype=np.int64)
+    count = np.zeros(len(rows), dtype=np.int64)
+    codes = t.chrom_codes[rows]
+    for c in np.unique(codes):
+        sel = np.flatnonzero(codes == c)
+        starts = t.starts[rows[sel]]
+        lo, hi = query_trees[t.chrom_names[int(c)]].span(starts - 1, starts + size)   # region [start, start + size]
+        ok = lo >= 0
+        first[sel[ok]] = lo[ok]
+        count[sel[ok]] = hi[ok] - lo[ok] + 1
+    return (np.repeat(first, 2), np.repeat(count, 2).astype(np.int64),
+            np.tile(np.array([0, 1], dtype=np.int32), len(rows)))
+
+
 def run_sim(args):
     """Body of `chess sim` (bin/chess:80-359) on the batched engine."""
     from .engine import CompareEngine, region_spans, visible_devices
-    from .helpers import load_pairs_for_chroms, load_regions, load_contacts, load_oe_contacts
+    from .helpers import load_pairs_table, load_regions, load_contacts, load_oe_contacts, RegionTable
 
     output_file = args.out
     output_dir = os.path.dirname(output_file)
@@ -179,32 +249,47 @@ def run_sim(args):
         raise RuntimeError("Specified output path not found.")
     logger.debug('Parameters:')
     logger.debug(args)
+    clock = _StageClock()
 
     loader = load_oe_contacts if args.oe_input else load_contacts
+    devices = visible_devices()
+    query_job = None
+    if len(devices) > 1:
+        # two samples, two GPUs: the query is read, parsed and normalised on the second one meanwhile
+        from concurrent.futures import ThreadPoolExecutor
+        query_job = ThreadPoolExecutor(1).submit(loader, args.query_contacts, args.query_regions, devices[1])
     logger.info('Loading reference contact data')
     try:
         reference_edges, reference_trees, reference_regions = loader(
-            args.reference_contacts, args.reference_regions)
+            args.reference_contacts, args.reference_regions, devices[0])
     except ValueError as error:
         logger.error(error)
         logger.error("Reference contact data could not be loaded. Please specify a valid input "
                      "file. Files in sparse format can only be loaded if --reference-regions is "
                      "specified.")
         sys.exit()
+    clock.mark("load reference contacts (+O/E)")
     logger.info('Loading query contact data')
     try:
-        query_edges, query_trees, query_regions = loader(args.query_contacts, args.query_regions)
+        if query_job is not None:
+            query_edges, query_trees, query_regions = query_job.result()
+        else:
+            query_edges, query_trees, query_regions = loader(args.query_contacts, args.query_regions, devices[0])
     except ValueError as error:
         logger.error(error)
         logger.error("Query contact data could not be loaded. Please specify a valid input file. "
                      "Files in sparse format can only be loaded if --query-regions is specified.")
         sys.exit()
 
-    reference_bin_size = max(r.end - r.start + 1 for r in reference_regions)
-    query_bin_size = max(r.end - r.start + 1 for r in query_regions)
+    clock.mark("load query contacts (+O/E)")
+    def bin_size(regions):
+        return regions.max_bin_size() if isinstance(regions, RegionTable) else max(r.end - r.start + 1 for r in regions)
+
+    reference_bin_size = bin_size(reference_regions)
+    query_bin_size = bin_size(query_regions)
 
     logger.info('Loading region pairs')
-    pairs, dropped = load_pairs_for_chroms(
+    pairs, dropped = load_pairs_table(
         args.pairs, set(reference_trees.keys()) | set(query_trees.keys()))
     if dropped > 0:
         logger.warning("{} region pairs have been dropped, because they involve chromosomes that "
@@ -213,8 +298,9 @@ def run_sim(args):
         logger.error("No valid region pairs found; aborting.")
         sys.exit()
 
-    max_ref_span = int(max(p[1].end - p[1].start + 1 for p in pairs) / reference_bin_size)
-    max_qry_span = int(max(p[2].end - p[2].start + 1 for p in pairs) / query_bin_size)
+    ref_bp, qry_bp = pairs.max_spans_bp()
+    max_ref_span = int(ref_bp / reference_bin_size)
+    max_qry_span = int(qry_bp / query_bin_size)
     for span, what, bin_size in ((max_ref_span, "reference", reference_bin_size),
                                  (max_qry_span, "query", query_bin_size)):
         if span < 20:  # bin/chess:169-187
@@ -224,7 +310,7 @@ def run_sim(args):
                          .format(what, span, bin_size))
             sys.exit()
 
-    devices = visible_devices()
+    clock.mark("load pairs, bin-size guard")
     logger.info("Launching comparison engine on GPU(s) {}".format(devices))
     engine = CompareEngine(reference_edges, reference_trees, query_edges, query_trees, devices=devices)
     params = dict(min_bins=20, keep_unmappable_bins=args.keep_unmappable_bins,
@@ -234,7 +320,9 @@ def run_sim(args):
 
     logger.info("Submitting pairs for comparison")
     ids, ssim, sn, status = engine.compare(pairs, compute_sn=True, **params)
+    clock.mark("compare (spans, bands, kernels, gather)")
     z_ssim = _zscores(ssim)
+    clock.mark("z-scores")
 
     background = args.background_regions is not None or args.background_query
     z_bg = p_bg = None
@@ -247,7 +335,7 @@ def run_sim(args):
             logger.info("Generating background regions from query")
         z_bg = np.full(len(pairs), np.nan)
         p_bg = np.full(len(pairs), np.nan)
-        rf, rn = region_spans(reference_trees, [p[1] for p in pairs])
+        rf, rn, qf, qn = engine.last_spans
         # strands as integer codes: a comparison is flipped iff the codes differ (sim.py:332-333)
         codes = {'+': 0, '-': 1, None: 2}
 
@@ -256,46 +344,47 @@ def run_sim(args):
                 codes[strand] = len(codes)
             return codes[strand]
 
-        ref_strand = np.array([strand_code(p[1].strand) for p in pairs], dtype=np.int32)
-        qry_strand = np.array([strand_code(p[2].strand) for p in pairs], dtype=np.int32)
-        qf, qn = region_spans(query_trees, [p[2] for p in pairs])
+        ref_strand = np.array([strand_code(v) for v in pairs.ref[3]], dtype=np.int32)
+        qry_strand = np.array([strand_code(v) for v in pairs.qry[3]], dtype=np.int32)
         # pairs that share a background set (the BED, or query size [+ chromosome]) go to the device
         # together: one chess_background_batch per set, nothing but z_bg / p_bg comes back
-        groups = {}
-        for k, pair in enumerate(pairs):
-            if background_regions is not None:
-                key = "bed"
-            else:
-                q = pair[2]
-                key = (q.chromosome if args.limit_background else None, q.end - q.start)
-            groups.setdefault(key, []).append(k)
+        if background_regions is not None:
+            groups = {"bed": np.arange(len(pairs))}
+        else:
+            import pandas as pd
+            size = pairs.qry[2] - pairs.qry[1]
+            keys = pd.DataFrame({"c": pairs.qry[0] if args.limit_background else np.zeros(len(pairs), dtype=object),
+                                 "s": size})
+            groups = {key: np.asarray(ix) for key, ix in keys.groupby(["c", "s"], sort=False).indices.items()}
         for key, ks in groups.items():
             if background_regions is not None:
-                regs = background_regions
+                bf, bn = region_spans(query_trees, background_regions)
+                bstrand = np.array([strand_code(r.strand) for r in background_regions], dtype=np.int32)
             else:
-                regs = _background_regions_from_query(query_regions, pairs[ks[0]][2], args.limit_background)
-            bf, bn = region_spans(query_trees, regs)
-            bstrand = np.array([strand_code(r.strand) for r in regs], dtype=np.int32)
-            ks = np.asarray(ks)
+                bf, bn, bstrand = _background_spans_from_query(query_regions, query_trees, pairs[int(ks[0])][2],
+                                                               args.limit_background)
             z, pv = engine.background(rf[ks], rn[ks], ref_strand[ks], np.asarray(ssim)[ks], bf, bn, bstrand,
                                       own=(qf[ks], qn[ks], qry_strand[ks]), **params)
             z_bg[ks] = z
             p_bg[ks] = pv
 
-    nan_counter = 0
+    if background:
+        clock.mark("background")
+    # rows in pairs-file order; numbers as '{}'.format(np.float64) prints them (shortest round-trip repr, 'nan');
+    # soft failures carry (nan, nan, nan), successful pairs their SN (bin/chess:236-256, 334-353)
+    ssim = np.asarray(ssim, dtype=np.float64)
+    failed = np.isnan(ssim)
+    nan_counter = int(failed.sum())
+    cols = [np.where(failed, np.nan, np.asarray(sn, dtype=np.float64)), ssim, np.asarray(z_ssim, dtype=np.float64)]
+    if background:
+        cols += [np.asarray(z_bg, dtype=np.float64), np.asarray(p_bg, dtype=np.float64)]
+    text = [[str(i) for i in ids]] + [_float_column(c) for c in cols]
     with open(output_file, 'w') as o:
         o.write("ID\tSN\tssim\tz_ssim\tz_bg\tp_bg\n" if background else "ID\tSN\tssim\tz_ssim\n")
-        for k, pair_id in enumerate(ids):
-            s = np.float64(ssim[k])
-            # soft failures carry (nan, nan, nan); successful pairs a Python float SN (sim.py:30)
-            row_sn = np.nan if np.isnan(s) else float(sn[k])
-            if np.isnan(s):
-                nan_counter += 1
-            if background:
-                o.write("{}\t{}\t{}\t{}\t{}\t{}\n".format(pair_id, row_sn, s, np.float64(z_ssim[k]),
-                                                        np.float64(z_bg[k]), np.float64(p_bg[k])))
-            else:
-                o.write("{}\t{}\t{}\t{}\n".format(pair_id, row_sn, s, np.float64(z_ssim[k])))
+        if len(ids):
+            o.write("\n".join(map("\t".join, zip(*text))))
+            o.write("\n")
+    clock.mark("write table")
     if nan_counter > 0:
         logger.info("Could not compute similarity for {}/{} region pairs. This can be due to faulty "
                     "coordinates, too small region sizes or too many unmappable bins".format(

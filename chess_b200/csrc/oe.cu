@@ -224,6 +224,59 @@ __global__ void band_scatter_kernel(const int *__restrict__ src, const int *__re
   }
 }
 
+// The same for a band that holds bins [bin_lo, bin_lo + n_range) only (per-GPU placement of a pair-list shard):
+// a contact is written where both of its bins lie in the range, at its position relative to bin_lo.
+__global__ void band_scatter_range_kernel(const int *__restrict__ src, const int *__restrict__ sink,
+                                          const double *__restrict__ value, long long nnz, int W, long long bin_lo,
+                                          long long n_range, double *__restrict__ band) {
+  const long long pitch = 2ll * W - 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long a = (long long)src[i] - bin_lo, b = (long long)sink[i] - bin_lo;
+    const long long dist = b - a;
+    if (a >= 0 && b >= 0 && a < n_range && b < n_range && dist < W && dist > -(long long)W) {
+      const double v = value[i];
+      band[a * pitch + dist + (W - 1)] = v;
+      band[b * pitch - dist + (W - 1)] = v;
+    }
+  }
+}
+
+// Facts about a COO list that decide how it may be used: smallest / largest index, entries with src > sink, and
+// entries that do not come strictly after their predecessor in (src, sink) order (0 = sorted and duplicate-free).
+__global__ void coo_check_kernel(const int *__restrict__ src, const int *__restrict__ sink, long long nnz,
+                                 long long *__restrict__ out /* [4]: min, max, n_noncanonical, n_unordered */) {
+  long long lo = 0x7fffffffffffffffll, hi = -1, nc = 0, un = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int a = src[i], b = sink[i];
+    lo = min(lo, (long long)min(a, b));
+    hi = max(hi, (long long)max(a, b));
+    nc += a > b;
+    if (i > 0) {
+      const int pa = src[i - 1], pb = sink[i - 1];
+      un += (pa > a) || (pa == a && pb >= b);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    nc += __shfl_xor_sync(0xffffffffu, nc, o);
+    un += __shfl_xor_sync(0xffffffffu, un, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(out, lo);
+    atomicMax(out + 1, hi);
+    if (nc) atomicAdd(reinterpret_cast<unsigned long long *>(out + 2), (unsigned long long)nc);
+    if (un) atomicAdd(reinterpret_cast<unsigned long long *>(out + 3), (unsigned long long)un);
+  }
+}
+
+__global__ void coo_check_init_kernel(long long *out) {
+  out[0] = 0x7fffffffffffffffll; out[1] = -1; out[2] = 0; out[3] = 0;
+}
+
 __global__ void gather_kernel(const double *__restrict__ base, long long off, int pitch, int n,
                               double *__restrict__ out) {
   const long long total = (long long)n * n;
@@ -337,6 +390,45 @@ extern "C" int chess_band_build(chess_ctx *ctx, const int32_t *src, const int32_
   ctx->launches += 1;
   if (nnz > 0) {
     band_scatter_kernel<<<grid_for(nnz, 256, ctx->sm_count), 256, 0, stream>>>(src, sink, value, nnz, W, band);
+    ctx->launches += 1;
+  }
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+extern "C" int chess_band_build_range(chess_ctx *ctx, const int32_t *src, const int32_t *sink,
+                                      const double *value, int64_t nnz, int64_t bin_lo, int64_t n_range, int32_t W,
+                                      double fill, double *band, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_range <= 0 || W <= 0 || !band || bin_lo < 0) {
+    ctx->err = "chess_band_build_range: bad arguments";
+    return CHESS_ERR_ARG;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long count = (long long)n_range * (2ll * W - 1);
+  band_fill_kernel<<<grid_for(count / 2 + 1, 256, ctx->sm_count), 256, 0, stream>>>(band, count, fill);
+  ctx->launches += 1;
+  if (nnz > 0) {
+    band_scatter_range_kernel<<<grid_for(nnz, 256, ctx->sm_count), 256, 0, stream>>>(src, sink, value, nnz, W, bin_lo,
+                                                                                     n_range, band);
+    ctx->launches += 1;
+  }
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+extern "C" int chess_coo_check(chess_ctx *ctx, const int32_t *src, const int32_t *sink, int64_t nnz, int64_t *out4,
+                               void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (!out4 || nnz < 0 || (nnz > 0 && (!src || !sink))) { ctx->err = "chess_coo_check: bad arguments"; return CHESS_ERR_ARG; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  coo_check_init_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<long long *>(out4));
+  ctx->launches += 1;
+  if (nnz > 0) {
+    coo_check_kernel<<<grid_for(nnz, 256, ctx->sm_count), 256, 0, stream>>>(src, sink, nnz,
+                                                                            reinterpret_cast<long long *>(out4));
     ctx->launches += 1;
   }
   CHESS_CUDA(ctx, cudaGetLastError());

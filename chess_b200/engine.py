@@ -54,6 +54,34 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+class DeviceTriples(object):
+    """Canonical COO triples that live on a GPU (what the device text parser returns): int32 src / sink and
+    float64 weight tensors on ``device``.  Lets the loaders hand a matrix from the parser to the O/E kernels and
+    on to the contact store without a round trip through host memory."""
+
+    def __init__(self, src, sink, value, device):
+        self.src, self.sink, self.value, self.device = src, sink, value, int(device)
+
+    def __len__(self):
+        return int(self.value.numel())
+
+    def host(self):
+        return (self.src.cpu().numpy().astype(np.int64), self.sink.cpu().numpy().astype(np.int64),
+                self.value.cpu().numpy())
+
+
+def coo_facts(d_src, d_sink, device):
+    """(min index, max index, #src > sink, #not strictly after the predecessor) of a device COO list."""
+    device = int(device)
+    ctx = get_context(device)
+    dev = torch.device("cuda", device)
+    with torch.cuda.device(dev):
+        out = torch.empty(4, dtype=torch.int64, device=dev)
+        check(lib.chess_coo_check(ctx.handle, _ptr(d_src), _ptr(d_sink), int(d_src.numel()), _ptr(out),
+                                  _stream_ptr(dev)), ctx.handle, "chess_coo_check")
+        return [int(v) for v in out.cpu().tolist()]
+
+
 class DeviceContacts(object):
     """The edges store of one sample: COO triples plus the HBM-resident band.
 
@@ -61,43 +89,90 @@ class DeviceContacts(object):
     chess/helpers.py:342-391.  ``store[source][sink]`` still works (host-side
     CSR view) so code written against the dict keeps running; the comparison
     kernels read the band.
+
+    The triples live in host arrays, or (``from_device``) on the GPU that parsed
+    and normalised them -- then the host copy is made only if something asks for
+    it.  Other GPUs receive what they need from there: the whole list, or, for a
+    sorted list, the contiguous slice of the bin range their share of the pair
+    list touches (peer copy), and build the band of that range only.
     """
 
     def __init__(self, src, sink, value, n_bins=None, fill=1.0):
         src = np.ascontiguousarray(src, dtype=np.int64)
         sink = np.ascontiguousarray(sink, dtype=np.int64)
-        self.value = np.ascontiguousarray(value, dtype=np.float64)
+        value = np.ascontiguousarray(value, dtype=np.float64)
         swap = src > sink
         if swap.any():
             src, sink = np.where(swap, sink, src), np.where(swap, src, sink)
         if len(src) and int(src.min()) < 0:
             raise ValueError("negative contact index")
+        self.sorted_unique = True
         if len(src) > 1:
             # a (source, sink) listed more than once: the reference's dict of dicts keeps the LAST occurrence
             # in input order (chess/helpers.py:353-356); keep exactly that one, so that the band scatter has
             # one writer per cell (deterministic, and both mirror cells agree)
             key = src * (int(sink.max()) + 1) + sink
-            if bool(np.all(key[1:] > key[:-1])):      # sorted input (the usual dump order): nothing repeats
-                dup = np.zeros(0, dtype=bool)
-            else:
+            if not bool(np.all(key[1:] > key[:-1])):   # sorted input (the usual dump order): nothing repeats
+                self.sorted_unique = False
                 order = np.argsort(key, kind="stable")
                 ks = key[order]
                 dup = ks[1:] == ks[:-1]
-            if dup.any():
-                last = np.ones(len(ks), dtype=bool)
-                last[:-1] = ~dup
-                keep = np.sort(order[last])
-                src, sink, self.value = src[keep], sink[keep], self.value[keep]
-        self.src, self.sink = src, sink
+                if dup.any():
+                    last = np.ones(len(ks), dtype=bool)
+                    last[:-1] = ~dup
+                    keep = np.sort(order[last])
+                    src, sink, value = src[keep], sink[keep], value[keep]
+        self._host = (src, sink, value)
+        self._home = None
         hi = int(sink.max()) + 1 if len(sink) else 0
         self.n_bins = int(n_bins) if n_bins is not None else hi
         if self.n_bins < hi:
             raise ValueError("contact indices exceed the number of regions")
+        self._init_caches(fill)
+
+    def _init_caches(self, fill):
         self.fill = float(fill)
-        self._bands = {}   # device -> (W, fill, tensor)
-        self._index = {}   # device -> (nd_lo, nd_hi, pmax, pmin) tensors for the current band
-        self._coo = {}     # device -> (src32, sink32, value) tensors
+        self._bands = {}   # device -> (W, fill, bin_lo, bin_hi, tensor)
+        self._index = {}   # device -> (nd_lo, nd_hi, pmax, pmin, rowpre) tensors for the current band
+        self._coo = {}     # device -> (src32, sink32, value) tensors: the whole list
+        self._coo_part = {}  # device -> (bin_lo, bin_hi, (src32, sink32, value)): a slice of a sorted list
         self._csr = None
+
+    @classmethod
+    def from_device(cls, triples, n_bins, fill=1.0):
+        """Store around triples that already live on a GPU (DeviceTriples).  A list that is not sorted and
+        duplicate-free goes through the host constructor (which keeps the last of repeated entries)."""
+        lo, hi, noncanon, unordered = coo_facts(triples.src, triples.sink, triples.device) if len(triples) else (0, -1, 0, 0)
+        if noncanon or unordered:
+            return cls(*triples.host(), n_bins=n_bins, fill=fill)
+        if len(triples) and (lo < 0 or hi >= int(n_bins)):
+            raise ValueError("contact indices exceed the number of regions")
+        self = cls.__new__(cls)
+        self._host = None
+        self._home = triples.device
+        self.sorted_unique = True
+        self.n_bins = int(n_bins)
+        self._init_caches(fill)
+        self._coo[triples.device] = (triples.src, triples.sink, triples.value)
+        return self
+
+    # -- host view of the triples (made on demand when they live on a GPU)
+    def _host_arrays(self):
+        if self._host is None:
+            s, t, v = self._coo[self._home]
+            self._host = (s.cpu().numpy().astype(np.int64), t.cpu().numpy().astype(np.int64), v.cpu().numpy())
+        return self._host
+
+    src = property(lambda self: self._host_arrays()[0])
+    sink = property(lambda self: self._host_arrays()[1])
+    value = property(lambda self: self._host_arrays()[2])
+
+    def __len__(self):
+        starts, _, _ = self._rows()
+        return int(np.count_nonzero(np.diff(starts)))
+
+    def n_contacts(self):
+        return len(self._host[2]) if self._host is not None else int(self._coo[self._home][2].numel())
 
     def ensure_bins(self, n_bins):
         """Make the store cover at least ``n_bins`` bins.  Bins after the last one with a contact
@@ -124,8 +199,9 @@ class DeviceContacts(object):
     # -- dict-like view (compatibility with code indexing the reference's dict)
     def _rows(self):
         if self._csr is None:
-            order = np.lexsort((self.sink, self.src))
-            s, t, w = self.src[order], self.sink[order], self.value[order]
+            src, sink, value = self._host_arrays()
+            order = np.lexsort((sink, src))
+            s, t, w = src[order], sink[order], value[order]
             starts = np.searchsorted(s, np.arange(self.n_bins + 1))
             self._csr = (starts, t, w)
         return self._csr
@@ -141,31 +217,51 @@ class DeviceContacts(object):
         starts, _, _ = self._rows()
         return 0 <= source < self.n_bins and starts[source] != starts[source + 1]
 
-    def __len__(self):
-        starts, _, _ = self._rows()
-        return int(np.count_nonzero(np.diff(starts)))
-
     def triples(self):
-        return self.src, self.sink, self.value
+        return self._host_arrays()
 
     # -- device residency
-    def coo_on(self, device):
+    def coo_on(self, device, bin_range=None):
+        """(src32, sink32, value) tensors on ``device``: the whole list, or -- for a sorted list and a bin range
+        -- the contiguous slice with src in [lo, hi) (all a band of those bins can use).  Comes from the host
+        arrays, or by peer copy from the GPU that holds the list."""
         device = int(device)
-        if device not in self._coo:
-            dev = torch.device("cuda", device)
-            self._coo[device] = (
-                torch.from_numpy(self.src.astype(np.int32)).to(dev),
-                torch.from_numpy(self.sink.astype(np.int32)).to(dev),
-                torch.from_numpy(self.value).to(dev))
+        if device in self._coo:
+            return self._coo[device]
+        dev = torch.device("cuda", device)
+        if bin_range is not None and self.sorted_unique:
+            lo, hi = int(bin_range[0]), int(bin_range[1])
+            have = self._coo_part.get(device)
+            if have is not None and have[0] <= lo and have[1] >= hi:
+                return have[2]
+            if self._host is not None:
+                i0, i1 = np.searchsorted(self._host[0], [lo, hi])
+                part = tuple(torch.from_numpy(np.ascontiguousarray(a[i0:i1], dtype=dt)).to(dev) for a, dt in
+                             zip(self._host, (np.int32, np.int32, np.float64)))
+            else:
+                s, t, v = self._coo[self._home]
+                cut = torch.searchsorted(s, torch.tensor([lo, hi], dtype=s.dtype, device=s.device)).cpu().tolist()
+                part = tuple(a[cut[0]:cut[1]].to(dev, non_blocking=True) for a in (s, t, v))
+            self._coo_part[device] = (lo, hi, part)
+            return part
+        if self._host is not None:
+            self._coo[device] = tuple(torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev) for a, dt in
+                                      zip(self._host, (np.int32, np.int32, np.float64)))
+        else:
+            self._coo[device] = tuple(a.to(dev, non_blocking=True) for a in self._coo[self._home])
         return self._coo[device]
 
-    def band_on(self, device, min_w, fill=None):
-        """The band on ``device`` with half-width >= min_w (rebuilt if too narrow)."""
+    def band_on(self, device, min_w, fill=None, bin_range=None):
+        """(W, band tensor, bin_lo): the band on ``device`` with half-width >= min_w covering ``bin_range``
+        (default: every bin); rebuilt if the one there is too narrow or covers less."""
         device = int(device)
         fill = self.fill if fill is None else float(fill)
+        lo, hi = (0, self.n_bins) if bin_range is None else (max(int(bin_range[0]), 0), min(int(bin_range[1]), self.n_bins))
+        if hi <= lo:
+            lo, hi = 0, max(min(self.n_bins, 1), 1)
         have = self._bands.get(device)
-        if have is not None and have[0] >= min_w and have[1] == fill:
-            return have[0], have[2]
+        if have is not None and have[0] >= min_w and have[1] == fill and have[2] <= lo and have[3] >= hi:
+            return have[0], have[4], have[2]
         W = max(int(min_w), 1)
         W = min(((W + 15) // 16) * 16, max(self.n_bins, 1))
         W = max(W, int(min_w))
@@ -174,62 +270,73 @@ class DeviceContacts(object):
         if have is not None:
             del self._bands[device]
             del have
-        band = torch.empty(self.n_bins * (2 * W - 1), dtype=torch.float64, device=dev)
-        s, t, v = self.coo_on(device)
+        band = torch.empty((hi - lo) * (2 * W - 1), dtype=torch.float64, device=dev)
+        whole = lo == 0 and hi == self.n_bins
+        s, t, v = self.coo_on(device, None if whole else (lo, hi))
         with torch.cuda.device(dev):
-            check(lib.chess_band_build(ctx.handle, _ptr(s), _ptr(t), _ptr(v), len(self.value),
-                                       self.n_bins, W, fill, _ptr(band), _stream_ptr(dev)),
-                  ctx.handle, "chess_band_build")
-        self._bands[device] = (W, fill, band)
+            check(lib.chess_band_build_range(ctx.handle, _ptr(s), _ptr(t), _ptr(v), int(v.numel()), lo, hi - lo, W,
+                                             fill, _ptr(band), _stream_ptr(dev)),
+                  ctx.handle, "chess_band_build_range")
+        self._bands[device] = (W, fill, lo, hi, band)
         self._index.pop(device, None)
-        return W, band
+        return W, band, lo
 
-    def sample_on(self, device, min_w, fill=None):
+    def sample_on(self, device, min_w, fill=None, bin_range=None, with_origin=False):
         """(W, band tensor, chess_sample) on ``device``: the band plus the per-bin index of the
-        nearest non-default entries (built once per band, lets the kernels predict masked bins)."""
+        nearest non-default entries (built once per band, lets the kernels predict masked bins).
+        With ``bin_range`` the band covers those bins only; ``with_origin`` appends the first bin of the
+        band (pair offsets into it count from there)."""
         device = int(device)
-        W, band = self.band_on(device, min_w, fill)
-        fill_v = self._bands[device][1]
+        W, band, bin_lo = self.band_on(device, min_w, fill, bin_range)
+        _, fill_v, lo, hi, _ = self._bands[device]
+        n_local = hi - lo
         have = self._index.get(device)
         if have is None:
             ctx = get_context(device)
             dev = torch.device("cuda", device)
-            nd_lo = torch.empty(self.n_bins, dtype=torch.int32, device=dev)
-            nd_hi = torch.empty(self.n_bins, dtype=torch.int32, device=dev)
+            nd_lo = torch.empty(n_local, dtype=torch.int32, device=dev)
+            nd_hi = torch.empty(n_local, dtype=torch.int32, device=dev)
+            pmax = torch.empty(n_local * W, dtype=torch.float64, device=dev)
+            pmin = torch.empty(n_local * W, dtype=torch.float64, device=dev)
+            rowpre = torch.empty(n_local * 2 * W, dtype=torch.float64, device=dev)
             with torch.cuda.device(dev):
-                check(lib.chess_band_index_build(ctx.handle, _ptr(band), self.n_bins, W, fill_v, _ptr(nd_lo),
-                                                 _ptr(nd_hi), _stream_ptr(dev)), ctx.handle, "chess_band_index_build")
-            pmax = torch.empty(self.n_bins * W, dtype=torch.float64, device=dev)
-            pmin = torch.empty(self.n_bins * W, dtype=torch.float64, device=dev)
-            with torch.cuda.device(dev):
-                check(lib.chess_band_extrema_build(ctx.handle, _ptr(band), self.n_bins, W, _ptr(pmax), _ptr(pmin),
-                                                   _stream_ptr(dev)), ctx.handle, "chess_band_extrema_build")
-            rowpre = torch.empty(self.n_bins * 2 * W, dtype=torch.float64, device=dev)
-            with torch.cuda.device(dev):
-                check(lib.chess_band_prefix_build(ctx.handle, _ptr(band), self.n_bins, W, _ptr(rowpre),
-                                                  _stream_ptr(dev)), ctx.handle, "chess_band_prefix_build")
+                stream = _stream_ptr(dev)
+                check(lib.chess_band_index_build(ctx.handle, _ptr(band), n_local, W, fill_v, _ptr(nd_lo),
+                                                 _ptr(nd_hi), stream), ctx.handle, "chess_band_index_build")
+                check(lib.chess_band_extrema_build(ctx.handle, _ptr(band), n_local, W, _ptr(pmax), _ptr(pmin),
+                                                   stream), ctx.handle, "chess_band_extrema_build")
+                check(lib.chess_band_prefix_build(ctx.handle, _ptr(band), n_local, W, _ptr(rowpre), stream),
+                      ctx.handle, "chess_band_prefix_build")
             have = (nd_lo, nd_hi, pmax, pmin, rowpre)
             self._index[device] = have
         sample = _native.chess_sample(band.data_ptr(), have[0].data_ptr(), have[1].data_ptr(),
-                                      have[2].data_ptr(), have[3].data_ptr(), self.n_bins, W, 0,
+                                      have[2].data_ptr(), have[3].data_ptr(), n_local, W, 0,
                                       have[4].data_ptr())
+        if with_origin:
+            return W, band, sample, bin_lo
+        if bin_lo != 0:
+            raise _native.ChessNativeError("internal error: a partial band was handed to a caller that indexes it "
+                                           "with absolute bins")
         return W, band, sample
 
     def drop_device_copies(self):
+        self._host_arrays()          # the triples must survive somewhere
+        self._home = None
         self._bands.clear()
         self._index.clear()
         self._coo.clear()
+        self._coo_part.clear()
 
     def submatrix(self, start_ix, n, default_weight=None, device=None):
         """Dense n x n numpy tile starting at bin ``start_ix`` (device gather + D2H)."""
         device = visible_devices()[0] if device is None else int(device)
         self.check_span([start_ix], [n])
-        W, band = self.band_on(device, n, default_weight)
+        W, band, bin_lo = self.band_on(device, n, default_weight)
         ctx = get_context(device)
         dev = torch.device("cuda", device)
         out = torch.empty((n, n), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            check(lib.chess_gather_submatrix(ctx.handle, _ptr(band), int(start_ix) * (2 * W - 1) + W - 1,
+            check(lib.chess_gather_submatrix(ctx.handle, _ptr(band), (int(start_ix) - bin_lo) * (2 * W - 1) + W - 1,
                                              2 * W - 2, int(n), _ptr(out), _stream_ptr(dev)),
                   ctx.handle, "chess_gather_submatrix")
         return out.cpu().numpy()
@@ -301,11 +408,32 @@ def region_spans(region_index, regions):
     return first, count
 
 
+def region_spans_columns(region_index, chroms, starts, ends):
+    """region_spans for regions given as columns (chromosome names, 1-based starts, ends): no per-region Python."""
+    import pandas as pd
+    n = len(starts)
+    first = np.full(n, -1, dtype=np.int64)
+    count = np.zeros(n, dtype=np.int64)
+    if n == 0:
+        return first, count
+    starts = np.asarray(starts, dtype=np.int64)
+    ends = np.asarray(ends, dtype=np.int64)
+    codes, names = pd.factorize(np.asarray(chroms, dtype=object), sort=False)
+    for c, chrom in enumerate(names):
+        index = region_index[chrom]          # KeyError for an unknown chromosome, like the reference
+        ks = np.flatnonzero(codes == c)
+        lo, hi = index.span(starts[ks] - 1, ends[ks])
+        ok = lo >= 0
+        first[ks[ok]] = lo[ok]
+        count[ks[ok]] = hi[ok] - lo[ok] + 1
+    return first, count
+
+
 def build_pair_table(ref_first, ref_n, ref_w, qry_first, qry_n, qry_w, flip):
     """chess_pair records for band-resident samples."""
     n = len(ref_first)
     tab = np.zeros(n, dtype=PAIR_DTYPE)
-    tab["ref_off"] = np.where(ref_n > 0, ref_first * (2 * ref_w - 1) + ref_w - 1, 0)
+    tab["ref_off"] = np.where(ref_n > 0, ref_first * (2 * ref_w - 1) + ref_w - 1, 0)   # first = bin - band origin
     tab["qry_off"] = np.where(qry_n > 0, qry_first * (2 * qry_w - 1) + qry_w - 1, 0)
     tab["ref_pitch"] = 2 * ref_w - 2
     tab["qry_pitch"] = 2 * qry_w - 2
@@ -324,7 +452,11 @@ class CompareEngine(object):
     on the host in input order).
     """
 
-    def __init__(self, reference_edges, reference_regions, query_edges, query_regions, devices=None):
+    def __init__(self, reference_edges, reference_regions, query_edges, query_regions, devices=None,
+                 placement="auto"):
+        """``placement``: "auto" = with several GPUs each one holds the band of the bin range its share of the pair
+        list reads, with one GPU the whole band; "range" / "whole" force either (tests, A/B runs)."""
+        self.placement = placement
         self.ref = as_device_contacts(reference_edges, index_bins(reference_regions))
         self.qry = as_device_contacts(query_edges, index_bins(query_regions))
         self.ref_index = reference_regions
@@ -360,6 +492,13 @@ class CompareEngine(object):
         ndev = min(len(self.devices), total)
         bounds = shard_bounds(total, ndev)
         pending = []
+
+        def span_range(first, n):
+            live = n > 0
+            if not live.any():
+                return (0, 1)
+            return int(first[live].min()), int((first[live] + n[live]).max())
+
         for k in range(ndev):
             device = self.devices[k]
             lo, hi = int(bounds[k]), int(bounds[k + 1])
@@ -368,9 +507,14 @@ class CompareEngine(object):
             ctx = get_context(device)
             dev = torch.device("cuda", device)
             with torch.cuda.device(dev):
-                rw, rband, rsample = self.ref.sample_on(device, max_n, default_value)
-                qw, qband, qsample = self.qry.sample_on(device, max_n, default_value)
-                tab = build_pair_table(ref_first[lo:hi], ref_n[lo:hi], rw, qry_first[lo:hi], qry_n[lo:hi], qw,
+                # one GPU: the whole band (later calls reuse it).  Several: every GPU holds the stretch of the
+                # genome its contiguous range of pairs reads (pairs files run chromosome by chromosome)
+                ranged = self.placement == "range" or (self.placement == "auto" and ndev > 1)
+                r_rng = span_range(ref_first[lo:hi], ref_n[lo:hi]) if ranged else None
+                q_rng = span_range(qry_first[lo:hi], qry_n[lo:hi]) if ranged else None
+                rw, rband, rsample, r0 = self.ref.sample_on(device, max_n, default_value, r_rng, with_origin=True)
+                qw, qband, qsample, q0 = self.qry.sample_on(device, max_n, default_value, q_rng, with_origin=True)
+                tab = build_pair_table(ref_first[lo:hi] - r0, ref_n[lo:hi], rw, qry_first[lo:hi] - q0, qry_n[lo:hi], qw,
                                        flip[lo:hi])
                 h_tab = torch.from_numpy(tab.view(np.uint8)).pin_memory()
                 d_tab = h_tab.to(dev, non_blocking=True)
@@ -495,20 +639,29 @@ class CompareEngine(object):
         ValueError -- in the reference skimage raises it and the run aborts
         (chess/sim.py:217-220, bin/chess:220-221).
         """
-        pairs = list(pairs)
-        ids = [p[0] for p in pairs]
+        from .helpers import PairTable
         if params.get("mappability_cutoff", 0.1) <= 0 and not params.get("keep_unmappable_bins", False):
             # np.union1d(*[]) in chess/sim.py:351
             raise TypeError("union1d() missing 2 required positional arguments: 'ar1' and 'ar2'")
-        rf, rn = region_spans(self.ref_index, [p[1] for p in pairs])
-        qf, qn = region_spans(self.qry_index, [p[2] for p in pairs])
+        table = pairs if isinstance(pairs, PairTable) else None
+        if table is not None:           # columns: spans and flips without a Python loop over the pairs
+            ids = table.ids
+            rf, rn = region_spans_columns(self.ref_index, table.ref[0], table.ref[1], table.ref[2])
+            qf, qn = region_spans_columns(self.qry_index, table.qry[0], table.qry[1], table.qry[2])
+        else:
+            pairs = list(pairs)
+            ids = [p[0] for p in pairs]
+            rf, rn = region_spans(self.ref_index, [p[1] for p in pairs])
+            qf, qn = region_spans(self.qry_index, [p[2] for p in pairs])
         big = np.nonzero((rn > MAX_BINS) | (qn > MAX_BINS))[0]
         if len(big):
             k = int(big[0])
             raise ValueError("region pair {} ({} / {}) spans {} bins; the comparison kernels handle at most {} bins "
                              "per region ({} such pair(s) in this run): use smaller regions or a larger bin size"
                              .format(ids[k], pairs[k][1], pairs[k][2], int(max(rn[k], qn[k])), MAX_BINS, len(big)))
-        flip = np.array([1 if p[1].strand != p[2].strand else 0 for p in pairs], dtype=np.int32)
+        flip = table.flips() if table is not None else \
+            np.array([1 if p[1].strand != p[2].strand else 0 for p in pairs], dtype=np.int32)
+        self.last_spans = (rf, rn, qf, qn)      # for callers that go on to the background statistics
         ssim, sn, status = self.compare_spans(rf, rn, qf, qn, flip, default_value=default_value,
                                               compute_sn=compute_sn, **params)
         if (status == _native.PAIR_WINDOW_EXCEEDS).any():

@@ -42,8 +42,8 @@ def log_ratio_stage(reference_edges, reference_regions, query_edges, query_regio
     out = []
     with torch.cuda.device(dev):
         sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        rw, rband = ref.band_on(device, max_n, 0.0)          # default_weight=0. (get_structures.py:99-108)
-        qw, qband = qry.band_on(device, max_n, 0.0)
+        rw, rband, _ = ref.band_on(device, max_n, 0.0)       # default_weight=0. (get_structures.py:99-108)
+        qw, qband, _ = qry.band_on(device, max_n, 0.0)
         table = build_pair_table(rf, rn, rw, qf, qn, qw, np.zeros(len(pairs), dtype=np.int32))
         chunk = max(1, (256 << 20) // (16 * max_n * max_n))  # ~256 MB of tiles per launch
         for lo in range(0, len(pairs), chunk):

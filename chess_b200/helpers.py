@@ -135,6 +135,170 @@ def load_regions(file_name, sep=None, ignore_ix=False):
     return regions, ix_converter, ix2reg
 
 
+class RegionTable(object):
+    """The regions of a BED file as columns (chromosome codes, starts, ends, bin indices) that behave like the
+    list of GenomicRegion objects ``load_regions`` returns: ``len``, indexing and iteration make the objects on
+    demand.  What the batched engine needs -- overlap queries for whole pair lists, the chromosome table of
+    the O/E kernels -- works on the columns, so a 300 000-bin genome costs no Python loop."""
+
+    def __init__(self, chrom_names, chrom_codes, starts, ends, ixs=None):
+        self.chrom_names = list(chrom_names)
+        self.chrom_codes = np.ascontiguousarray(chrom_codes, dtype=np.int32)
+        self.starts = np.ascontiguousarray(starts, dtype=np.int64)
+        self.ends = np.ascontiguousarray(ends, dtype=np.int64)
+        self.ixs = np.arange(len(self.starts), dtype=np.int64) if ixs is None else np.ascontiguousarray(ixs, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.starts)
+
+    def _make(self, k):
+        return GenomicRegion(chromosome=self.chrom_names[int(self.chrom_codes[k])], start=int(self.starts[k]),
+                             end=int(self.ends[k]), ix=int(self.ixs[k]))
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._make(i) for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        return self._make(k)
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self._make(k)
+
+    def max_bin_size(self):
+        """max(r.end - r.start + 1) over the regions (bin/chess:140-143)."""
+        return int((self.ends - self.starts + 1).max()) if len(self) else 0
+
+    def chromosome_ends(self):
+        """{chromosome: largest end}."""
+        out = {}
+        for c, name in enumerate(self.chrom_names):
+            sel = self.chrom_codes == c
+            if sel.any():
+                out[name] = int(self.ends[sel].max())
+        return out
+
+
+class _TableRows(object):
+    """Rows of a RegionTable as a sequence of region objects (made on demand)."""
+
+    def __init__(self, table, rows):
+        self.table, self.rows = table, rows
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, k):
+        return self.table._make(int(self.rows[k]))
+
+
+def load_regions_table(file_name, ignore_ix=False):
+    """``load_regions`` for the batched engine: (RegionTable, ix_converter).  The BED is read by the pandas C
+    parser; a file it cannot take as a plain table (ragged lines, blank lines in the middle, a name column) goes
+    through ``load_regions`` itself, so behaviour and errors are the reference's in every case."""
+    import pandas as pd
+    try:
+        with _open(file_name, "r") as fh:
+            frame = pd.read_csv(fh, sep=r"\s+", header=None, comment=None, skip_blank_lines=False, engine="c",
+                                dtype={0: str}, keep_default_na=False)
+        plain = frame.shape[1] >= 3 and not frame.isnull().any().any() and not (frame.astype(str) == "").any().any()
+        if plain and frame.shape[1] > 3 and not ignore_ix:
+            plain = bool((frame[3].astype(str) == ".").all())
+        if plain:
+            codes, names = pd.factorize(frame[0], sort=False)
+            return RegionTable(list(names), codes, frame[1].to_numpy(dtype=np.int64),
+                               frame[2].to_numpy(dtype=np.int64)), None
+    except Exception:
+        pass
+    regions, ix_converter, _ = load_regions(file_name, ignore_ix=ignore_ix)
+    names, codes = [], []
+    seen = {}
+    for r in regions:
+        if r.chromosome not in seen:
+            seen[r.chromosome] = len(names)
+            names.append(r.chromosome)
+        codes.append(seen[r.chromosome])
+    return RegionTable(names, codes, [r.start for r in regions], [r.end for r in regions],
+                       [r.ix for r in regions]), ix_converter
+
+
+class PairTable(object):
+    """A pair list as columns.  Behaves like the list of (ID, reference_region, query_region) tuples of
+    ``load_pairs_for_chroms`` (len, indexing, iteration make the tuples on demand); the engine reads the columns."""
+
+    def __init__(self, ids, ref_chrom, ref_start, ref_end, ref_strand, qry_chrom, qry_start, qry_end, qry_strand):
+        self.ids = list(ids)
+        self.ref = (np.asarray(ref_chrom, dtype=object), np.asarray(ref_start, dtype=np.int64),
+                    np.asarray(ref_end, dtype=np.int64), np.asarray(ref_strand, dtype=object))
+        self.qry = (np.asarray(qry_chrom, dtype=object), np.asarray(qry_start, dtype=np.int64),
+                    np.asarray(qry_end, dtype=np.int64), np.asarray(qry_strand, dtype=object))
+
+    def __len__(self):
+        return len(self.ids)
+
+    def _make(self, k):
+        r, q = self.ref, self.qry
+        return (self.ids[k],
+                GenomicRegion(chromosome=r[0][k], start=int(r[1][k]), end=int(r[2][k]), strand=r[3][k]),
+                GenomicRegion(chromosome=q[0][k], start=int(q[1][k]), end=int(q[2][k]), strand=q[3][k]))
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            idx = range(*k.indices(len(self)))
+            return PairTable([self.ids[i] for i in idx], *[c[k] for c in self.ref], *[c[k] for c in self.qry])
+        if k < 0:
+            k += len(self)
+        return self._make(int(k))
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self._make(k)
+
+    def flips(self):
+        """1 where the strands of a pair differ (the query is rotated by 180 degrees, chess/sim.py:332-333)."""
+        return (self.ref[3] != self.qry[3]).astype(np.int32)
+
+    def max_spans_bp(self):
+        """(max reference span, max query span) in bp, as bin/chess:160-167 computes them."""
+        return (int((self.ref[2] - self.ref[1] + 1).max()), int((self.qry[2] - self.qry[1] + 1).max()))
+
+
+def load_pairs_table(file_name, chromosomes, sep=None):
+    """``load_pairs_for_chroms`` (chess/helpers.py:483-527) as a PairTable: (pairs, dropped).  Read by the pandas C
+    parser; anything that is not a plain 10-column table (comment lines, ragged lines) goes through
+    ``load_pairs_for_chroms`` itself, so errors and corner cases are the reference's."""
+    import pandas as pd
+    try:
+        with _open(file_name, "r") as fh:
+            text = fh.read()
+        if "#" in text or sep is not None:
+            raise ValueError("not a plain table")
+        frame = pd.read_csv(io.StringIO(text), sep=r"\s+", header=None, engine="c", dtype=str, keep_default_na=False,
+                            skip_blank_lines=False)
+        if frame.shape[1] != 10 or frame.isnull().any().any() or (frame == "").any().any():
+            raise ValueError("not a plain table")
+        ids = frame[6]
+        if ids.duplicated().any():
+            raise ValueError("duplicate")
+        keep = (frame[0].isin(chromosomes) & frame[3].isin(chromosomes)).to_numpy()
+        dropped = int((~keep).sum())
+        f = frame[keep]
+        table = PairTable(f[6].tolist(), f[0].to_numpy(), f[1].to_numpy(dtype=np.int64) + 1, f[2].to_numpy(dtype=np.int64),
+                          f[8].to_numpy(), f[3].to_numpy(), f[4].to_numpy(dtype=np.int64) + 1,
+                          f[5].to_numpy(dtype=np.int64), f[9].to_numpy())
+        return table, dropped
+    except Exception:
+        pass
+    res, dropped = load_pairs_for_chroms(file_name, chromosomes, sep=sep)
+    if not res:
+        return PairTable([], [], [], [], [], [], [], [], []), dropped
+    ids = [p[0] for p in res]
+    cols = lambda side, attr: [getattr(p[side], attr) for p in res]  # noqa: E731
+    return PairTable(ids, cols(1, "chromosome"), cols(1, "start"), cols(1, "end"), cols(1, "strand"),
+                     cols(2, "chromosome"), cols(2, "start"), cols(2, "end"), cols(2, "strand")), dropped
+
+
 class _Hit(object):
     """What iterating an intervaltree slice yields: an object with ``.data``."""
     __slots__ = ("begin", "end", "data")
@@ -153,11 +317,19 @@ class RegionIndex(object):
     is what the batched engine uses instead of one tree query per pair.
     """
 
-    def __init__(self, regions):
-        self.regions = list(regions)
-        begins = np.array([r.start - 1 for r in self.regions], dtype=np.int64)
-        ends = np.array([r.end for r in self.regions], dtype=np.int64)
-        ixs = np.array([r.ix for r in self.regions], dtype=np.int64)
+    def __init__(self, regions, arrays=None):
+        """``regions``: the chromosome's region objects -- or, with ``arrays`` = (starts, ends, ixs), any
+        sequence that yields them on demand (RegionTable rows), so that nothing is materialised up front."""
+        if arrays is not None:
+            self.regions = regions
+            begins = np.asarray(arrays[0], dtype=np.int64) - 1
+            ends = np.asarray(arrays[1], dtype=np.int64)
+            ixs = np.asarray(arrays[2], dtype=np.int64)
+        else:
+            self.regions = list(regions)
+            begins = np.array([r.start - 1 for r in self.regions], dtype=np.int64)
+            ends = np.array([r.end for r in self.regions], dtype=np.int64)
+            ixs = np.array([r.ix for r in self.regions], dtype=np.int64)
         order = np.argsort(begins, kind="stable")
         self.order = order
         self.begins, self.ends, self.ixs = begins[order], ends[order], ixs[order]
@@ -166,7 +338,7 @@ class RegionIndex(object):
                                                 and np.all(np.diff(self.ixs) > 0)))
 
     def __len__(self):
-        return len(self.regions)
+        return len(self.begins)
 
     def __getitem__(self, sl):
         a, b = sl.start, sl.stop
@@ -202,6 +374,17 @@ class RegionIndex(object):
 
 def region_interval_trees(regions):
     """{chromosome: RegionIndex}; chess/helpers.py:209-219."""
+    if isinstance(regions, RegionTable):
+        out = {}
+        codes = regions.chrom_codes
+        order = np.argsort(codes, kind="stable")
+        cuts = np.searchsorted(codes[order], np.arange(len(regions.chrom_names) + 1))
+        for c, name in enumerate(regions.chrom_names):
+            rows = order[cuts[c]:cuts[c + 1]]
+            if len(rows):
+                out[name] = RegionIndex(_TableRows(regions, rows), (regions.starts[rows], regions.ends[rows],
+                                                                    regions.ixs[rows]))
+        return out
     per_chrom = defaultdict(list)
     for region in regions:
         per_chrom[region.chromosome].append(region)
@@ -269,19 +452,23 @@ def _cuda_visible():
     return torch.cuda.is_available()
 
 
-def _parse_sparse(file_name, ix_converter=None, sep="\t"):
+def _parse_sparse(file_name, ix_converter=None, sep="\t", want_device=False, device=None):
     """(src, sink, weight) arrays, canonical and finite; the array form of
-    edges_from_sparse_matrix (chess/helpers.py:309-339)."""
+    edges_from_sparse_matrix (chess/helpers.py:309-339).  ``want_device``: when the text was parsed on a GPU,
+    return the triples where they are (engine.DeviceTriples) instead of copying them to host arrays."""
     if ix_converter is None and sep == "\t" and _cuda_visible():
         # index-addressed matrix: the text is parsed on the GPU (csrc/ingest.cu); None = this file
         # needs the host parser below (lone carriage returns / mostly unusual number spellings)
         from .ingest import parse_sparse_text
-        parsed = parse_sparse_text(os.path.expanduser(file_name))
+        parsed = parse_sparse_text(os.path.expanduser(file_name), device=device, return_device=want_device)
         if parsed is not None:
             lo, hi, w, total, n_bad = parsed
             if total and n_bad / total > 0.05:
                 logger.warning("Could not import more than 5% of matrix entries ({}/{}), "
                                "as they were not finite".format(n_bad, total))
+            if want_device:
+                from .engine import DeviceTriples, visible_devices
+                return DeviceTriples(lo, hi, w, visible_devices()[0] if device is None else device)
             return lo, hi, w
     import pandas as pd
     with _open(file_name, "r") as fh:
@@ -334,7 +521,11 @@ def edges_dict_from_sparse(edges, n_bins=None):
     the reference signature) = number of regions the matrix goes with: bins after
     the last contact exist and read as the default value.
     """
-    from .engine import DeviceContacts
+    from .engine import DeviceContacts, DeviceTriples
+    if isinstance(edges, DeviceTriples):
+        if n_bins is None:
+            return DeviceContacts(*edges.host())
+        return DeviceContacts.from_device(edges, n_bins=n_bins)
     if isinstance(edges, tuple) and len(edges) == 3 and isinstance(edges[0], np.ndarray):
         return DeviceContacts(*edges, n_bins=n_bins)
     triples = list(edges)
@@ -454,11 +645,14 @@ def _try_fanc(matrix_file):
     return fanc.load(matrix_file)
 
 
-def load_contacts(matrix_file, regions_file=None):
+def load_contacts(matrix_file, regions_file=None, device=None):
     """Balanced contacts -> (O/E edges store, region index, regions).
 
     chess/helpers.py:548-573.  Sparse-format input is normalised on the device
     (``oe.observed_expected_arrays``); fanc-readable files use fanc's own O/E.
+    ``device`` (not in the reference): the GPU that parses and normalises.  The text
+    goes to that GPU once; parsed triples, expected values and O/E values never
+    leave it, and the regions come back as a RegionTable (columns, objects on demand).
     """
     from .oe import observed_expected_arrays
     try:
@@ -471,16 +665,16 @@ def load_contacts(matrix_file, regions_file=None):
         try:
             assert regions_file is not None, ("Regions file needs to be"
                                               "specified for sparse input.")
-            regions, ix_converter, _ = load_regions(regions_file)
+            regions, ix_converter = load_regions_table(regions_file)
             region_trees = region_interval_trees(regions)
-            triples = _parse_sparse(matrix_file, ix_converter)
-            edges = observed_expected_arrays(regions, triples)
+            triples = _parse_sparse(matrix_file, ix_converter, want_device=True, device=device)
+            edges = observed_expected_arrays(regions, triples, device=device)
         except AssertionError as error:
             raise ValueError(error)
     return edges, region_trees, regions
 
 
-def load_oe_contacts(matrix_file, regions_file=None):
+def load_oe_contacts(matrix_file, regions_file=None, device=None):
     """Already O/E-transformed contacts; chess/helpers.py:576-598."""
     try:
         loaded = _try_fanc(matrix_file)
@@ -490,9 +684,10 @@ def load_oe_contacts(matrix_file, regions_file=None):
     except ValueError:
         try:
             assert regions_file is not None
-            regions, ix_converter, _ = load_regions(regions_file)
+            regions, ix_converter = load_regions_table(regions_file)
             region_trees = region_interval_trees(regions)
-            edges = edges_dict_from_sparse(_parse_sparse(matrix_file, ix_converter), n_bins=len(regions))
+            edges = edges_dict_from_sparse(_parse_sparse(matrix_file, ix_converter, want_device=True, device=device),
+                                           n_bins=len(regions))
         except AssertionError:
             raise ValueError
     return edges, region_trees, regions

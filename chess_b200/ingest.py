@@ -30,6 +30,41 @@ def read_bytes(file_name):
     return np.fromfile(file_name, dtype=np.uint8)
 
 
+_STAGE = {}
+
+
+def read_to_device(file_name, device):
+    """The bytes of a (plain) file as a uint8 tensor on ``device``: read in 32 MB pieces into two pinned staging
+    buffers, each piece copied to the GPU while the next one is being read."""
+    import os
+    import torch
+    dev = torch.device("cuda", int(device))
+    size = os.path.getsize(file_name)
+    text = torch.empty(size, dtype=torch.uint8, device=dev)
+    chunk = 32 << 20
+    key = int(device)
+    if key not in _STAGE:
+        _STAGE[key] = ([torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                       [torch.cuda.Event() for _ in range(2)])
+    bufs, events = _STAGE[key]
+    views = [b.numpy() for b in bufs]
+    with torch.cuda.device(dev), open(file_name, "rb", buffering=0) as fh:
+        off, k = 0, 0
+        while off < size:
+            slot = k & 1
+            if k >= 2:
+                events[slot].synchronize()        # the copy that last used this buffer is done
+            got = fh.readinto(memoryview(views[slot])[:min(chunk, size - off)])
+            if not got:
+                break
+            text[off:off + got].copy_(bufs[slot][:got], non_blocking=True)
+            events[slot].record()
+            off += got
+            k += 1
+        torch.cuda.current_stream(dev).synchronize()
+    return text[:off] if off != size else text
+
+
 def _host_line(raw):
     """One line exactly as the reference parses it (helpers.py:313-335) -> (kind, src, sink, weight)."""
     line = raw.decode("utf-8")
@@ -63,21 +98,29 @@ def parse_sparse_text(data, device=None, return_device=False):
     from ._native import lib, check
     from .engine import get_context, visible_devices
 
+    device = visible_devices()[0] if device is None else int(device)
+    text = None
     if isinstance(data, str):
-        data = read_bytes(data)
+        with open(data, "rb") as fh:
+            gz = fh.read(2) == b"\x1f\x8b"
+        if gz:
+            data = read_bytes(data)
+        else:
+            text = read_to_device(data, device)       # straight to the GPU; lines come back only if needed
+            data = None
     elif isinstance(data, (bytes, bytearray)):
         data = np.frombuffer(bytearray(data), dtype=np.uint8)
-    device = visible_devices()[0] if device is None else int(device)
     ctx = get_context(device)
     dev = torch.device("cuda", device)
-    n_bytes = int(data.size)
+    n_bytes = int(data.size) if data is not None else int(text.numel())
     empty = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64), 0, 0)
     if n_bytes == 0:
         return empty
     ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     with torch.cuda.device(dev):
         sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        text = torch.from_numpy(np.ascontiguousarray(data)).to(dev)
+        if text is None:
+            text = torch.from_numpy(np.ascontiguousarray(data)).to(dev)
         n_lines, n_cr = C.c_int64(0), C.c_int64(0)
         check(lib.chess_sparse_text_lines(ctx.handle, ptr(text), n_bytes, C.byref(n_lines), C.byref(n_cr), sp),
               ctx.handle, "chess_sparse_text_lines")
@@ -107,7 +150,10 @@ def parse_sparse_text(data, device=None, return_device=False):
             lines = torch.sort(fb_lines[:n_fb]).values
             begin = line_start[lines].cpu().numpy()
             end = (line_start[lines + 1] - 1).cpu().numpy()
-            patch = [_host_line(data[b:e].tobytes()) for b, e in zip(begin, end)]
+            if data is not None:
+                patch = [_host_line(data[b:e].tobytes()) for b, e in zip(begin, end)]
+            else:
+                patch = [_host_line(text[int(b):int(e)].cpu().numpy().tobytes()) for b, e in zip(begin, end)]
             kind[lines] = torch.tensor([p[0] for p in patch], dtype=torch.uint8, device=dev)
             src[lines] = torch.tensor([p[1] for p in patch], dtype=torch.int32, device=dev)
             sink[lines] = torch.tensor([p[2] for p in patch], dtype=torch.int32, device=dev)

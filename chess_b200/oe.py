@@ -13,7 +13,7 @@ import torch
 
 from . import _native
 from ._native import lib, check
-from .engine import DeviceContacts, get_context, visible_devices, _ptr, _stream_ptr
+from .engine import DeviceContacts, DeviceTriples, coo_facts, get_context, visible_devices, _ptr, _stream_ptr
 from .helpers import load_regions, _parse_sparse, string_types
 
 
@@ -33,6 +33,19 @@ class _Layout(object):
 
     def __init__(self, regions):
         self.n_bins = len(regions)
+        table = getattr(regions, "chrom_codes", None)
+        if table is not None:          # helpers.RegionTable: columns instead of 300 000 objects
+            codes = np.asarray(regions.chrom_codes)
+            change = np.flatnonzero(np.diff(codes)) + 1 if len(codes) else np.zeros(0, dtype=np.int64)
+            firsts = np.concatenate([[0], change]).astype(np.int64) if len(codes) else np.zeros(0, dtype=np.int64)
+            run_codes = codes[firsts] if len(codes) else codes
+            if len(set(run_codes.tolist())) != len(run_codes):
+                name = regions.chrom_names[int(run_codes[np.argmax(np.bincount(run_codes))])]
+                raise ValueError("regions of chromosome {} are not contiguous".format(name))
+            self.names = [regions.chrom_names[int(c)] for c in run_codes]
+            self.chrom_start = np.concatenate([firsts, [self.n_bins]]).astype(np.int64)
+            self.bin_chrom = np.repeat(np.arange(len(firsts), dtype=np.int32), np.diff(self.chrom_start))
+            return
         self.names = []
         starts = []
         bin_chrom = np.empty(self.n_bins, dtype=np.int32)
@@ -70,27 +83,38 @@ def _as_triples(sparse_matrix):
     return a, b, w
 
 
-def _device_expected(regions, triples, device=None, want_oe=False, apply_log2=False):
-    """Run K1 (and optionally the O/E division of K2) on one GPU."""
-    device = visible_devices()[0] if device is None else int(device)
+def _device_expected(regions, triples, device=None, want_oe=False, apply_log2=False, keep_oe_on_device=False):
+    """Run K1 (and optionally the O/E division of K2) on one GPU.  ``triples``: host arrays (a, b, w) or a
+    DeviceTriples (then nothing is uploaded, and with ``keep_oe_on_device`` the O/E values stay there too)."""
     layout = _Layout(regions)
-    a, b, w = triples
+    n = layout.n_bins
+    if n >= 2 ** 31:
+        raise ValueError("more than 2^31 - 1 regions are not supported")
+    on_device = isinstance(triples, DeviceTriples)
+    if on_device:
+        device = triples.device
+        nnz = len(triples)
+        lo, hi, _, _ = coo_facts(triples.src, triples.sink, device) if nnz else (0, -1, 0, 0)
+    else:
+        device = visible_devices()[0] if device is None else int(device)
+        a, b, w = triples
+        nnz = len(w)
+        lo, hi = (int(min(a.min(), b.min())), int(max(a.max(), b.max()))) if nnz else (0, -1)
     # the kernels index marginals, chromosome table and expected values with these: a matrix that does not
     # go with the regions file must fail here, as it does in the reference (marginals[source], oe.py:107)
-    if layout.n_bins >= 2 ** 31:
-        raise ValueError("more than 2^31 - 1 regions are not supported")
-    if len(a) and (int(min(a.min(), b.min())) < 0 or int(max(a.max(), b.max())) >= layout.n_bins):
+    if nnz and (lo < 0 or hi >= n):
         raise IndexError("matrix index {} is out of bounds for {} regions: the sparse matrix does not match "
-                         "the regions file".format(int(max(a.max(), b.max())) if int(min(a.min(), b.min())) >= 0
-                                                   else int(min(a.min(), b.min())), layout.n_bins))
+                         "the regions file".format(hi if lo >= 0 else lo, n))
     ctx = get_context(device)
     dev = torch.device("cuda", device)
-    n = layout.n_bins
     with torch.cuda.device(dev):
         stream = _stream_ptr(dev)
-        d_a = torch.from_numpy(a.astype(np.int32)).to(dev)
-        d_b = torch.from_numpy(b.astype(np.int32)).to(dev)
-        d_w = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
+        if on_device:
+            d_a, d_b, d_w = triples.src, triples.sink, triples.value
+        else:
+            d_a = torch.from_numpy(a.astype(np.int32)).to(dev)
+            d_b = torch.from_numpy(b.astype(np.int32)).to(dev)
+            d_w = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
         d_chrom = torch.from_numpy(layout.bin_chrom).to(dev)
         d_start = torch.from_numpy(layout.chrom_start).to(dev)
         d_exp = torch.empty(n, dtype=torch.float64, device=dev)
@@ -100,19 +124,24 @@ def _device_expected(regions, triples, device=None, want_oe=False, apply_log2=Fa
         d_poss = torch.empty(n, dtype=torch.int64, device=dev)
         ws_bytes = int(lib.chess_expected_workspace_bytes(n))
         d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.chess_expected_from_coo(ctx.handle, _ptr(d_a), _ptr(d_b), _ptr(d_w), len(w), _ptr(d_chrom),
+        check(lib.chess_expected_from_coo(ctx.handle, _ptr(d_a), _ptr(d_b), _ptr(d_w), nnz, _ptr(d_chrom),
                                           _ptr(d_start), len(layout.names), n, _ptr(d_exp), _ptr(d_inter),
                                           _ptr(d_map), _ptr(d_poss), _ptr(d_sum), _ptr(d_ws), ws_bytes, stream),
               ctx.handle, "chess_expected_from_coo")
-        out = {"layout": layout, "expected": d_exp.cpu().numpy(), "inter": float(d_inter.cpu()[0]),
-               "mappable": d_map.cpu().numpy().astype(bool), "possible": d_poss.cpu().numpy(),
-               "diag_sum": d_sum.cpu().numpy()}
+        out = {"layout": layout, "device": device}
+        if not keep_oe_on_device:
+            out.update(expected=d_exp.cpu().numpy(), inter=float(d_inter.cpu()[0]),
+                       mappable=d_map.cpu().numpy().astype(bool), possible=d_poss.cpu().numpy(),
+                       diag_sum=d_sum.cpu().numpy())
         if want_oe:
-            d_oe = torch.empty(len(w), dtype=torch.float64, device=dev)
-            check(lib.chess_oe_values(ctx.handle, _ptr(d_a), _ptr(d_b), _ptr(d_w), len(w), _ptr(d_chrom),
+            d_oe = torch.empty(nnz, dtype=torch.float64, device=dev)
+            check(lib.chess_oe_values(ctx.handle, _ptr(d_a), _ptr(d_b), _ptr(d_w), nnz, _ptr(d_chrom),
                                       _ptr(d_start), _ptr(d_exp), _ptr(d_inter), 1 if apply_log2 else 0,
                                       _ptr(d_oe), stream), ctx.handle, "chess_oe_values")
-            out["oe"] = d_oe.cpu().numpy()
+            if keep_oe_on_device:
+                out["oe_triples"] = DeviceTriples(d_a, d_b, d_oe, device)
+            else:
+                out["oe"] = d_oe.cpu().numpy()
     return out
 
 
@@ -190,7 +219,11 @@ def _oe_generator(sparse_matrix, ix_to_chromosome, intra_expected, inter_expecte
 
 
 def observed_expected_arrays(regions, triples, apply_log2=False, device=None):
-    """O/E of canonical COO arrays -> DeviceContacts (array form used by the CLI)."""
+    """O/E of canonical COO triples -> DeviceContacts (array form used by the CLI).  Triples that already
+    live on a GPU (DeviceTriples, from the device text parser) are normalised there and stay there."""
+    if isinstance(triples, DeviceTriples):
+        res = _device_expected(regions, triples, want_oe=True, apply_log2=apply_log2, keep_oe_on_device=True)
+        return DeviceContacts.from_device(res["oe_triples"], n_bins=len(regions))
     a, b, w = _as_triples(triples)
     res = _device_expected(regions, (a, b, w), device=device, want_oe=True, apply_log2=apply_log2)
     return DeviceContacts(a, b, res["oe"], n_bins=len(regions))

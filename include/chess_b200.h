@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CHESS_B200_ABI_VERSION 3
+#define CHESS_B200_ABI_VERSION 4
 
 typedef struct chess_ctx chess_ctx;
 
@@ -157,6 +157,20 @@ int chess_oe_values(chess_ctx *ctx, const int32_t *src, const int32_t *sink, con
 int chess_band_build(chess_ctx *ctx, const int32_t *src, const int32_t *sink, const double *value,
                      int64_t nnz, int64_t n_bins, int32_t W, double fill, double *band,
                      void *stream);
+/* The same for bins [bin_lo, bin_lo + n_range) only (ABI 4): the band of the stretch of the genome one GPU's
+ * share of the pair list touches (the reference forks the whole dict into every worker, bin/chess:196-208;
+ * here a GPU holds what its contiguous range of pairs reads).  band holds n_range*(2W-1) doubles, row 0 = bin
+ * bin_lo; triples with a bin outside the range are skipped.  Pair offsets into it use first_bin - bin_lo.      */
+int chess_band_build_range(chess_ctx *ctx, const int32_t *src, const int32_t *sink, const double *value,
+                           int64_t nnz, int64_t bin_lo, int64_t n_range, int32_t W, double fill, double *band,
+                           void *stream);
+/* Facts about a device-resident COO list (ABI 4): out4 (DEVICE, 4 x int64) = smallest index, largest index,
+ * number of triples with src > sink, number of triples that do not come strictly after their predecessor in
+ * (src, sink) order.  0 in the last slot = sorted and free of duplicates, so that "a later line overwrites an
+ * earlier one" (edges_d[source][sink] = weight, chess/helpers.py:353-356) has nothing to decide and contiguous
+ * bin ranges are contiguous slices.                                                                           */
+int chess_coo_check(chess_ctx *ctx, const int32_t *src, const int32_t *sink, int64_t nnz, int64_t *out4,
+                    void *stream);
 
 /* Dense copy of one submatrix view, out[r*n + c] = base[off + r*pitch + c]:
  * the return value of sub_matrix_from_edges_dict, chess/helpers.py:286-306.   */

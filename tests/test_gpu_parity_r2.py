@@ -326,3 +326,42 @@ def test_full_size_hg38_properties(cb):
     assert np.all(np.abs(s[ok] - 1.0) < 1e-12) and np.all(np.isnan(sn[ok]))
     re_.drop_device_copies()
     qe.drop_device_copies()
+
+
+def test_ranged_bands_and_device_resident_triples(cb, hg38_like, tmp_path):
+    """Per-GPU placement: a GPU holds the band of the bin range its share of the pair list reads
+    (chess_band_build_range), fed by a slice of the sorted COO list; triples that were parsed on the GPU are
+    normalised and kept there (DeviceTriples -> DeviceContacts.from_device).  Same bytes as the whole band."""
+    import torch
+    from chess_b200 import synth
+    from chess_b200.engine import DeviceTriples, DeviceContacts, coo_facts
+    from chess_b200.helpers import load_contacts
+    genome, regions, trees, re_, qe, qe2, pairs = hg38_like
+    whole = cb.CompareEngine(re_, trees, qe2, trees, devices=[0]).compare(pairs, absolute_window_size=7)
+    # three shards on one GPU, each with the band of its own bin range
+    for devs in ([0, 0, 0], [0] * 7):
+        part = cb.CompareEngine(re_, trees, qe2, trees, devices=devs, placement="range").compare(
+            pairs, absolute_window_size=7)
+        assert part[1].tobytes() == whole[1].tobytes() and part[2].tobytes() == whole[2].tobytes()
+        assert np.array_equal(part[3], whole[3])
+    # the same samples through files: parsed on the device, O/E on the device, never on the host
+    files = synth.write_dataset(str(tmp_path), genome, synth.synthetic_sample(genome, 215, seed=11, structure_seed=7),
+                                synth.synthetic_sample(genome, 215, seed=13, structure_seed=9, perturb=0.1), pairs)
+    r_edges, r_trees, r_regions = load_contacts(files["reference"], files["regions"], device=0)
+    q_edges, q_trees, q_regions = load_contacts(files["query"], files["regions"], device=0)
+    assert r_edges._host is None and r_edges._home == 0 and r_edges.sorted_unique      # still only on the GPU
+    assert len(r_regions) == genome.n_bins and r_regions[7].ix == 7
+    for devs, placement in (([0], "auto"), ([0, 0, 0], "range")):
+        got = cb.CompareEngine(r_edges, r_trees, q_edges, q_trees, devices=devs, placement=placement).compare(
+            pairs, absolute_window_size=7)
+        # %.17g text round-trips every weight, so the file path gives the very same numbers
+        assert got[1].tobytes() == whole[1].tobytes() and got[2].tobytes() == whole[2].tobytes()
+    assert np.array_equal(r_edges.triples()[2], re_.triples()[2])      # host view on demand
+    # an unsorted / repeated list on the device goes through the host constructor (last entry wins)
+    dev = torch.device("cuda", 0)
+    t = DeviceTriples(torch.tensor([3, 0, 3, 1], dtype=torch.int32, device=dev),
+                      torch.tensor([4, 1, 4, 1], dtype=torch.int32, device=dev),
+                      torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64, device=dev), 0)
+    assert coo_facts(t.src, t.sink, 0) == [0, 4, 0, 2]
+    dc = DeviceContacts.from_device(t, n_bins=6)
+    assert dc[3] == {4: 3.0} and dc[0] == {1: 2.0} and dc[1] == {1: 4.0} and dc.n_bins == 6

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     from chess_b200 import _native
-    assert lib.chess_abi_version() == _native.ABI_VERSION == 3
+    assert lib.chess_abi_version() == _native.ABI_VERSION == 4
     assert ctypes.sizeof(_native.chess_pair) == 40 and ctypes.sizeof(_native.chess_params) == 56
 
 
@@ -203,3 +203,70 @@ def test_oversized_and_mismatched_inputs_fail_with_a_clear_message():
             oe._device_expected(regions, (np.array([-1]), np.array([1]), np.array([1.0])))
     finally:
         oemod.visible_devices = orig
+
+
+def test_region_and_pair_tables_match_the_object_loaders(toy, tmp_path):
+    """The columnar loaders of the batched engine (RegionTable, PairTable) against the reference-style loaders:
+    same regions, indices, pairs, dropped counts and errors -- including files the fast path must hand over."""
+    from chess_b200 import helpers as H
+    for bed in ("ref.bed", "qry.bed", "named.bed", "background.bed"):
+        table, conv = H.load_regions_table(toy(bed))
+        regions, conv0, _ = H.load_regions(toy(bed))
+        assert conv == conv0 and len(table) == len(regions)
+        assert all(a.__dict__ == b.__dict__ for a, b in zip(table, regions))
+        assert table.max_bin_size() == max(r.end - r.start + 1 for r in regions)
+        trees, trees0 = H.region_interval_trees(table), H.region_interval_trees(regions)
+        assert set(trees) == set(trees0)
+        for chrom in trees:
+            assert np.array_equal(trees[chrom].begins, trees0[chrom].begins)
+            assert np.array_equal(trees[chrom].ixs, trees0[chrom].ixs)
+            hits = sorted(h.data.ix for h in trees[chrom][5000:12000])
+            assert hits == sorted(h.data.ix for h in trees0[chrom][5000:12000])
+    # a BED with a blank line in the middle: the bin index is the LINE number (helpers.py:176-201)
+    odd = tmp_path / "odd.bed"
+    odd.write_text("c\t0\t10\nc\t10\t20\n\nc\t20\t30\n")
+    table, _ = H.load_regions_table(str(odd))
+    regions, _, _ = H.load_regions(str(odd))
+    assert [r.ix for r in table] == [r.ix for r in regions] == [0, 1, 3]
+    trees = H.region_interval_trees(H.load_regions_table(toy("ref.bed"))[0])
+    chroms = set(trees)
+    pt, dropped = H.load_pairs_table(toy("pairs.bedpe"), chroms)
+    pl, dropped0 = H.load_pairs_for_chroms(toy("pairs.bedpe"), chroms)
+    assert dropped == dropped0 and len(pt) == len(pl)
+    for a, b in zip(pt, pl):
+        assert a[0] == b[0] and str(a[1]) == str(b[1]) and str(a[2]) == str(b[2])
+    assert pt.flips().tolist() == [1 if p[1].strand != p[2].strand else 0 for p in pl]
+    assert pt.max_spans_bp() == (max(p[1].end - p[1].start + 1 for p in pl), max(p[2].end - p[2].start + 1 for p in pl))
+    assert [p[0] for p in pt[3:7]] == [p[0] for p in pl[3:7]]
+    # comment lines, duplicate IDs and ragged lines: the reference loader decides
+    text = open(toy("pairs.bedpe")).read()
+    (tmp_path / "c.bedpe").write_text("# comment\n" + text)
+    assert len(H.load_pairs_table(str(tmp_path / "c.bedpe"), chroms)[0]) == len(pl)
+    (tmp_path / "d.bedpe").write_text(text + text.splitlines()[0] + "\n")
+    with pytest.raises(ValueError, match="not unique"):
+        H.load_pairs_table(str(tmp_path / "d.bedpe"), chroms)
+    (tmp_path / "r.bedpe").write_text(text + "chrA\t1\t2\n")
+    with pytest.raises(ValueError, match="10 columns expected"):
+        H.load_pairs_table(str(tmp_path / "r.bedpe"), chroms)
+
+
+def test_background_spans_and_table_text_match_the_loops(toy):
+    """Vectorised pieces of cli.run_sim against the loops they replace: background regions generated from the
+    query bins (bin/chess:272-298) and the number formatting of the output table."""
+    from chess_b200 import cli, helpers as H
+    from chess_b200.engine import region_spans
+    table, _ = H.load_regions_table(toy("qry.bed"))
+    regions, _, _ = H.load_regions(toy("qry.bed"))
+    trees = H.region_interval_trees(table)
+    for q, limit in ((H.GenomicRegion(chromosome="chrA", start=4001, end=28000, strand="+"), True),
+                     (H.GenomicRegion(chromosome="chrB", start=1, end=20000, strand="-"), False),
+                     (H.GenomicRegion(chromosome="chrQ", start=1, end=20000), True)):
+        regs = cli._background_regions_from_query(regions, q, limit)
+        bf0, bn0 = region_spans(H.region_interval_trees(regions), regs) if regs else (np.zeros(0), np.zeros(0))
+        bs0 = [0 if r.strand == '+' else 1 for r in regs]
+        bf, bn, bs = cli._background_spans_from_query(table, trees, q, limit)
+        assert np.array_equal(bf, bf0) and np.array_equal(bn, bn0) and bs.tolist() == bs0
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.normal(0, 1, 2000) * 10.0 ** rng.integers(-20, 20, 2000),
+                           [np.nan, 0.0, -0.0, 1.0, 1e16, 1e-5, 123456789.125, np.inf, -np.inf, 5e-324, 1.7976931348623157e308]])
+    assert cli._float_column(vals) == ["{}".format(np.float64(v)) for v in vals]

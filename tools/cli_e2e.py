@@ -1,12 +1,14 @@
-"""Wall-clock of the whole `chess sim` command on synthetic chr2 @ 25 kb files (development tool).
+"""Wall clock of the whole `chess sim` command on synthetic input FILES, with the time of every stage.
 
-    python tools/cli_e2e.py [--background]
+    python tools/cli_e2e.py [--workload chr2_25kb|hg38_10kb] [--window 7] [--background] [--runs 2] [--devices 0,1,..]
 
-Writes ref/qry sparse matrices, the region BED and the pair BEDPE to a temp dir, runs the CLI in-process and
-prints the time of each stage (from the log timestamps) and the total.
+Writes the reference / query sparse matrices, the region BED and the pair BEDPE of the bench workload to a
+temp dir (in parallel: the hg38 matrices are 47 M lines each), runs the CLI in-process `--runs` times and prints,
+per run, the stage table that cli.run_sim records (cli.LAST_STAGES) and the total.  One JSON line at the end.
 """
 import argparse
-import logging
+import json
+import multiprocessing as mp
 import os
 import sys
 import tempfile
@@ -17,36 +19,65 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def _write_part(args):
+    path, a, b, w = args
+    import pyarrow as pa
+    import pyarrow.csv as pc
+    pc.write_csv(pa.table({"a": a, "b": b, "w": w}), path,
+                 write_options=pc.WriteOptions(include_header=False, delimiter="\t"))
+    return path
+
+
+def write_sparse_parallel(path, sample, pool, parts):
+    a, b, w = sample
+    cuts = np.linspace(0, len(w), parts + 1).astype(np.int64)
+    names = pool.map(_write_part, [(path + ".part%d" % k, a[cuts[k]:cuts[k + 1]], b[cuts[k]:cuts[k + 1]],
+                                    w[cuts[k]:cuts[k + 1]]) for k in range(parts)])
+    with open(path, "wb") as out:
+        for name in names:
+            with open(name, "rb") as fh:
+                while True:
+                    buf = fh.read(64 << 20)
+                    if not buf:
+                        break
+                    out.write(buf)
+            os.remove(name)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="chr2_25kb", choices=["chr2_25kb", "hg38_10kb"])
     ap.add_argument("--background", action="store_true")
     ap.add_argument("--window", default=None)
+    ap.add_argument("--runs", type=int, default=2)
+    ap.add_argument("--devices", default=None, help="comma-separated GPU indices (default: all visible)")
+    ap.add_argument("--keep", default=None, help="directory to write the input files to (kept)")
     args = ap.parse_args()
+    if args.devices:
+        os.environ["CHESS_B200_DEVICES"] = args.devices
     import bench
-    from chess_b200.cli import Chess
-    genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(["--workload", "chr2_25kb"])))
-    tmp = tempfile.mkdtemp()
     t0 = time.perf_counter()
-    regions = genome.regions()
-    with open(os.path.join(tmp, "regions.bed"), "w") as fh:
-        for r in regions:
-            fh.write("%s\t%d\t%d\n" % (r.chromosome, r.start, r.end))
-    for name, s in (("ref", ref), ("qry", qry)):
-        with open(os.path.join(tmp, name + ".sparse"), "w") as fh:
-            fh.write("".join("%d\t%d\t%r\n" % t for t in zip(s[0].tolist(), s[1].tolist(), s[2].tolist())))
+    genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(["--workload", args.workload])))
+    t_gen = time.perf_counter() - t0
+    tmp = args.keep or tempfile.mkdtemp()
+    os.makedirs(tmp, exist_ok=True)
+    t0 = time.perf_counter()
+    genome.write_bed(os.path.join(tmp, "regions.bed"))
+    cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(min(cores, 16)) as pool:
+        for name, s in (("ref", ref), ("qry", qry)):
+            write_sparse_parallel(os.path.join(tmp, name + ".sparse"), s, pool, min(cores, 16))
     with open(os.path.join(tmp, "pairs.bedpe"), "w") as fh:
-        for pid, a, b in pairs:
-            fh.write("%s\t%d\t%d\t%s\t%d\t%d\t%s\t.\t%s\t%s\n" % (a.chromosome, a.start - 1, a.end, b.chromosome,
-                                                                  b.start - 1, b.end, pid, a.strand, b.strand))
-    print("wrote inputs in %.1f s: %d contacts per sample, %d pairs" % (time.perf_counter() - t0, len(ref[2]),
-                                                                        len(pairs)))
-    stamps = []
+        fh.write("".join("%s\t%d\t%d\t%s\t%d\t%d\t%s\t.\t%s\t%s\n" % (a.chromosome, a.start - 1, a.end, b.chromosome,
+                                                                      b.start - 1, b.end, pid, a.strand, b.strand)
+                         for pid, a, b in pairs))
+    sizes = {f: os.path.getsize(os.path.join(tmp, f)) for f in ("ref.sparse", "qry.sparse", "regions.bed", "pairs.bedpe")}
+    print("generated in %.1f s, wrote inputs in %.1f s: %d contacts per sample, %d pairs, files %s" % (
+        t_gen, time.perf_counter() - t0, len(ref[2]), len(pairs), sizes), flush=True)
+    n_pairs, n_contacts = len(pairs), int(len(ref[2]))
+    del ref, qry, pairs
 
-    class H(logging.Handler):
-        def emit(self, record):
-            stamps.append((time.perf_counter(), record.getMessage()[:60]))
-
-    logging.getLogger('').addHandler(H())
+    from chess_b200 import cli
     argv = ["chess", "sim", os.path.join(tmp, "ref.sparse"), os.path.join(tmp, "qry.sparse"),
             os.path.join(tmp, "pairs.bedpe"), os.path.join(tmp, "out.tsv"), "--reference-regions",
             os.path.join(tmp, "regions.bed"), "--query-regions", os.path.join(tmp, "regions.bed")]
@@ -54,17 +85,22 @@ def main():
         argv += ["--background-query", "--limit-background"]
     if args.window:
         argv += ["-a", args.window]
-    for rep in range(2):
-        del stamps[:]
+    runs = []
+    for rep in range(args.runs):
         t0 = time.perf_counter()
-        Chess(argv)
+        cli.Chess(argv)
         total = time.perf_counter() - t0
+        stages = dict(cli.LAST_STAGES)
+        runs.append({"total_s": total, "stages": stages})
         print("run %d: total %.3f s" % (rep, total))
-        prev = t0
-        for t, msg in stamps:
-            print("   +%.3f s  %s" % (t - prev, msg))
-            prev = t
-    print(open(os.path.join(tmp, "out.tsv")).read()[:300])
+        for name, secs in stages.items():
+            print("   %-34s %8.3f s" % (name, secs))
+        print("   %-34s %8.3f s" % ("(unaccounted)", total - sum(stages.values())), flush=True)
+    print(open(os.path.join(tmp, "out.tsv")).read()[:240])
+    import torch
+    print(json.dumps({"workload": args.workload, "pairs": n_pairs, "contacts_per_sample": n_contacts,
+                      "devices": os.environ.get("CHESS_B200_DEVICES") or "all (%d)" % torch.cuda.device_count(),
+                      "argv": argv[2:], "input_bytes": sizes, "runs": runs}))
 
 
 if __name__ == "__main__":
