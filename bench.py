@@ -551,7 +551,9 @@ class Resident(object):
     """One workload resident on this rank's GPU: both samples (O/E, band, index arrays) and the spans of the
     whole pair list; `table(lo, hi)` gives the chess_pair records of a contiguous range."""
 
-    def __init__(self, w, R, max_n=None):
+    def __init__(self, w, R, max_n=None, shard=None):
+        """``shard`` = (lo, hi): this rank compares pairs lo .. hi-1 only and holds the bands of the bin range they
+        read (per-GPU placement); None = the whole bands."""
         import torch
         import chess_b200 as cb
         from chess_b200.engine import region_spans
@@ -569,17 +571,31 @@ class Resident(object):
         t0 = time.perf_counter()
         self.re_ = cb.observed_expected_arrays(self.regions, self.ref, device=R.local_rank)
         self.qe = cb.observed_expected_arrays(self.regions, self.qry, device=R.local_rank)
-        self.rw, self.rband, self.rsample = self.re_.sample_on(R.local_rank, self.max_n)
-        self.qw, self.qband, self.qsample = self.qe.sample_on(R.local_rank, self.max_n)
+        self.place(shard)
         torch.cuda.synchronize(R.dev)
         self.setup_s = time.perf_counter() - t0
         self.coo_bytes = int(sum(len(s[2]) * 16 for s in (self.ref, self.qry)))
 
+    def place(self, shard=None):
+        """Bands (and index arrays) on this rank's GPU: of the bins the pairs shard[0] .. shard[1]-1 read, or whole."""
+        def rng(first, n):
+            if shard is None:
+                return None
+            f, c = first[shard[0]:shard[1]], n[shard[0]:shard[1]]
+            live = c > 0
+            return (int(f[live].min()), int((f[live] + c[live]).max())) if live.any() else (0, 1)
+        dev = self.R.local_rank
+        self.rw, self.rband, self.rsample, self.r0 = self.re_.sample_on(dev, self.max_n, None, rng(self.rf, self.rn),
+                                                                        with_origin=True)
+        self.qw, self.qband, self.qsample, self.q0 = self.qe.sample_on(dev, self.max_n, None, rng(self.qf, self.qn),
+                                                                        with_origin=True)
+        self.band_bytes = int(self.rband.numel() * 8 + self.qband.numel() * 8)
+
     def table(self, lo=0, hi=None):
         from chess_b200.engine import build_pair_table
         hi = len(self.pairs) if hi is None else hi
-        return build_pair_table(self.rf[lo:hi], self.rn[lo:hi], self.rw, self.qf[lo:hi], self.qn[lo:hi], self.qw,
-                                self.flip[lo:hi])
+        return build_pair_table(self.rf[lo:hi] - self.r0, self.rn[lo:hi], self.rw, self.qf[lo:hi] - self.q0,
+                                self.qn[lo:hi], self.qw, self.flip[lo:hi])
 
     def alg_bytes(self, lo=0, hi=None):
         n = np.maximum(self.rn[lo:hi], self.qn[lo:hi]).astype(np.float64)
@@ -604,14 +620,15 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
     from chess_b200 import _native
     from chess_b200._native import lib, check
     from chess_b200.engine import get_context
-    from chess_b200.distributed import gather_to_rank0, run_zscores, my_shard
+    from chess_b200.distributed import gather_tensors_to_rank0, run_zscores, my_shard
 
     steps = steps or args.steps
     warmup = max(warmup or args.warmup, 3)
     dev, rank, world = R.dev, R.rank, R.world
     strong = w["scaling"] == "strong" and world > 1
     own = res is None
-    res = res or Resident(w, R)
+    if res is None:
+        res = Resident(w, R, shard=my_shard(workload_spec(args)["pairs"], rank, world) if strong else None)
     total = len(res.pairs)
     lo, hi = my_shard(total, rank, world) if strong else (0, total)
     n_local = hi - lo
@@ -632,15 +649,21 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
                                             _np_ptr(h_status), _np_ptr(h_z), sp), ctx.handle, "chess_sim_band_batch_host")
         return h_ssim, h_sn, h_status, h_z
 
-    def host_sharded():    # N > 1: this rank's range, host gather, z on rank 0 (bin/chess:216-233)
-        check(lib.chess_compare_band_batch_host(ctx.handle, C.byref(res.rsample), C.byref(res.qsample),
-                                                _np_ptr(table), n_local, res.max_n, C.byref(p), _np_ptr(h_ssim),
-                                                _np_ptr(h_sn), _np_ptr(h_status), sp),
-              ctx.handle, "chess_compare_band_batch_host")
-        got = gather_to_rank0((h_ssim, h_sn, h_status), total, rank, world, R.dist, group=R.gloo)
+    pinned_table = torch.from_numpy(table.view(np.uint8)).pin_memory() if strong else None
+    e_tab = torch.empty(table.nbytes, dtype=torch.uint8, device=dev) if strong else None
+    e_ssim = torch.empty(n_local, dtype=torch.float64, device=dev)
+    e_sn = torch.empty(n_local, dtype=torch.float64, device=dev)
+    e_status = torch.empty(n_local, dtype=torch.int32, device=dev)
+
+    def host_sharded():    # N > 1: this rank's range; results gathered on rank 0 and copied to its host; z there
+        e_tab.copy_(pinned_table, non_blocking=True)                      # the host pair table of this range
+        check(lib.chess_compare_band_batch(ctx.handle, C.byref(res.rsample), C.byref(res.qsample), _ptr(e_tab),
+                                           n_local, res.max_n, C.byref(p), _ptr(e_ssim), _ptr(e_sn), _ptr(e_status),
+                                           sp), ctx.handle, "chess_compare_band_batch")
+        got = gather_tensors_to_rank0((e_ssim, e_sn, e_status), total, rank, world, R.dist)
         if rank != 0:
             return None
-        return got + (run_zscores(got[0]),)
+        return got + (run_zscores(got[0]),)           # bin/chess:216-233 on the gathered values
 
     host_step = host_sharded if strong else host_sim
     t0 = time.perf_counter()
@@ -732,8 +755,10 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
     z_ok = bool(np.allclose(z_dev, z_numpy, rtol=1e-9, atol=1e-12, equal_nan=True) and
                 np.allclose(g_z, z_numpy, rtol=1e-9, atol=1e-12, equal_nan=True))
     run = {"pairs_ok": int((g_status == 0).sum()), "pairs_this_rank": n_local, "max_n": res.max_n,
+           "band_bytes_this_rank": res.band_bytes,
            "wall_s_timed_region": wall, "zscore_device_matches_host": z_ok}
     if strong:
+        res.place(None)            # rank 0 alone, after the timed regions: the whole bands for the reference run
         full_tab = res.table()
         f_ssim, f_sn = np.empty(total), np.empty(total)
         f_status = np.empty(total, dtype=np.int32)
@@ -764,9 +789,10 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
                                   % (kern_ms * 1e3, n_local), traffic), traffic_source=traffic_note),
         "e2e": {"value": all_pairs * steps / e2e_s, "unit": "pairs/s", "ms_per_step": 1e3 * e2e_s / steps,
                 "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_local * (28 if not strong else 20)),
-                "call": ("chess_compare_band_batch_host on every rank's range (host pair table in; ssim, SN, status out "
-                         "to host arrays), distributed.gather_to_rank0 over gloo (20 B per pair, one collective), "
-                         "distributed.run_zscores on rank 0 -- all timed" if strong else
+                "call": ("every rank: its range of the host pair table -> GPU, chess_compare_band_batch; "
+                         "distributed.gather_tensors_to_rank0 (ssim, SN, status of all ranks in one NCCL gather, 20 B "
+                         "per pair, then ONE copy to rank 0's host memory); distributed.run_zscores on rank 0 -- all "
+                         "timed" if strong else
                          "chess_sim_band_batch_host (host pair table in; ssim, SN, status, z_ssim out to host arrays; "
                          "up to 8192 pairs the kernels read / write the pinned staging buffer directly, larger "
                          "batches use one DMA each way)")},
@@ -950,8 +976,8 @@ def measure_sweep(args, R, w):
         res.qf, res.qn, res.flip = res.rf, res.rn, np.zeros(len(res.pairs), dtype=np.int32)
         res.max_n = int(res.rn.max())
         res.re_._bands.clear(), res.re_._index.clear(), res.qe._bands.clear(), res.qe._index.clear()
-        res.rw, res.rband, res.rsample = res.re_.sample_on(R.local_rank, res.max_n)
-        res.qw, res.qband, res.qsample = res.qe.sample_on(R.local_rank, res.max_n)
+        from chess_b200.distributed import my_shard as _shard
+        res.place(_shard(len(res.pairs), R.rank, R.world) if R.world > 1 else None)
         for win in [x for x in WINDOWS if x in args.sweep_windows.split(",")]:
             a = copy.copy(args)
             a.window = win

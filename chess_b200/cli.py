@@ -253,6 +253,14 @@ def run_sim(args):
 
     loader = load_oe_contacts if args.oe_input else load_contacts
     devices = visible_devices()
+    if len(devices) > 1:
+        # CUDA contexts cost about a second each: create them side by side, not one after the other
+        from concurrent.futures import ThreadPoolExecutor
+        from .engine import get_context
+        import torch
+        with ThreadPoolExecutor(len(devices)) as pool:
+            list(pool.map(lambda d: (torch.cuda.synchronize(d), get_context(d)), devices))
+        clock.mark("create GPU contexts", sync=False)
     query_job = None
     if len(devices) > 1:
         # two samples, two GPUs: the query is read, parsed and normalised on the second one meanwhile

@@ -72,6 +72,42 @@ def gather_to_rank0(local_arrays, total, rank, world, dist=None, group=None, dev
     return tuple(out)
 
 
+def gather_tensors_to_rank0(local_tensors, total, rank, world, dist=None, group=None):
+    """The same gather for results that are still on the GPU: the per-rank tensors (this rank's shard, e.g. ssim,
+    SN, status on its device) travel as one padded byte buffer in one collective over the default group (NCCL:
+    device to device over NVLink), and rank 0 alone copies the gathered buffer to the host -- one D2H instead of
+    one per rank plus a host-side collective.  Works unchanged on CPU tensors over gloo.  Returns numpy arrays in
+    pair order on rank 0, ``None`` elsewhere."""
+    import torch
+    if world == 1 or dist is None:
+        return tuple(t.cpu().numpy() for t in local_tensors)
+    bounds = shard_bounds(total, world)
+    longest = int(np.max(np.diff(bounds)))
+    sizes = [t.element_size() for t in local_tensors]
+    ref = local_tensors[0]
+    buf = torch.zeros(longest * sum(sizes), dtype=torch.uint8, device=ref.device)
+    off = 0
+    for t, size in zip(local_tensors, sizes):
+        n = t.numel() * size
+        if n:                      # a rank may hold no pair at all
+            buf[off:off + n] = t.contiguous().view(torch.uint8).reshape(-1)
+        off += longest * size
+    bucket = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, gather_list=bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    host = torch.stack(bucket).cpu().numpy()          # one copy for everything
+    dtypes = [torch.empty(0, dtype=t.dtype).numpy().dtype for t in local_tensors]
+    out = [np.empty(total, dtype=dt) for dt in dtypes]
+    for k in range(world):
+        n = int(bounds[k + 1] - bounds[k])
+        off = 0
+        for full, size in zip(out, sizes):
+            full[bounds[k]:bounds[k + 1]] = host[k, off:off + n * size].view(full.dtype)
+            off += longest * size
+    return tuple(out)
+
+
 def run_zscores(ssim):
     """z_ssim over the whole run from the gathered ssim values (bin/chess:228-233): nanmean / nanstd
     (ddof 0) over the non-NaN entries, NaN kept.  Rank 0 calls this after `gather_to_rank0`."""

@@ -39,9 +39,15 @@ def _worker(rank, world, port, total, out_path):
     got = gather_to_rank0((ssim, sn, status), total, rank, world, dist)
     # the same through an explicit (second) gloo group, as bench.py does beside an NCCL default group
     again = gather_to_rank0((ssim, sn, status), total, rank, world, dist, group=dist.new_group(backend="gloo"))
+    # ... and the tensor form (what the ranks use when the results are still on their GPUs)
+    import torch
+    from chess_b200.distributed import gather_tensors_to_rank0
+    third = gather_tensors_to_rank0(tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in (ssim, sn, status)),
+                                    total, rank, world, dist)
     slowest = max_over_ranks(1.0 + rank, world, dist)
     if rank == 0:
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, again))
+        assert all(np.array_equal(a, b, equal_nan=True) and a.dtype == b.dtype for a, b in zip(got, third))
         from chess_b200.distributed import run_zscores
         np.savez(out_path, ssim=got[0], sn=got[1], status=got[2], slowest=slowest, z=run_zscores(got[0]))
     else:
