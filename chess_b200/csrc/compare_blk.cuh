@@ -47,7 +47,7 @@ compare_r1_blk_kernel(chess_item_args a) {
     first_item = false;
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * (31 * G - 6), lane, kmap, mflag, it)) continue;
+    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * 29 * G, lane, kmap, mflag, it)) continue;
     const long long pi = it.pi;
     const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;
@@ -62,7 +62,7 @@ compare_r1_blk_kernel(chess_item_args a) {
       continue;
     }
     const int m = np_ - win + 1;
-    if ((np_ + nb - 1) / nb < 8) {  // blocks narrower than their halos (almost everything masked): generic kernel
+    if ((np_ + nb - 1) / nb < 8 || (((np_ + nb - 1) / nb + G - 1) / G) > 29) {  // blocks narrower than their halos (almost everything masked): generic kernel
       if (part == 0 && lane == 0) {
         a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
         atomicOr(a.retry_cur, 1);
@@ -76,32 +76,18 @@ compare_r1_blk_kernel(chess_item_args a) {
                                                                       // background regions (a bin masked on one side)
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
 
-    // ---- this item's block (bi, bj), bj >= bi, of nb x nb equal blocks of the compacted pair:
-    // rows [lo, hi), emitted columns [clo, chi), three halo rows / columns either side
+    // ---- this item's block (bi, bj), bj >= bi, of nb x nb square blocks of the compacted pair (tri_rows.cuh:
+    // blk_lane): `side` rows, a multiple of the strip width, so that every lane is block or halo as a whole
     int bi = 0, bj = 0;
     {
       int left = part;
       while (left >= nb - bi) { left -= nb - bi; ++bi; }
       bj = bi + left;
     }
-    const int side = (np_ + nb - 1) / nb;
-    const int lo = min(bi * side, np_), hi = min(lo + side, np_);
-    const int clo = min(bj * side, np_), chi = min(clo + side, np_);
-    const int cbase = clo - 3 + G * lane;
-    const int rows_max = (chi > clo) ? hi - lo : 0;
+    const int side = (((np_ + nb - 1) / nb + G - 1) / G) * G;
+    const TriLane ln = blk_lane(bi, bj, side, lane, G, np_, WITH_SN ? 3 : 0);
+    const int rows_max = (min(bj * side, np_) < np_) ? ln.hi - ln.lo : 0;
     const double wblock = bi == bj ? 1.0 : 2.0;   // a block above the diagonal stands for its mirror image too
-    unsigned xo[G], yo[G];
-    bool valid[G];
-    double wc[G];   // weight of the column: 0 in the halo, the block's weight inside
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c = cbase + g;
-      valid[g] = c >= 0 && c < np_ && c < chi + 3;
-      wc[g] = (c >= clo && c < chi) ? wblock : 0.0;
-      const int kc = valid[g] ? (int)kmap[c] : 0;
-      xo[g] = (unsigned)kc;
-      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
-    }
     double *rec = a.scratch + ((size_t)pi * ipp + part) * kTriRec;
 
     // first row totals (first item) / last row totals (last item) for the 2x2 SSIM map
@@ -125,156 +111,12 @@ compare_r1_blk_kernel(chess_item_args a) {
     bool overflow = false;
 
     if (rows_max > 0) {
-      // per-lane row cursor: halo rows above the band only where the SN window needs them
-      const int halo = WITH_SN ? 3 : 0;
-      const int first = lo - halo < 0 ? 0 : lo - halo;            // the top blocks start at row 0
-      const int t_emit0 = bi == 0 ? halo : 2 * halo;             // first iteration with a complete window
-      const int T = rows_max + (bi == 0 ? halo : 2 * halo);
-      double ccnt[G];
-      double Sd[G], Se[G];
-      unsigned hist[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int c = cbase + g;
-        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-        Sd[g] = 0.0; Se[g] = 0.0; hist[g] = 0u;
-        if (WITH_SN) {
-#pragma unroll
-          for (int k = 0; k < 7; ++k) myring[(k * G + g) * 32] = 0.0;
-        }
-      }
-      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-      double *ringrow = myring;
-      int slot = 0;
-      double xn[G], yn[G];
-      auto fetch = [&](int row) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
-        if (row < np_) {
-          const unsigned kr = (unsigned)kmap[row];
-          const unsigned ro = kr * (unsigned)rp;
-          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
-          }
-        }
-      };
-      // two instances of the row loop: the usual one, and one that also tracks min / max of the data
-      double vmax = -CUDART_INF, vmin = CUDART_INF;
-      auto run = [&](auto minmax_tag) {
-      constexpr bool MINMAX = decltype(minmax_tag)::value;
-      int row = first;
-      fetch(row);
-      for (int t = 0; t < T; ++t, ++row) {
-        double dv[G];
-        bool nzv[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { dv[g] = xn[g] - yn[g]; nzv[g] = xn[g] != yn[g]; }
-        if (row >= lo && row < hi) {  // the block's own rows: weighted moments
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const double wx = wc[g] * xn[g], wy = wc[g] * yn[g];
-            T0 += wx; T1 += wy;
-            T2 = fma(wx, xn[g], T2); T3 = fma(wy, yn[g], T3); T4 = fma(wx, yn[g], T4);
-            if (MINMAX) {  // every loaded element of an own row belongs to the compacted pair
-              const bool xgt = xn[g] > yn[g];
-              const double hi2 = xgt ? xn[g] : yn[g];
-              const double lo2 = xgt ? yn[g] : xn[g];
-              vmax = (valid[g] & (hi2 > vmax)) ? hi2 : vmax;
-              vmin = (valid[g] & (lo2 < vmin)) ? lo2 : vmin;
-            }
-          }
-        }
-        if (t + 1 < T) fetch(row + 1);
-        if (WITH_SN) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            double *cell = ringrow + g * 32;
-            const double dold = *cell;
-            *cell = dv[g];
-            Sd[g] += dv[g]; Sd[g] -= dold;
-            Se[g] = fma(dv[g], dv[g], Se[g]); Se[g] = fma(-dold, dold, Se[g]);
-            hist[g] = ((hist[g] << 1) & 0x7fu) | (nzv[g] ? 1u : 0u);
-            Se[g] = hist[g] == 0u ? 0.0 : Se[g];
-          }
-          if (slot == 6) { slot = 0; ringrow = myring; } else { slot += 1; ringrow += G * 32; }
-          if (slot == 0) {
-            // the ring has just wrapped: rebuild the column sums from its seven rows.  A running sum keeps the
-            // rounding of every value that ever passed through it; rebuilt once per window height it is exact
-            // to a few ulps of the current window, which the quiet windows after a loud stretch need
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
-#pragma unroll
-              for (int k = 0; k < 7; ++k) { const double v = myring[(k * G + g) * 32]; s2 = fma(v, v, s2); }
-              Se[g] = hist[g] == 0u ? 0.0 : s2;
-            }
-          }
-          if (t >= t_emit0) {
-            const int rc = row - 3;
-            const bool emit_row = rc >= lo && rc < hi;
-            const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-            double P1[G + 1], P2[G + 1];
-            P1[0] = 0.0; P2[0] = 0.0;
-            P1[1] = Sd[0]; P2[1] = Se[0];
-#pragma unroll
-            for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
-            // suffix sums as well: a window that ends at the strip's right edge is a suffix, and no window of 7
-            // starts after column 0 without reaching that edge (G <= 8), so nothing is ever subtracted -- a
-            // difference of prefixes would carry the rounding of every column left of the window
-            double X1[G], X2[G];
-            X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
-#pragma unroll
-            for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
-            double up1[3], up2[3], dn1[3], dn2[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
-              const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
-              up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
-              up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
-              dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
-              dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
-            }
-            unsigned suspect = 0u;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int a0 = g - 3 < 0 ? 0 : g - 3;
-              const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
-              double w1 = a0 == 0 ? P1[b0 + 1] : X1[a0];
-              double w2 = a0 == 0 ? P2[b0 + 1] : X2[a0];
-              if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
-              if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
-              const bool own = emit_row & (wc[g] != 0.0);
-              const double cnt = rcnt * ccnt[g];
-              const double m2 = w2 * cnt;
-              const double den = fma(-w1, w1, m2);
-              const bool good = own & (den > fma(m2, kVarGuard, 1e-290));
-              const double gq = fabs(w1) * cnt * fast_rcp(den);
-              sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
-              sn_cnt += good ? wc[g] : 0.0;
-              if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
-            }
-            if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                if (suspect & (1u << g)) {
-                  const int e = atomicAdd(susp_n, 1);
-                  if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
-                }
-              }
-            }
-          }
-        }
-      }
-      };
-      if (inloop_minmax) {
-        run(std::true_type());
-        xmax = warp_max(vmax); xmin = warp_min(vmin);
-      } else {
-        run(std::false_type());
-      }
+      TriPartSums ps;
+      tri_r1_part<G, WITH_SN>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, bi == 0, rows_max,
+                              inloop_minmax, susp, susp_n, ps);
+      T0 = ps.T[0]; T1 = ps.T[1]; T2 = ps.T[2]; T3 = ps.T[3]; T4 = ps.T[4];
+      sn_sum = ps.sn_sum; sn_cnt = ps.sn_cnt;
+      if (inloop_minmax) { xmax = warp_max(ps.vmax); xmin = warp_min(ps.vmin); }
       if (WITH_SN) {
         __syncwarp();
         const int ns = *susp_n;

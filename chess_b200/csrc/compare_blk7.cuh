@@ -41,7 +41,7 @@ compare_win7_blk_kernel(chess_item_args a) {
     first_item = false;
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * (31 * G - 2 * 3), lane, kmap, mflag, it)) continue;
+    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * 29 * G, lane, kmap, mflag, it)) continue;
     const long long pi = it.pi;
     const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;
@@ -66,7 +66,7 @@ compare_win7_blk_kernel(chess_item_args a) {
 
     // ---- this item's block (bi, bj), bj >= bi, of nb x nb equal blocks of the compacted pair:
     // rows [lo, hi), emitted columns [clo, chi), HALO rows / columns either side
-    if ((np_ + nb - 1) / nb < 8 + 3) {  // blocks narrower than their halos (almost everything masked)
+    if ((np_ + nb - 1) / nb < 8 + 3 || !(C2 > 0.0) || (((np_ + nb - 1) / nb + G - 1) / G) > 29) {  // blocks narrower than their halos; constant matrices (almost everything masked)
       if (part == 0 && lane == 0) {
         a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
         atomicOr(a.retry_cur, 1);
@@ -79,176 +79,17 @@ compare_win7_blk_kernel(chess_item_args a) {
       while (left >= nb - bi) { left -= nb - bi; ++bi; }
       bj = bi + left;
     }
-    const int side = (np_ + nb - 1) / nb;
-    const int lo = min(bi * side, np_), hi = min(lo + side, np_);
-    const int clo = min(bj * side, np_), chi = min(clo + side, np_);
-    const int cbase = clo - 3 + G * lane;
-    const int rows_max = (chi > clo) ? hi - lo : 0;
+    const int side = (((np_ + nb - 1) / nb + G - 1) / G) * G;
+    const TriLane ln = blk_lane(bi, bj, side, lane, G, np_, 3);
+    const int rows_max = (min(bj * side, np_) < np_) ? ln.hi - ln.lo : 0;
     const double wblock = bi == bj ? 1.0 : 2.0;   // a block above the diagonal stands for its mirror image too
-    unsigned xo[G], yo[G];
-    bool valid[G];
-    double wc[G];   // weight of the column: 0 in the halo, the block's weight inside
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c = cbase + g;
-      valid[g] = c >= 0 && c < np_ && c < chi + 3;
-      wc[g] = (c >= clo && c < chi) ? wblock : 0.0;
-      const int kc = valid[g] ? (int)kmap[c] : 0;
-      xo[g] = (unsigned)kc;
-      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
-    }
     double *rec = a.scratch + ((size_t)pi * ipp + part) * kTriRec;
     double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
     bool overflow = false;
 
     if (rows_max > 0) {
-      const int first = max(lo - 3, 0);                           // the top blocks start at row 0
-      const int t_emit0 = bi == 0 ? 3 : 6;                        // first iteration with a complete window
-      const int T = rows_max + (bi == 0 ? 3 : 6);
-      const double inv_np = 1.0 / 49.0;
-      const double cov_norm = 49.0 / 48.0;
-      double ccnt[G], wss[G];
-      double Vx[G], Vy[G], Vq[G], Vxy[G];
-      unsigned hist[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int c = cbase + g;
-        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-        wss[g] = (c >= 3 && c <= np_ - 4) ? wc[g] : 0.0;          // SSIM windows need 3 columns either side
-        Vx[g] = Vy[g] = Vq[g] = Vxy[g] = 0.0;
-        hist[g] = 0u;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
-      }
-      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-      int slot = 0;
-      double xn[G], yn[G];
-      auto fetch = [&](int row) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
-        if (row < np_) {
-          const unsigned kr = (unsigned)kmap[row];
-          const unsigned ro = kr * (unsigned)rp;
-          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
-          }
-        }
-      };
-      int row = first;
-      fetch(row);
-      for (int t = 0; t < T; ++t, ++row) {
-        double x[G], y[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
-        if (t + 1 < T) fetch(row + 1);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          double *cell = myring + ((slot * G + g) * 2) * 32;   // the slot being overwritten holds row - 7
-          const double xold = cell[0], yold = cell[32];
-          cell[0] = x[g];
-          cell[32] = y[g];
-          Vx[g] += x[g]; Vx[g] -= xold;
-          Vy[g] += y[g]; Vy[g] -= yold;
-          Vq[g] = fma(x[g], x[g], fma(y[g], y[g], Vq[g]));
-          Vq[g] = fma(-xold, xold, fma(-yold, yold, Vq[g]));
-          Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xold, yold, Vxy[g]);
-          hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
-          if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
-        }
-        slot = slot == 6 ? 0 : slot + 1;
-        if (slot == 0) {
-          // the ring has just wrapped: rebuild the four column sums from its seven rows.  A running sum keeps the
-          // rounding of every value that ever passed through it; rebuilt once per window height it is exact to a
-          // few ulps of the current window (sum d*d = Wq - 2 Wxy magnifies whatever error Vq and Vxy carry)
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            double vq = 0.0, vxy = 0.0;   // the quadratic sums only: errors in sum x, sum y enter linearly
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-              const double xk = myring[((k * G + g) * 2) * 32], yk = myring[((k * G + g) * 2 + 1) * 32];
-              vq = fma(xk, xk, fma(yk, yk, vq));
-              vxy = fma(xk, yk, vxy);
-            }
-            Vq[g] = vq; Vxy[g] = vxy;
-            if (hist[g] == 0u) { Vy[g] = Vx[g]; Vq[g] = 2.0 * Vxy[g]; }
-          }
-        }
-
-        if (t >= t_emit0) {
-          const int rc = row - 3;   // centre row of the SSIM window and SN pixel row
-          const bool emit_row = rc >= lo && rc < hi;
-          const bool ssim_row = emit_row && rc >= 3 && rc <= np_ - 4;
-          double W4[4][G];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vq : Vxy;
-            double P[G + 1];
-            P[0] = 0.0; P[1] = V[0];
-#pragma unroll
-            for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
-            double up[3], dn[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
-              up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
-              dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int a0 = g - 3 < 0 ? 0 : g - 3;
-              const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
-              double w = a0 == 0 ? P[b0 + 1] : P[b0 + 1] - P[a0];
-              if (g - 3 < 0) w += up[2 - g];
-              if (g + 3 > G - 1) w += dn[g + 3 - G];
-              W4[q][g] = w;
-            }
-          }
-          const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-          unsigned suspect = 0u;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            {
-              const double ux = W4[0][g] * inv_np, uy = W4[1][g] * inv_np;
-              const double uq = W4[2][g] * inv_np, uxy = W4[3][g] * inv_np;
-              const double m2s = fma(ux, ux, uy * uy);                  // ux^2 + uy^2
-              const double vsum = cov_norm * (uq - m2s);                // vx + vy
-              const double vxy = cov_norm * fma(-ux, uy, uxy);
-              const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
-              const double B1s = m2s + C1, B2s = vsum + C2;
-              const double den = B1s * B2s;
-              const double num = A1 * A2;
-              double S = num * fast_rcp(den);
-              if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
-              if (ssim_row && wss[g] != 0.0) ss_sum = fma(wss[g], S, ss_sum);
-            }
-            if (with_sn) {
-              const double w1 = W4[0][g] - W4[1][g];
-              const double w2 = fma(-2.0, W4[3][g], W4[2][g]);
-              const bool own = emit_row & (wc[g] != 0.0);
-              const double cnt = rcnt * ccnt[g];
-              const double m2 = w2 * cnt;
-              const double den = fma(-w1, w1, m2);
-              // trusted: one-pass variance well conditioned AND the q - 2xy subtraction kept >= 10 digits
-              const bool good = own & (den > fma(m2, kVarGuard, 1e-290)) & (w2 > 1e-6 * W4[2][g]);
-              const double gq = fabs(w1) * cnt * fast_rcp(den);
-              sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
-              sn_cnt += good ? wc[g] : 0.0;
-              if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
-            }
-          }
-          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (suspect & (1u << g)) {
-                const int e = atomicAdd(susp_n, 1);
-                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
-              }
-            }
-          }
-        }
-      }
+      tri_w7_part<G>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, bi == 0, rows_max, with_sn,
+                     C1 * 2401.0, C2 * 2401.0, susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();
         const int ns = *susp_n;

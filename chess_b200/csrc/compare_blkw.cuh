@@ -44,7 +44,7 @@ compare_win_blk_kernel(chess_item_args a) {
     first_item = false;
     if (item >= n_items) break;
     TriItem it;
-    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * (31 * G - 2 * HALO), lane, kmap, mflag, it)) continue;
+    if (!tri_item_begin(a, item / ipp, (int)(item % ipp), nb * 29 * G, lane, kmap, mflag, it)) continue;
     const long long pi = it.pi;
     const int part = it.part, n = it.n, np_ = it.np_, flip = it.flip;
     const double *R = it.R, *Q = it.Q;
@@ -69,7 +69,7 @@ compare_win_blk_kernel(chess_item_args a) {
 
     // ---- this item's block (bi, bj), bj >= bi, of nb x nb equal blocks of the compacted pair:
     // rows [lo, hi), emitted columns [clo, chi), HALO rows / columns either side
-    if ((np_ + nb - 1) / nb < 8 + HALO) {  // blocks narrower than their halos (almost everything masked)
+    if ((np_ + nb - 1) / nb < 8 + HALO || !(C2 > 0.0) || (((np_ + nb - 1) / nb + G - 1) / G) > 29) {  // blocks narrower than their halos; constant matrices (almost everything masked)
       if (part == 0 && lane == 0) {
         a.ssim[pi] = qnan; a.sn[pi] = qnan; a.status[pi] = CHESS_PAIR_RETRY;
         atomicOr(a.retry_cur, 1);
@@ -82,212 +82,18 @@ compare_win_blk_kernel(chess_item_args a) {
       while (left >= nb - bi) { left -= nb - bi; ++bi; }
       bj = bi + left;
     }
-    const int side = (np_ + nb - 1) / nb;
-    const int lo = min(bi * side, np_), hi = min(lo + side, np_);
-    const int clo = min(bj * side, np_), chi = min(clo + side, np_);
-    const int cbase = clo - HALO + G * lane;
-    const int rows_max = (chi > clo) ? hi - lo : 0;
+    const int side = (((np_ + nb - 1) / nb + G - 1) / G) * G;   // a multiple of the strip width (tri_rows.cuh: blk_lane)
+    const TriLane ln = blk_lane(bi, bj, side, lane, G, np_, HALO);
+    const int rows_max = (min(bj * side, np_) < np_) ? ln.hi - ln.lo : 0;
     const double wblock = bi == bj ? 1.0 : 2.0;   // a block above the diagonal stands for its mirror image too
-    unsigned xo[G], yo[G];
-    bool valid[G];
-    double wc[G];   // weight of the column: 0 in the halo, the block's weight inside
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c = cbase + g;
-      valid[g] = c >= 0 && c < np_ && c < chi + HALO;
-      wc[g] = (c >= clo && c < chi) ? wblock : 0.0;
-      const int kc = valid[g] ? (int)kmap[c] : 0;
-      xo[g] = (unsigned)kc;
-      yo[g] = (unsigned)(flip ? n - 1 - kc : kc);
-    }
     double *rec = a.scratch + ((size_t)pi * ipp + part) * kTriRec;
     double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
     bool overflow = false;
 
     if (rows_max > 0) {
-      const int first = max(lo - HALO, 0);                        // the top blocks start at row 0
-      const int t_own0 = bi == 0 ? 0 : HALO;                      // iteration of the block's first own row
-      const int T = rows_max + (bi == 0 ? HALO : 2 * HALO);
-      constexpr int WIN = 2 * H + 1;
-      const double inv_np = 1.0 / (double)(WIN * WIN);
-      const double cov_norm = (double)(WIN * WIN) / (double)(WIN * WIN - 1);
-      double ccnt[G], wss[G];
-      double Sd[G], Se[G], Vx[G], Vy[G], Vxx[G], Vyy[G], Vxy[G];
-      unsigned hist[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int c = cbase + g;
-        ccnt[g] = (double)(min(c + 3, np_ - 1) - max(c - 3, 0) + 1);
-        wss[g] = (c >= H && c <= np_ - 1 - H) ? wc[g] : 0.0;      // SSIM windows need H columns either side
-        Sd[g] = Se[g] = Vx[g] = Vy[g] = Vxx[g] = Vyy[g] = Vxy[g] = 0.0;
-        hist[g] = 0u;
-#pragma unroll
-        for (int k = 0; k < D; ++k) { myring[((k * G + g) * 2) * 32] = 0.0; myring[((k * G + g) * 2 + 1) * 32] = 0.0; }
-      }
-      const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-      int slot = 0;
-      double xn[G], yn[G];
-      auto fetch = [&](int row) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) { xn[g] = 0.0; yn[g] = 0.0; }
-        if (row < np_) {
-          const unsigned kr = (unsigned)kmap[row];
-          const unsigned ro = kr * (unsigned)rp;
-          const unsigned qo = (flip ? (unsigned)(n - 1) - kr : kr) * (unsigned)qp;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (valid[g]) { xn[g] = __ldg(R + (ro + xo[g])); yn[g] = __ldg(Q + (qo + yo[g])); }
-          }
-        }
-      };
-      int row = first;
-      fetch(row);
-      for (int t = 0; t < T; ++t, ++row) {
-        double x[G], y[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { x[g] = xn[g]; y[g] = yn[g]; }
-        if (t + 1 < T) fetch(row + 1);
-        // ring positions of the rows that leave the 7-row and the WIN-row windows
-        const int s7 = slot + D - 7 >= D ? slot - 7 : slot + D - 7;        // row - 7
-        const int sw = slot + D - WIN >= D ? slot - WIN : slot + D - WIN;  // row - WIN
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const double xo7 = myring[((s7 * G + g) * 2) * 32], yo7 = myring[((s7 * G + g) * 2 + 1) * 32];
-          const double xow = myring[((sw * G + g) * 2) * 32], yow = myring[((sw * G + g) * 2 + 1) * 32];
-          myring[((slot * G + g) * 2) * 32] = x[g];
-          myring[((slot * G + g) * 2 + 1) * 32] = y[g];
-          const double dv = x[g] - y[g], dold = xo7 - yo7;
-          Sd[g] += dv; Sd[g] -= dold;
-          Se[g] = fma(dv, dv, Se[g]); Se[g] = fma(-dold, dold, Se[g]);
-          hist[g] = ((hist[g] << 1) & 0x7fu) | (x[g] != y[g] ? 1u : 0u);
-          Se[g] = hist[g] == 0u ? 0.0 : Se[g];
-          Vx[g] += x[g]; Vx[g] -= xow;
-          Vy[g] += y[g]; Vy[g] -= yow;
-          Vxx[g] = fma(x[g], x[g], Vxx[g]); Vxx[g] = fma(-xow, xow, Vxx[g]);
-          Vyy[g] = fma(y[g], y[g], Vyy[g]); Vyy[g] = fma(-yow, yow, Vyy[g]);
-          Vxy[g] = fma(x[g], y[g], Vxy[g]); Vxy[g] = fma(-xow, yow, Vxy[g]);
-        }
-        slot = slot == D - 1 ? 0 : slot + 1;
-        if (slot == 0) {
-          // the ring has just wrapped: rebuild the 7-row difference sums from its most recent seven rows
-          // (slots D-7 .. D-1).  A running sum keeps the rounding of every value that ever passed through it;
-          // rebuilt once per wrap it is exact to a few ulps of the current window
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            double s2 = 0.0;   // sum d*d only: an error in sum d enters the variance linearly and is harmless
-#pragma unroll
-            for (int k = D - 7; k < D; ++k) {
-              const double dk = myring[((k * G + g) * 2) * 32] - myring[((k * G + g) * 2 + 1) * 32];
-              s2 = fma(dk, dk, s2);
-            }
-            Se[g] = hist[g] == 0u ? 0.0 : s2;
-          }
-        }
-
-
-        // ---- SSIM windows whose centre row is row - H
-        if (t >= t_own0 + H) {
-          const int rcs = row - H;
-          const bool ssim_row = rcs >= lo && rcs < hi && rcs >= H && rcs <= np_ - 1 - H;
-          double W5[5][G];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const double *V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vxx : q == 3 ? Vyy : Vxy;
-            double P[G + 1];
-            P[0] = 0.0; P[1] = V[0];
-#pragma unroll
-            for (int g = 1; g < G; ++g) P[g + 1] = P[g] + V[g];
-            double up[H], dn[H];
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-              const double sfx = j == 0 ? V[G - 1] : (G - 1 - j == 0 ? P[G] : P[G] - P[G - 1 - j]);
-              up[j] = __shfl_sync(0xffffffffu, sfx, up_lane);
-              dn[j] = __shfl_sync(0xffffffffu, P[j + 1], dn_lane);
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int a0 = g - H < 0 ? 0 : g - H;
-              const int b0 = g + H > G - 1 ? G - 1 : g + H;
-              double w = a0 == 0 ? P[b0 + 1] : P[b0 + 1] - P[a0];
-              if (g - H < 0) w += up[H - 1 - g];
-              if (g + H > G - 1) w += dn[g + H - G];
-              W5[q][g] = w;
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const double ux = W5[0][g] * inv_np, uy = W5[1][g] * inv_np;
-            const double uxx = W5[2][g] * inv_np, uyy = W5[3][g] * inv_np, uxy = W5[4][g] * inv_np;
-            const double vx = cov_norm * fma(-ux, ux, uxx);
-            const double vy = cov_norm * fma(-uy, uy, uyy);
-            const double vxy = cov_norm * fma(-ux, uy, uxy);
-            const double A1 = fma(2.0 * ux, uy, C1), A2 = fma(2.0, vxy, C2);
-            const double B1s = fma(ux, ux, fma(uy, uy, C1)), B2s = vx + vy + C2;
-            const double den = B1s * B2s;
-            const double num = A1 * A2;
-            double S = num * fast_rcp(den);
-            if (den == 0.0) S = num * CUDART_INF;  // zero data range: +-inf or NaN exactly like num / 0
-            if (ssim_row && wss[g] != 0.0) ss_sum = fma(wss[g], S, ss_sum);
-          }
-        }
-
-        // ---- SN pixels of row - 3
-        if (with_sn && t >= t_own0 + 3) {
-          const int rc = row - 3;
-          const bool emit_row = rc >= lo && rc < hi;
-          const double rcnt = (double)(min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1);
-          double P1[G + 1], P2[G + 1];
-          P1[0] = 0.0; P2[0] = 0.0;
-          P1[1] = Sd[0]; P2[1] = Se[0];
-#pragma unroll
-          for (int g = 1; g < G; ++g) { P1[g + 1] = P1[g] + Sd[g]; P2[g + 1] = P2[g] + Se[g]; }
-          // suffix sums as well: a window that ends at the strip's right edge is a suffix, and no window of 7
-          // starts after column 0 without reaching that edge (G <= 8), so nothing is ever subtracted -- a
-          // difference of prefixes would carry the rounding of every column left of the window
-          double X1[G], X2[G];
-          X1[G - 1] = Sd[G - 1]; X2[G - 1] = Se[G - 1];
-#pragma unroll
-          for (int g = G - 2; g >= 0; --g) { X1[g] = X1[g + 1] + Sd[g]; X2[g] = X2[g + 1] + Se[g]; }
-          unsigned suspect = 0u;
-          double up1[3], up2[3], dn1[3], dn2[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const double s1 = X1[G - 1 - j < 0 ? 0 : G - 1 - j];
-            const double s2 = X2[G - 1 - j < 0 ? 0 : G - 1 - j];
-            up1[j] = __shfl_sync(0xffffffffu, s1, up_lane);
-            up2[j] = __shfl_sync(0xffffffffu, s2, up_lane);
-            dn1[j] = __shfl_sync(0xffffffffu, P1[j + 1], dn_lane);
-            dn2[j] = __shfl_sync(0xffffffffu, P2[j + 1], dn_lane);
-          }
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const int a0 = g - 3 < 0 ? 0 : g - 3;
-            const int b0 = g + 3 > G - 1 ? G - 1 : g + 3;
-            double w1 = a0 == 0 ? P1[b0 + 1] : X1[a0];
-            double w2 = a0 == 0 ? P2[b0 + 1] : X2[a0];
-            if (g - 3 < 0) { w1 += up1[2 - g]; w2 += up2[2 - g]; }
-            if (g + 3 > G - 1) { w1 += dn1[g + 3 - G]; w2 += dn2[g + 3 - G]; }
-            const bool own = emit_row & (wc[g] != 0.0);
-            const double cnt = rcnt * ccnt[g];
-            const double m2 = w2 * cnt;
-            const double den = fma(-w1, w1, m2);
-            const bool good = own & (den > fma(m2, kVarGuard, 1e-290));
-            const double gq = fabs(w1) * cnt * fast_rcp(den);
-            sn_sum = fma(wc[g], good ? gq : 0.0, sn_sum);
-            sn_cnt += good ? wc[g] : 0.0;
-            if (!good && own && w2 != 0.0) suspect |= 1u << g;  // rare: cancellation
-          }
-          if (suspect) {  // one test per row instead of one per column: exact recompute after the loop
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (suspect & (1u << g)) {
-                const int e = atomicAdd(susp_n, 1);
-                if (e < kSuspCap) susp[e] = (rc << 16) | (cbase + g);
-              }
-            }
-          }
-        }
-      }
+      constexpr double NP2 = (double)((2 * H + 1) * (2 * H + 1)) * (double)((2 * H + 1) * (2 * H + 1));
+      tri_win_part<G, H>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, bi == 0, rows_max, with_sn,
+                         C1 * NP2, C2 * NP2, susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();
         const int ns = *susp_n;

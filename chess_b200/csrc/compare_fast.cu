@@ -572,12 +572,15 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   // count that cost the fewest lane-columns (blocks x rows per block x strip width)
   int blk_nb = 0;
   if (!tri && (r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre && max_n > 93) {
+    // blocks of `side` rows, a multiple of the strip width and at most 29 strips (one halo lane either side and
+    // an idle lane for the neighbour exchange to wrap onto): cost = items x rows per item x strip width
     long best = -1;
     const int halo = H > 3 ? H : 3;
-    for (int g = 5; g <= 8; ++g) {
-      const int nb = (max_n + (31 * g - 2 * halo) - 1) / (31 * g - 2 * halo);
+    for (int g = (H > 5 ? H : 5); g <= 8; ++g) {
+      const int nb = (max_n + 29 * g - 1) / (29 * g);
       if (nb < 2 || nb > 7) continue;
-      const long cost = (long)(nb * (nb + 1) / 2) * ((max_n + nb - 1) / nb + 2 * halo) * g;
+      const int side = (((max_n + nb - 1) / nb + g - 1) / g) * g;
+      const long cost = (long)(nb * (nb + 1) / 2) * (side + 2 * halo) * g;
       if (best < 0 || cost < best) { best = cost; G = g; blk_nb = nb; }
     }
   }

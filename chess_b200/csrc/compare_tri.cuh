@@ -251,8 +251,8 @@ __device__ __forceinline__ bool tri_r1_run_part(const TriItem &it, int part, int
   if (rows_max > 0) {
     if (lane == 0) *susp_n = 0;
     __syncwarp();
-    tri_r1_part<G, WITH_SN>(it.R, it.Q, (unsigned)it.rp, (unsigned)it.qp, it.n, np_, it.flip, kmap, myring, ln, part,
-                            rows_max, minmax, susp, susp_n, ps);
+    tri_r1_part<G, WITH_SN>(it.R, it.Q, (unsigned)it.rp, (unsigned)it.qp, it.n, np_, it.flip, kmap, myring, ln,
+                            part == 0, rows_max, minmax, susp, susp_n, ps);
     if (WITH_SN) {
       __syncwarp();
       const int ns = *susp_n;

@@ -98,7 +98,7 @@ compare_win_tri_kernel(chess_item_args a) {
     const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, HALO);
     const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
     if (rows_max > 0) {
-      tri_win_part<G, H>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, part, rows_max, with_sn, c1,
+      tri_win_part<G, H>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, part == 0, rows_max, with_sn, c1,
                          c2, susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();

@@ -103,6 +103,7 @@ struct TriLane {
   int lo, hi;      // rows of the lane's band
   int cbase;       // first column of the lane's strip (1 << 20: idle lane)
   int first;       // first row the lane reads (lo - 3, clamped)
+  int cend;        // columns are read up to here (the matrix edge, or the end of a block's right halo lane)
   double wl;       // weight of the lane's columns: 0 halo, 1 diagonal block, 2 right of it
 };
 
@@ -118,7 +119,24 @@ __device__ __forceinline__ TriLane tri_lane(int part, int lane, int G, int np_, 
     g.lo = B2; g.hi = np_; g.cbase = B2 - G + G * (lane - L1 - 1);
   }
   g.first = g.lo - halo < 0 ? 0 : g.lo - halo;
+  g.cend = np_;
   g.wl = g.cbase < g.lo ? 0.0 : (g.cbase < g.hi ? 1.0 : 2.0);
+  return g;
+}
+
+// Matrices wider than one warp: nb x nb square blocks of `side` rows (a multiple of G, at most 29 G), the blocks
+// on and above the diagonal are the work items.  Block (bi, bj): rows [bi side, ...), columns [bj side, ...) plus
+// one whole lane of halo columns on either side that exists; the block's lanes weigh 1 on the diagonal (its full
+// square is summed once) and 2 above it (it stands for its mirror image), halo lanes 0.
+__device__ __forceinline__ TriLane blk_lane(int bi, int bj, int side, int lane, int G, int np_, int halo) {
+  TriLane g;
+  g.lo = min(bi * side, np_); g.hi = min(g.lo + side, np_);
+  const int clo = min(bj * side, np_), chi = min(clo + side, np_);
+  g.cbase = (clo == 0 ? 0 : clo - G) + G * lane;
+  g.cend = min(np_, chi + G);
+  if (g.cbase >= g.cend) g.cbase = 1 << 20;          // idle lane
+  g.first = g.lo - halo < 0 ? 0 : g.lo - halo;
+  g.wl = (g.cbase >= clo && g.cbase < chi) ? (bi == bj ? 1.0 : 2.0) : 0.0;
   return g;
 }
 
@@ -137,14 +155,15 @@ struct TriPartSums {
 template <int G, bool WITH_SN>
 __device__ __forceinline__ void tri_r1_part(const double *__restrict__ R, const double *__restrict__ Q, unsigned rp,
                                             unsigned qp, int n, int np_, int flip, const short *kmap,
-                                            double *myring, const TriLane &ln, int part, int rows_max,
+                                            double *myring, const TriLane &ln, bool top, int rows_max,
                                             bool minmax, int *susp, int *susp_n, TriPartSums &out) {
+  // `top`: the rows start at row 0 of the matrix (no halo rows above them)
   constexpr int HALO = WITH_SN ? 3 : 0;
   const int lo = ln.lo, hi = ln.hi, cbase = ln.cbase;
-  const int t_emit0 = part == 0 ? HALO : 2 * HALO;           // first iteration with a complete window
-  const int T = rows_max + (part == 0 ? HALO : 2 * HALO);
+  const int t_emit0 = top ? HALO : 2 * HALO;           // first iteration with a complete window
+  const int T = rows_max + (top ? HALO : 2 * HALO);
   // number of columns of the strip that exist; the others keep x = y = 0 for the whole loop
-  int nv = np_ - cbase;
+  int nv = ln.cend - cbase;
   nv = nv < 0 ? 0 : (nv > G ? G : nv);
   unsigned xo[G];
   double ccnt[G];
@@ -339,13 +358,13 @@ __device__ __forceinline__ void tri_r1_part(const double *__restrict__ R, const 
 template <int G>
 __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const double *__restrict__ Q, unsigned rp,
                                             unsigned qp, int n, int np_, int flip, const short *kmap,
-                                            double *myring, const TriLane &ln, int part, int rows_max,
+                                            double *myring, const TriLane &ln, bool top, int rows_max,
                                             bool with_sn, double c1, double c2, int *susp, int *susp_n,
                                             double &ss_out, double &sn_out, double &cnt_out) {
   const int lo = ln.lo, hi = ln.hi, cbase = ln.cbase;
-  const int t_emit0 = part == 0 ? 3 : 6;           // first iteration with a complete window
-  const int T = rows_max + (part == 0 ? 3 : 6);
-  int nv = np_ - cbase;
+  const int t_emit0 = top ? 3 : 6;           // first iteration with a complete window
+  const int T = rows_max + (top ? 3 : 6);
+  int nv = ln.cend - cbase;
   nv = nv < 0 ? 0 : (nv > G ? G : nv);
   unsigned xo[G];
   double ccnt[G];
@@ -535,7 +554,7 @@ __device__ __forceinline__ void tri_w7_part(const double *__restrict__ R, const 
 template <int G, int H>
 __device__ __forceinline__ void tri_win_part(const double *__restrict__ R, const double *__restrict__ Q, unsigned rp,
                                              unsigned qp, int n, int np_, int flip, const short *kmap,
-                                             double *myring, const TriLane &ln, int part, int rows_max,
+                                             double *myring, const TriLane &ln, bool top, int rows_max,
                                              bool with_sn, double c1, double c2, int *susp, int *susp_n,
                                              double &ss_out, double &sn_out, double &cnt_out) {
   static_assert(H >= 1 && H <= 5 && H != 3 && G >= H, "window 3 / 5 / 9 / 11");
@@ -543,9 +562,9 @@ __device__ __forceinline__ void tri_win_part(const double *__restrict__ R, const
   constexpr int WIN = 2 * H + 1;
   constexpr int D = WIN > 7 ? WIN : 7;          // ring depth in rows
   const int lo = ln.lo, hi = ln.hi, cbase = ln.cbase;
-  const int t_own0 = part == 0 ? 0 : HALO;      // iteration of the band's first own row
-  const int T = rows_max + (part == 0 ? HALO : 2 * HALO);
-  int nv = np_ - cbase;
+  const int t_own0 = top ? 0 : HALO;      // iteration of the band's first own row
+  const int T = rows_max + (top ? HALO : 2 * HALO);
+  int nv = ln.cend - cbase;
   nv = nv < 0 ? 0 : (nv > G ? G : nv);
   unsigned xo[G];
   double ccnt[G];
