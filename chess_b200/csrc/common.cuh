@@ -55,6 +55,7 @@ struct chess_item_args {
   double *ssim, *sn;
   int *status;
   int ncol_pad;               // columns reserved per pair in maps and records (max n, rounded to 32)
+  int max_n;                  // largest matrix of the batch, in bins
   int blocks;                 // block-triangle kernel: blocks per matrix side
   long long pair_items;       // triangle -r 1 kernel: leading pairs walked whole by one warp (set by its launcher)
   double *scratch;            // n_pairs * kBands * (kItemHdr + 2*ncol_pad)

@@ -5,14 +5,15 @@
 
 namespace {
 
-template <int G, int H>
-__global__ void __launch_bounds__(128, 2)
+// NW = warps per CTA: 4, or 1 for windows 9 / 11 (see compare_triw.cuh)
+template <int G, int H, int NW>
+__global__ void __launch_bounds__(32 * NW, (NW == 1 ? 1 : 2))
 compare_win_blk_kernel(chess_item_args a) {
   static_assert((H == 1 || H == 2 || H == 4 || H == 5) && G >= H, "window 3 / 5 / 9 / 11 (window 7 has its own kernel)");
   constexpr int HALO = H > 3 ? H : 3;           // halo rows / columns around a band: the wider of the two windows
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;  // ring depth in rows
-  __shared__ int s_susp[4][kSuspCap];
-  __shared__ int s_susp_n[4];
+  __shared__ int s_susp[NW][kSuspCap];
+  __shared__ int s_susp_n[NW];
   extern __shared__ __align__(16) double ringbuf[];  // per warp: D rows of x and y, D*2*G*32 doubles
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -21,9 +22,9 @@ compare_win_blk_kernel(chess_item_args a) {
   constexpr int RING = D * 2 * G * 32;
   double *myring = ringbuf + (size_t)warp * RING + lane;
   const int NCOL = a.ncol_pad;
-  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
-  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) +
-                                                          (size_t)4 * NCOL) + (size_t)warp * NCOL;
+  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)NW * RING) + (size_t)warp * NCOL;
+  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)NW * RING) +
+                                                          (size_t)NW * NCOL) + (size_t)warp * NCOL;
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
@@ -33,10 +34,10 @@ compare_win_blk_kernel(chess_item_args a) {
 
   // the first item of every warp is its own index: no storm of atomics on one counter when the grid
   // starts; later items come from the counter, offset by the number of warps
-  const long long n_warps = (long long)gridDim.x * 4;
+  const long long n_warps = (long long)gridDim.x * NW;
   bool first_item = true;
   while (true) {
-    long long item = (long long)blockIdx.x * 4 + warp;
+    long long item = (long long)blockIdx.x * NW + warp;
     if (!first_item) {
       if (lane == 0) item = n_warps + (long long)atomicAdd(a.counter_cur, 1ull);
       item = __shfl_sync(0xffffffffu, item, 0);
@@ -167,11 +168,12 @@ compare_win_blk_kernel(chess_item_args a) {
 
 template <int G, int H>
 int launch_blkw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  auto kern = compare_win_blk_kernel<G, H>;
+  constexpr int NW = H >= 4 ? 1 : 4;
+  auto kern = compare_win_blk_kernel<G, H, NW>;
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;
   constexpr int RING = D * 2 * G * 32;
-  const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
-  const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 1024 * 3;
+  const size_t smem = (size_t)NW * RING * sizeof(double) + (size_t)NW * a.ncol_pad * 3;
+  const size_t smem_max = (size_t)NW * RING * sizeof(double) + (size_t)NW * 1024 * 3;
   static bool configured[64] = {false};
   if (ctx->device >= 64 || !configured[ctx->device]) {
     CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -179,14 +181,14 @@ int launch_blkw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   }
   static int per_sm = 0, per_sm_ncol = -1;
   if (per_sm_ncol != a.ncol_pad) {
-    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NW, smem));
     if (per_sm < 1) per_sm = 1;
     per_sm_ncol = a.ncol_pad;
   }
   long long grid = (long long)ctx->sm_count * per_sm;
-  const long long need = (a.n_pairs * (a.blocks * (a.blocks + 1) / 2) + 3) / 4;
+  const long long need = (a.n_pairs * (a.blocks * (a.blocks + 1) / 2) + NW - 1) / NW;
   if (grid > need) grid = need;
-  kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  kern<<<(unsigned)grid, 32 * NW, smem, stream>>>(a);
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;

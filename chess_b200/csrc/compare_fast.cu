@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "compare_kernels.cuh"
+#include "tri_rows.cuh"
 
 namespace {
 
@@ -518,7 +519,16 @@ extern "C" int chess_band_prefix_build(chess_ctx *ctx, const double *band, int64
 // smallest strip width whose triangle split (compare_tri.cuh: tri_split) fits the warp, 0 if none
 static int tri_strip_width(int n, int halo = 3) {
   static const int g_env = getenv("CHESS_TRI_G") ? atoi(getenv("CHESS_TRI_G")) : 3;  // experiments only
+  static const int mono_env = getenv("CHESS_TRI_MONO") ? atoi(getenv("CHESS_TRI_MONO")) : 1;  // A/B runs
   const int g_min = g_env > halo ? g_env : halo;  // a window may reach into one neighbour lane only
+  // small matrices: the narrowest strip with which all three bands fit one warp side by side (tri_rows.cuh:
+  // tri_mode) -- one pass per pair instead of two items
+  if (mono_env) {
+    for (int G = g_min < 3 ? 3 : g_min; G <= 4; ++G) {
+      int b1, b2, l1, l2;
+      if (n <= 31 * G && tri_mode(n, G, b1, b2, l1, l2) == 1) return G;
+    }
+  }
   for (int G = g_min < 3 ? 3 : g_min; G <= 8; ++G) {
     if (n > 31 * G || n < 24) continue;
     const int x = (n - halo) / 3;
@@ -630,6 +640,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   a.ref_pre = ref->rowpre; a.qry_pre = qry->rowpre;
   a.p = p;
   a.ncol_pad = ncol_pad;
+  a.max_n = max_n;
   a.blocks = blk_nb;
   a.done = reinterpret_cast<int *>(base + head);
   a.scratch = reinterpret_cast<double *>(base + head + done_bytes);

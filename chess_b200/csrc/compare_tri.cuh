@@ -239,10 +239,13 @@ __device__ __forceinline__ bool tri_r1_run_part(const TriItem &it, int part, int
                                                 double *myring, int *susp, int *susp_n, bool minmax,
                                                 double (&tot)[7], double &vmax, double &vmin) {
   const int np_ = it.np_;
+  constexpr int HALO = WITH_SN ? 3 : 0;
   int B1, B2, L1, L2;
-  tri_split_aligned(np_, G, B1, B2, L1, L2);
-  const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, WITH_SN ? 3 : 0);
-  const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
+  const int mode = tri_mode(np_, G, B1, B2, L1, L2);
+  // part: 0 = band 0 (or the whole matrix), 1 = bands 1 and 2, 2 = all three bands in one pass (mode 1)
+  const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, HALO);
+  const int rows_max = part == 0 ? B1 : part == 1 ? (mode == 2 ? max(B2 - B1, np_ - B2) : 0)
+                                                  : max(B1, max(B2 - B1, np_ - B2) + HALO);
   TriPartSums ps;
 #pragma unroll
   for (int k = 0; k < 5; ++k) ps.T[k] = 0.0;
@@ -252,7 +255,7 @@ __device__ __forceinline__ bool tri_r1_run_part(const TriItem &it, int part, int
     if (lane == 0) *susp_n = 0;
     __syncwarp();
     tri_r1_part<G, WITH_SN>(it.R, it.Q, (unsigned)it.rp, (unsigned)it.qp, it.n, np_, it.flip, kmap, myring, ln,
-                            part == 0, rows_max, minmax, susp, susp_n, ps);
+                            part != 1, rows_max, minmax, susp, susp_n, ps);
     if (WITH_SN) {
       __syncwarp();
       const int ns = *susp_n;
@@ -271,7 +274,7 @@ __device__ __forceinline__ bool tri_r1_run_part(const TriItem &it, int part, int
           const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
                                       (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
           const double gq = sn_window_exact(it.R, it.Q, it.rp, it.qp, kmap, it.n, it.flip, rc, c, np_, cnt);
-          const int band_hi = part == 0 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
+          const int band_hi = rc < B1 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
           if (gq == gq) { ps.sn_sum += c >= band_hi ? gq + gq : gq; ps.sn_cnt += c >= band_hi ? 2.0 : 1.0; }
         }
       } else if (ns > kSuspCap) {
@@ -387,10 +390,12 @@ compare_r1_tri_kernel(chess_item_args a) {
     // and ONE routine (tri_r1_finish, not inlined) turns two records into the result: a pair gives the same
     // bits whichever way it ran
     bool overflow = false;
+    int tB1, tB2, tL1, tL2;
+    const bool mono = tri_mode(np_, G, tB1, tB2, tL1, tL2) == 1;   // all bands in one pass: the first part does it all
     for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
       double tot[7], vmax = -CUDART_INF, vmin = CUDART_INF;
-      overflow |= !tri_r1_run_part<G, WITH_SN>(it, part, lane, kmap, myring, susp, susp_n, inloop_minmax, tot, vmax,
-                                               vmin);
+      overflow |= !tri_r1_run_part<G, WITH_SN>(it, (mono && part == 0) ? 2 : part, lane, kmap, myring, susp, susp_n,
+                                               inloop_minmax, tot, vmax, vmin);
       double rt[5] = {0, 0, 0, 0, 0};     // first (part 0) / last (part 1) row totals for the 2x2 SSIM map (np even)
       if (m == 2) tri_edge_row(it, part, lane, kmap, rt);
       if (lane == 0) {
@@ -460,6 +465,8 @@ int launch_tri_impl(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   long long pair_items = !HYBRID ? 0 : (a.n_pairs >= 8 * slots ? a.n_pairs : (a.n_pairs / slots) * slots);
   if (pair_env == 0) pair_items = 0;
   if (pair_env == 1 && HYBRID) pair_items = a.n_pairs;
+  int b1, b2, l1, l2;
+  if (HYBRID && tri_mode(a.max_n, G, b1, b2, l1, l2) != 2) pair_items = a.n_pairs;  // one pass per pair: nothing to halve
   a.pair_items = pair_items;
   const long long need = (pair_items + 2 * (a.n_pairs - pair_items) + 3) / 4;
   if (grid > need) grid = need;

@@ -82,17 +82,19 @@ compare_win7_tri_kernel(chess_item_args a) {
 
     // ---- the parts of this item (tri_rows.cuh: bands cut at multiples of G, lane-uniform weights)
     int B1, B2, L1, L2;
-    tri_split_aligned(np_, G, B1, B2, L1, L2);
+    const int mode = tri_mode(np_, G, B1, B2, L1, L2);   // 1: all three bands in one pass (the first part does it all)
     double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
     bool overflow = false;
     const double c1 = C1 * 2401.0, c2 = C2 * 2401.0;
     for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
     if (lane == 0) *susp_n = 0;
     __syncwarp();
-    const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, 3);
-    const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
+    const int pcode = (mode == 1 && part == 0) ? 2 : part;
+    const TriLane ln = tri_lane(pcode, lane, G, np_, B1, B2, L1, L2, 3);
+    const int rows_max = pcode == 0 ? B1 : pcode == 1 ? (mode == 2 ? max(B2 - B1, np_ - B2) : 0)
+                                                      : max(B1, max(B2 - B1, np_ - B2) + 3);
     if (rows_max > 0) {
-      tri_w7_part<G>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, part == 0, rows_max, with_sn, c1, c2,
+      tri_w7_part<G>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, pcode != 1, rows_max, with_sn, c1, c2,
                      susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();
@@ -112,7 +114,7 @@ compare_win7_tri_kernel(chess_item_args a) {
             const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
                                         (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
             const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
-            const int band_hi = part == 0 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
+            const int band_hi = rc < B1 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
             if (gq == gq) { sn_sum += c >= band_hi ? gq + gq : gq; sn_cnt += c >= band_hi ? 2.0 : 1.0; }
           }
         } else if (ns > kSuspCap) {
@@ -216,6 +218,8 @@ int launch_tri7(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   static const int pair_env = getenv("CHESS_TRI_PAIR") ? atoi(getenv("CHESS_TRI_PAIR")) : -1;  // A/B runs
   if (pair_env == 0) pair_items = 0;
   if (pair_env == 1 && G <= 4) pair_items = a.n_pairs;
+  int b1, b2, l1, l2;
+  if (G <= 4 && tri_mode(a.max_n, G, b1, b2, l1, l2) != 2) pair_items = a.n_pairs;   // one pass per pair: nothing to halve
   a.pair_items = pair_items;
   const long long need = (pair_items + 2 * (a.n_pairs - pair_items) + 3) / 4;
   if (grid > need) grid = need;

@@ -8,15 +8,17 @@
 
 namespace {
 
-template <int G, int H>
-__global__ void __launch_bounds__(128, (G <= 4 ? 3 : 2))
+// NW = warps per CTA: 4, or 1 for windows 9 / 11, whose ring of 9 / 11 rows of x and y (32 / 39 KB per warp at 7
+// columns per lane) lets only ONE 4-warp CTA onto an SM -- one-warp CTAs pack 7 / 5 of them
+template <int G, int H, int NW>
+__global__ void __launch_bounds__(32 * NW, (NW == 1 ? 1 : (G <= 4 ? 3 : 2)))
 compare_win_tri_kernel(chess_item_args a) {
   static_assert((H == 1 || H == 2 || H == 4 || H == 5) && G >= H, "window 3 / 5 / 9 / 11 (window 7 has its own kernel)");
   constexpr int HALO = H > 3 ? H : 3;           // halo rows / columns around a band: the wider of the two windows
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;  // ring depth in rows
-  __shared__ int s_susp[4][kSuspCap];
-  __shared__ int s_susp_n[4];
-  __shared__ double s_part[4][4];   // per warp: totals of the parts of the current item (pair items)
+  __shared__ int s_susp[NW][kSuspCap];
+  __shared__ int s_susp_n[NW];
+  __shared__ double s_part[NW][4];   // per warp: totals of the parts of the current item (pair items)
   constexpr bool HYB = G <= 4;      // pair items only for the narrow strips (see compare_tri.cuh)
   extern __shared__ __align__(16) double ringbuf[];  // per warp: D rows of x and y, D*2*G*32 doubles
 
@@ -26,9 +28,9 @@ compare_win_tri_kernel(chess_item_args a) {
   constexpr int RING = D * 2 * G * 32;
   double *myring = ringbuf + (size_t)warp * RING + lane;
   const int NCOL = a.ncol_pad;
-  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) + (size_t)warp * NCOL;
-  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)4 * RING) +
-                                                          (size_t)4 * NCOL) + (size_t)warp * NCOL;
+  short *kmap = reinterpret_cast<short *>(ringbuf + (size_t)NW * RING) + (size_t)warp * NCOL;
+  unsigned char *mflag = reinterpret_cast<unsigned char *>(reinterpret_cast<short *>(ringbuf + (size_t)NW * RING) +
+                                                          (size_t)NW * NCOL) + (size_t)warp * NCOL;
   const chess_params &p = a.p;
   const double qnan = CUDART_NAN;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *a.counter_next = 0ull; *a.retry_next = 0; }
@@ -37,10 +39,10 @@ compare_win_tri_kernel(chess_item_args a) {
 
   // the first item of every warp is its own index: no storm of atomics on one counter when the grid
   // starts; later items come from the counter, offset by the number of warps
-  const long long n_warps = (long long)gridDim.x * 4;
+  const long long n_warps = (long long)gridDim.x * NW;
   bool first_item = true;
   while (true) {
-    long long item = (long long)blockIdx.x * 4 + warp;
+    long long item = (long long)blockIdx.x * NW + warp;
     if (!first_item) {
       if (lane == 0) item = n_warps + (long long)atomicAdd(a.counter_cur, 1ull);
       item = __shfl_sync(0xffffffffu, item, 0);
@@ -87,7 +89,7 @@ compare_win_tri_kernel(chess_item_args a) {
 
     // ---- the parts of this item (tri_rows.cuh: bands cut at multiples of G, lane-uniform weights)
     int B1, B2, L1, L2;
-    tri_split_aligned(np_, G, B1, B2, L1, L2);
+    const int mode = tri_mode(np_, G, B1, B2, L1, L2);   // 1: all three bands in one pass (the first part does it all)
     double sn_sum = 0.0, sn_cnt = 0.0, ss_sum = 0.0;
     bool overflow = false;
     constexpr double NP2 = (double)((2 * H + 1) * (2 * H + 1)) * (double)((2 * H + 1) * (2 * H + 1));
@@ -95,10 +97,12 @@ compare_win_tri_kernel(chess_item_args a) {
     for (int part = part0; part <= (PAIR ? 1 : part0); ++part) {
     if (lane == 0) *susp_n = 0;
     __syncwarp();
-    const TriLane ln = tri_lane(part, lane, G, np_, B1, B2, L1, L2, HALO);
-    const int rows_max = part == 0 ? B1 : max(B2 - B1, np_ - B2);
+    const int pcode = (mode == 1 && part == 0) ? 2 : part;
+    const TriLane ln = tri_lane(pcode, lane, G, np_, B1, B2, L1, L2, HALO);
+    const int rows_max = pcode == 0 ? B1 : pcode == 1 ? (mode == 2 ? max(B2 - B1, np_ - B2) : 0)
+                                                      : max(B1, max(B2 - B1, np_ - B2) + HALO);
     if (rows_max > 0) {
-      tri_win_part<G, H>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, part == 0, rows_max, with_sn, c1,
+      tri_win_part<G, H>(R, Q, (unsigned)rp, (unsigned)qp, n, np_, flip, kmap, myring, ln, pcode != 1, rows_max, with_sn, c1,
                          c2, susp, susp_n, ss_sum, sn_sum, sn_cnt);
       if (with_sn) {
         __syncwarp();
@@ -118,7 +122,7 @@ compare_win_tri_kernel(chess_item_args a) {
             const double cnt = (double)((min(rc + 3, np_ - 1) - max(rc - 3, 0) + 1) *
                                         (min(c + 3, np_ - 1) - max(c - 3, 0) + 1));
             const double gq = sn_window_exact(R, Q, rp, qp, kmap, n, flip, rc, c, np_, cnt);
-            const int band_hi = part == 0 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
+            const int band_hi = rc < B1 ? B1 : (rc < B2 ? B2 : np_);  // end of the row's diagonal block
             if (gq == gq) { sn_sum += c >= band_hi ? gq + gq : gq; sn_cnt += c >= band_hi ? 2.0 : 1.0; }
           }
         } else if (ns > kSuspCap) {
@@ -200,11 +204,12 @@ compare_win_tri_kernel(chess_item_args a) {
 
 template <int G, int H>
 int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  auto kern = compare_win_tri_kernel<G, H>;
+  constexpr int NW = H >= 4 ? 1 : 4;
+  auto kern = compare_win_tri_kernel<G, H, NW>;
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;
   constexpr int RING = D * 2 * G * 32;
-  const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
-  const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 256 * 3;
+  const size_t smem = (size_t)NW * RING * sizeof(double) + (size_t)NW * a.ncol_pad * 3;
+  const size_t smem_max = (size_t)NW * RING * sizeof(double) + (size_t)NW * 256 * 3;
   static bool configured[64] = {false};
   if (ctx->device >= 64 || !configured[ctx->device]) {
     CHESS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -212,21 +217,23 @@ int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   }
   static int per_sm = 0, per_sm_ncol = -1;
   if (per_sm_ncol != a.ncol_pad) {
-    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    CHESS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NW, smem));
     if (per_sm < 1) per_sm = 1;
     per_sm_ncol = a.ncol_pad;
   }
   long long grid = (long long)ctx->sm_count * per_sm;
   // narrow strips: whole waves of pairs run as pair items (compare_tri.cuh: launch_tri)
-  const long long slots = grid * 4;
+  const long long slots = grid * NW;
   long long pair_items = G > 4 ? 0 : (a.n_pairs >= 8 * slots ? a.n_pairs : (a.n_pairs / slots) * slots);
   static const int pair_env = getenv("CHESS_TRI_PAIR") ? atoi(getenv("CHESS_TRI_PAIR")) : -1;  // A/B runs
   if (pair_env == 0) pair_items = 0;
   if (pair_env == 1 && G <= 4) pair_items = a.n_pairs;
+  int b1, b2, l1, l2;
+  if (G <= 4 && tri_mode(a.max_n, G, b1, b2, l1, l2) != 2) pair_items = a.n_pairs;   // one pass per pair: nothing to halve
   a.pair_items = pair_items;
-  const long long need = (pair_items + 2 * (a.n_pairs - pair_items) + 3) / 4;
+  const long long need = (pair_items + 2 * (a.n_pairs - pair_items) + NW - 1) / NW;
   if (grid > need) grid = need;
-  kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  kern<<<(unsigned)grid, 32 * NW, smem, stream>>>(a);
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;

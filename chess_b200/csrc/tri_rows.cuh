@@ -98,6 +98,18 @@ __device__ __forceinline__ void pin_before_loads(const unsigned (&v)[G]) {
   for (int g = 0; g < G; ++g) asm volatile("" ::"r"(v[g]));
 }
 
+// How a pair is walked: 0 = one band (too small to cut), 1 = all three bands side by side in ONE pass of one warp
+// (small matrices: band 0 on lanes [0, L), an idle lane, band 1, an idle lane, band 2 -- half as many warp-rows as
+// two parts, no records to combine), 2 = two parts (item A = band 0, item B = bands 1 and 2).
+__host__ __device__ __forceinline__ int tri_mode(int np_, int G, int &B1, int &B2, int &L1, int &L2) {
+  if (!tri_split_aligned(np_, G, B1, B2, L1, L2)) return 0;
+  const int L = (np_ + G - 1) / G;
+  // strips of up to 4 columns only (16 warps per SM): measured at 81 bins, one pass of 7-column strips at 8 warps
+  // per SM loses to two parts of 3-column strips (3.6 against 2.9 ms per 100 k pairs); at 41 bins one pass of
+  // 4-column strips wins (1.59 against 1.76 ms)
+  return (G <= 4 && L + 1 + L1 + 1 + L2 <= 31) ? 1 : 2;
+}
+
 // Geometry of one lane in one part of a pair.
 struct TriLane {
   int lo, hi;      // rows of the lane's band
@@ -113,10 +125,17 @@ __device__ __forceinline__ TriLane tri_lane(int part, int lane, int G, int np_, 
   g.lo = 0; g.hi = 0; g.cbase = 1 << 20;
   if (part == 0) {
     g.lo = 0; g.hi = B1; g.cbase = G * lane;
-  } else if (lane < L1) {
-    g.lo = B1; g.hi = B2; g.cbase = B1 - G + G * lane;
-  } else if (lane > L1 && lane <= L1 + L2) {
-    g.lo = B2; g.hi = np_; g.cbase = B2 - G + G * (lane - L1 - 1);
+  } else {
+    // part 1: bands 1 and 2 from lane 0; part 2 (all bands in one pass): behind band 0 and an idle lane
+    const int base = part == 2 ? (np_ + G - 1) / G + 1 : 0;
+    const int l = lane - base;
+    if (part == 2 && lane < base - 1) {
+      g.lo = 0; g.hi = B1; g.cbase = G * lane;
+    } else if (l >= 0 && l < L1) {
+      g.lo = B1; g.hi = B2; g.cbase = B1 - G + G * l;
+    } else if (l > L1 && l <= L1 + L2) {
+      g.lo = B2; g.hi = np_; g.cbase = B2 - G + G * (l - L1 - 1);
+    }
   }
   g.first = g.lo - halo < 0 ? 0 : g.lo - halo;
   g.cend = np_;
