@@ -1128,7 +1128,8 @@ def measure_synthetic(local_rank, n=100, pool=1000):
         for rel in S.distinct_windows(n):
             win = S.window_size(n, rel)
             prm = _native.make_params(absolute_window_size=win, min_bins=0, keep_unmappable_bins=True,
-                                      mappability_cutoff=0.0, compute_sn=False, data_range=2.0)
+                                      mappability_cutoff=0.0, compute_sn=False, data_range=2.0,
+                                      flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES)
             best = None
             for rep in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1157,7 +1158,8 @@ def measure_synthetic(local_rank, n=100, pool=1000):
         cpu_s = (time.perf_counter() - t0) / k
         dev_rel = float(np.max(np.abs(control[:k] - want) / np.abs(want)))
     return {"what": "configs[0]: one dense O/E reference vs truth + %d decoys, %d bins, SSIM only, data_range 2.0 "
-                    "(utils/run_synthetic_test.py:97-121), generic kernel" % (pool, n),
+                    "(utils/run_synthetic_test.py:97-121); windows 7 and 9 on the upper-triangle kernels (symmetric "
+                    "matrices), larger windows on the generic kernel" % (pool, n),
             "pairs_per_launch": P, "device": rows, "gpu_launches": launches,
             "e2e": {"windows": len(rels), "pairs_per_s": P * len(rels) / e2e_s, "seconds": e2e_s,
                     "h2d_bytes": int((P + 1) * n * n * 8), "d2h_bytes": int(P * 8 * len(rels)),

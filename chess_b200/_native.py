@@ -115,6 +115,7 @@ SIGNATURES = {
     "chess_sparse_text_compact": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                             C.POINTER(C.c_int64), _vp]),
     "chess_log_ratio_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "chess_background_regions": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "chess_background_batch": (C.c_int, [_vp, _SP, _SP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _PP,
                                          _vp, _vp, _vp, _vp]),
 }

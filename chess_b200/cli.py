@@ -235,6 +235,20 @@ def _background_spans_from_query(query_regions, query_trees, query_region, limit
             np.tile(np.array([0, 1], dtype=np.int32), len(rows)))
 
 
+def _background_set_from_query(query_regions, query_trees, query_region, limit_background):
+    """The same set, enumerated and looked up on the GPU (engine.QueryBackgroundSet) when the regions are a regular
+    RegionTable; otherwise the host columns above.  Returns what CompareEngine.background takes as
+    (bg_first, bg_n, bg_strand)."""
+    from .engine import QueryBackgroundSet
+    from .helpers import RegionTable
+    if isinstance(query_regions, RegionTable):
+        bg = QueryBackgroundSet(query_regions, query_region.end - query_region.start,
+                                query_region.chromosome if limit_background else None)
+        if bg.ok:
+            return bg, None, None
+    return _background_spans_from_query(query_regions, query_trees, query_region, limit_background)
+
+
 def run_sim(args):
     """Body of `chess sim` (bin/chess:80-359) on the batched engine."""
     from .engine import CompareEngine, region_spans, visible_devices
@@ -369,8 +383,8 @@ def run_sim(args):
                 bf, bn = region_spans(query_trees, background_regions)
                 bstrand = np.array([strand_code(r.strand) for r in background_regions], dtype=np.int32)
             else:
-                bf, bn, bstrand = _background_spans_from_query(query_regions, query_trees, pairs[int(ks[0])][2],
-                                                               args.limit_background)
+                bf, bn, bstrand = _background_set_from_query(query_regions, query_trees, pairs[int(ks[0])][2],
+                                                             args.limit_background)
             z, pv = engine.background(rf[ks], rn[ks], ref_strand[ks], np.asarray(ssim)[ks], bf, bn, bstrand,
                                       own=(qf[ks], qn[ks], qry_strand[ks]), **params)
             z_bg[ks] = z

@@ -103,10 +103,23 @@ extern "C" int chess_compare_batch(chess_ctx *ctx, const double *ref_base, const
   if (n_pairs == 0) return CHESS_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (params->kernel != 1 && params->data_range == 0.0) {   // a fixed data range is the generic kernel's
+  if (params->kernel != 1 && params->data_range == 0.0) {   // a fixed data range is the generic kernel's ...
     bool handled = false;
     rc = chess_launch_compare_fast(ctx, ref_base, qry_base, pairs, n_pairs, max_n, *params, ssim, sn,
                                    status, stream, &handled);
+    if (rc) return rc;
+    if (handled) return CHESS_OK;
+  }
+  if (params->kernel == 0 && params->data_range > 0.0 && (params->flags & CHESS_FLAG_SYMMETRIC) &&
+      (params->flags & CHESS_FLAG_EQUAL_SIZES) && !(params->mappability_cutoff > 0)) {
+    // ... except for symmetric, equal-sized matrices without masks (the dense one-vs-many batches of
+    // utils/run_synthetic_test.py): they are views like any band view, and the triangle / block kernels need
+    // nothing of a sample but its base pointer then
+    chess_sample rs = {}, qs = {};
+    rs.band = ref_base; qs.band = qry_base;
+    bool handled = false;
+    rc = chess_launch_compare_items(ctx, &rs, &qs, pairs, n_pairs, max_n, *params, ssim, sn, status, stream,
+                                    &handled);
     if (rc) return rc;
     if (handled) return CHESS_OK;
   }

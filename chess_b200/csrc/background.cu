@@ -36,6 +36,66 @@ bg_table_kernel(const int64_t *__restrict__ ref_first, const int32_t *__restrict
   }
 }
 
+// Background regions generated from the query bins (bin/chess:272-298): every bin start x {+, -} with the size of
+// the pair's query region, kept where it ends inside its chromosome (and, with --limit-background, lies on the
+// pair's chromosome).  One thread per bin decides and looks the region up -- the bins that overlap
+// [start - 1, start + size) in the half-open sense of chess/helpers.py:212-242, by two bisections inside the
+// bin's chromosome (bins sorted and contiguous per chromosome) -- then a single-CTA scan packs the kept regions
+// in bin order, '+' before '-', exactly the order of the reference's list.
+__global__ void __launch_bounds__(256)
+bg_candidates_kernel(const int64_t *__restrict__ bin_begin, const int64_t *__restrict__ bin_end,
+                     const int32_t *__restrict__ bin_chrom, const int64_t *__restrict__ chrom_first,
+                     const int64_t *__restrict__ chrom_end_bp, long long n_bins, long long size, int limit_chrom,
+                     int64_t *__restrict__ first, int32_t *__restrict__ count, unsigned char *__restrict__ keep) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_bins) return;
+  const int c = bin_chrom[i];
+  const long long start = bin_begin[i] + 1;           // region = [start, start + size], looked up as [start-1, end)
+  const bool ok = (limit_chrom < 0 || c == limit_chrom) && start + size <= chrom_end_bp[c];
+  keep[i] = ok ? 1 : 0;
+  if (!ok) return;
+  const long long qb = start - 1, qe = start + size;
+  long long lo = chrom_first[c], hi = chrom_first[c + 1];
+  // first bin whose end > qb
+  long long a = lo, b = hi;
+  while (a < b) { const long long m = (a + b) >> 1; if (bin_end[m] > qb) b = m; else a = m + 1; }
+  const long long f = a;
+  // last bin whose begin < qe
+  a = lo; b = hi;
+  while (a < b) { const long long m = (a + b) >> 1; if (bin_begin[m] < qe) a = m + 1; else b = m; }
+  const long long l = a - 1;
+  first[i] = f <= l ? f : -1;
+  count[i] = f <= l ? (int32_t)(l - f + 1) : 0;
+}
+
+__global__ void __launch_bounds__(1024)
+bg_pack_kernel(const int64_t *__restrict__ first, const int32_t *__restrict__ count,
+               const unsigned char *__restrict__ keep, long long n_bins, int64_t *__restrict__ out_first,
+               int32_t *__restrict__ out_n, int32_t *__restrict__ out_strand, long long *__restrict__ n_out) {
+  __shared__ long long sh[1024];
+  const long long per = (n_bins + 1023) / 1024;
+  const long long lo = per * threadIdx.x, hi = lo + per < n_bins ? lo + per : n_bins;
+  long long s = 0;
+  for (long long i = lo; i < hi; ++i) s += keep[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < 1024; ++t) { const long long v = sh[t]; sh[t] = run; run += v; }
+    *n_out = 2 * run;
+  }
+  __syncthreads();
+  long long run = sh[threadIdx.x];
+  for (long long i = lo; i < hi; ++i) {
+    if (keep[i]) {
+      out_first[2 * run] = first[i]; out_first[2 * run + 1] = first[i];
+      out_n[2 * run] = count[i]; out_n[2 * run + 1] = count[i];
+      out_strand[2 * run] = 0; out_strand[2 * run + 1] = 1;      // '+', then '-'
+      run += 1;
+    }
+  }
+}
+
 __device__ __forceinline__ double block_sum(double v, double *red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_sum(v);
@@ -112,6 +172,36 @@ bg_stats_kernel(const double *__restrict__ vals, const int32_t *__restrict__ sta
 }
 
 }  // namespace
+
+extern "C" int chess_background_regions(chess_ctx *ctx, const int64_t *bin_begin, const int64_t *bin_end,
+                                        const int32_t *bin_chrom, const int64_t *chrom_first,
+                                        const int64_t *chrom_end_bp, int64_t n_bins, int64_t size,
+                                        int32_t limit_chrom, int64_t *bg_first, int32_t *bg_n, int32_t *bg_strand,
+                                        int64_t *n_regions, void *workspace, void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (n_bins < 0 || (n_bins > 0 && (!bin_begin || !bin_end || !bin_chrom || !chrom_first || !chrom_end_bp ||
+                                    !bg_first || !bg_n || !bg_strand || !workspace)) || !n_regions) {
+    ctx->err = "chess_background_regions: bad arguments";
+    return CHESS_ERR_ARG;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  // workspace: first int64[n_bins] | count int32[n_bins] | keep u8[n_bins]  (13 bytes per bin)
+  int64_t *first = reinterpret_cast<int64_t *>(workspace);
+  int32_t *count = reinterpret_cast<int32_t *>(first + n_bins);
+  unsigned char *keep = reinterpret_cast<unsigned char *>(count + n_bins);
+  if (n_bins > 0) {
+    bg_candidates_kernel<<<(unsigned)((n_bins + 255) / 256), 256, 0, stream>>>(
+        bin_begin, bin_end, bin_chrom, chrom_first, chrom_end_bp, (long long)n_bins, (long long)size, limit_chrom,
+        first, count, keep);
+    ctx->launches += 1;
+  }
+  bg_pack_kernel<<<1, 1024, 0, stream>>>(first, count, keep, (long long)n_bins, bg_first, bg_n, bg_strand,
+                                         reinterpret_cast<long long *>(n_regions));
+  ctx->launches += 1;
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
 
 extern "C" int chess_background_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
                                       const int64_t *ref_first, const int32_t *ref_n,

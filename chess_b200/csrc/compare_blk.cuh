@@ -72,9 +72,11 @@ compare_r1_blk_kernel(chess_item_args a) {
 
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, mflag, xmax, xmin);  // rare in aligned samples, common against
+    const bool fixed_range = p.data_range > 0.0;     // chess_params.data_range: no look-up, no scan
+    const bool inloop_minmax = !fixed_range && tri_extrema(a, it, lane, mflag, xmax, xmin);  // rare in aligned samples, common against
                                                                       // background regions (a bin masked on one side)
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
+    if (fixed_range) { xmax = p.data_range; xmin = 0.0; }
 
     // ---- this item's block (bi, bj), bj >= bi, of nb x nb square blocks of the compacted pair (tri_rows.cuh:
     // blk_lane): `side` rows, a multiple of the strip width, so that every lane is block or halo as a whole

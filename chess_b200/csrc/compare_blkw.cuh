@@ -64,7 +64,8 @@ compare_win_blk_kernel(chess_item_args a) {
     // ---- data range from the running extrema, else min / max from the data
     double xmax, xmin;
     // C1 / C2 are needed before the first window: the rare data scan runs up front
-    if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    if (p.data_range > 0.0) { xmax = p.data_range; xmin = 0.0; }   // fixed range (chess_params.data_range): no look-up
+    else if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
 

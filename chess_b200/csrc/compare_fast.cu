@@ -552,13 +552,21 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
     H = (w - 1) / 2;
   }
   // windows 3 / 5 / 7 have a full-square and a triangle kernel, 9 / 11 the triangle kernel only
-  const bool windowed = p.abs_window > 0 && H >= 1 && H <= 5 && ref->pmax && ref->pmin && qry->pmax && qry->pmin;
+  // a sample without index arrays (dense matrices handed to chess_compare_batch) can still take the tuned
+  // kernels when it needs none of them: no masks to predict or verify (mappability_cutoff <= 0, chess/sim.py:336)
+  // and a fixed data range (chess_params.data_range) -- the dense one-vs-many batches of BASELINE configs[0]
+  const bool no_masks = !(p.mappability_cutoff > 0);
+  const bool have_index = ref->nd_lo && ref->nd_hi && qry->nd_lo && qry->nd_hi;
+  const bool have_pm = ref->pmax && ref->pmin && qry->pmax && qry->pmin;
+  const bool have_pre = ref->rowpre && qry->rowpre;
+  const bool bare = no_masks && p.data_range > 0.0 && (p.flags & CHESS_FLAG_SYMMETRIC);
+  const bool windowed = p.abs_window > 0 && H >= 1 && H <= 5 && (have_pm || bare);
   const bool plain_default = p.default_value == 1.0 || p.default_value == 0.0;
   // unequal-sized pairs would all bounce to the generic kernel: leave such batches to the other paths
   if (!(r1 || windowed) || !plain_default || max_n > 1024 ||
-      !(p.flags & (CHESS_FLAG_EQUAL_SIZES | CHESS_FLAG_MOSTLY_EQUAL_SIZES)) || !ref->nd_lo ||
-      !ref->nd_hi || !qry->nd_lo || !qry->nd_hi)
+      !(p.flags & (CHESS_FLAG_EQUAL_SIZES | CHESS_FLAG_MOSTLY_EQUAL_SIZES)) || !(have_index || bare))
     return CHESS_OK;
+  if (!bare && p.data_range > 0.0) return CHESS_OK;   // a fixed range on indexed samples: generic kernel, as before
   // column-strip width: the narrowest strip that holds the matrix in one block; wider matrices are
   // swept in blocks of 31*G - 6 columns, with the width that wastes the fewest lane-columns
   int G = 8;
@@ -574,14 +582,14 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   }
   // -r 1 over the upper triangle when both samples carry their row prefix sums (kernel = 3 keeps the
   // full-square walk for A/B runs)
-  const int tri_G = ((r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre)
+  const int tri_G = ((r1 || windowed) && p.kernel != 3 && (have_pre || bare))
                         ? tri_strip_width(max_n, H > 3 ? H : 3) : 0;
   const bool tri = tri_G != 0;
   if (tri) G = tri_G;
   // -r 1 on matrices wider than one warp: square blocks on and above the diagonal; strip width and block
   // count that cost the fewest lane-columns (blocks x rows per block x strip width)
   int blk_nb = 0;
-  if (!tri && (r1 || windowed) && p.kernel != 3 && ref->rowpre && qry->rowpre && max_n > 93) {
+  if (!tri && (r1 || windowed) && p.kernel != 3 && (have_pre || bare) && max_n > 93) {
     // blocks of `side` rows, a multiple of the strip width and at most 29 strips (one halo lane either side and
     // an idle lane for the neighbour exchange to wrap onto): cost = items x rows per item x strip width
     long best = -1;
@@ -596,6 +604,7 @@ int chess_launch_compare_items(chess_ctx *ctx, const chess_sample *ref, const ch
   }
   const bool blk = blk_nb != 0;
   if (H > 3 && !tri && !blk) return CHESS_OK;  // windows 9 / 11 have no full-square kernel: generic
+  if (bare && !tri && !blk) return CHESS_OK;   // the full-square work-item kernels need the index arrays
   const int ipp = tri ? 2 : blk ? blk_nb * (blk_nb + 1) / 2 : kBands;  // work items (records) per pair
   const int ncol_pad = ((max_n + 31) / 32) * 32;
   const size_t stride = (tri || blk) ? (size_t)16 : items_stride(ncol_pad);

@@ -383,8 +383,10 @@ compare_r1_tri_kernel(chess_item_args a) {
     // ---- data range from the running extrema, else min / max from the data (rare in aligned samples, common
     // against background regions: a bin masked on one side)
     double xmax, xmin;
-    const bool inloop_minmax = tri_extrema(a, it, lane, mflag, xmax, xmin);
+    const bool fixed_range = a.p.data_range > 0.0;   // chess_params.data_range: no look-up, no scan
+    const bool inloop_minmax = !fixed_range && tri_extrema(a, it, lane, mflag, xmax, xmin);
     if (inloop_minmax) { xmax = -CUDART_INF; xmin = CUDART_INF; }   // neutral for an item without rows
+    if (fixed_range) { xmax = a.p.data_range; xmin = 0.0; }
 
     // every part ends in a record -- in shared memory for a pair item, in the scratch array for a half item --
     // and ONE routine (tri_r1_finish, not inlined) turns two records into the result: a pair gives the same

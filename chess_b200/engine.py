@@ -443,6 +443,64 @@ def build_pair_table(ref_first, ref_n, ref_w, qry_first, qry_n, qry_w, flip):
     return tab
 
 
+class QueryBackgroundSet(object):
+    """The background regions `chess sim --background-query` derives from the query bins (bin/chess:272-298) for
+    one region size [and chromosome], enumerated and looked up ON THE DEVICE (chess_background_regions): per GPU
+    that asks, (first_bin, n_bins, strand code) tensors in the reference's order.  Needs a RegionTable whose bins
+    are sorted and contiguous per chromosome (any BED that `chess pairs` / a matrix goes with)."""
+
+    def __init__(self, table, size, limit_chromosome=None):
+        self.table, self.size = table, int(size)
+        codes = np.asarray(table.chrom_codes)
+        change = np.flatnonzero(np.diff(codes)) + 1 if len(codes) else np.zeros(0, dtype=np.int64)
+        firsts = np.concatenate([[0], change]).astype(np.int64) if len(codes) else np.zeros(0, dtype=np.int64)
+        runs = codes[firsts] if len(codes) else codes
+        self.ok = len(set(runs.tolist())) == len(runs) and bool(np.array_equal(table.ixs, np.arange(len(table)))) \
+            and all(bool(np.all(np.diff(table.starts[a:b]) > 0) and np.all(np.diff(table.ends[a:b]) >= 0))
+                    for a, b in zip(firsts, list(firsts[1:]) + [len(codes)]))
+        self.run_of_code = {int(c): k for k, c in enumerate(runs)}
+        self.chrom_first = np.concatenate([firsts, [len(codes)]]).astype(np.int64)
+        self.bin_run = np.repeat(np.arange(len(firsts), dtype=np.int32), np.diff(self.chrom_first))
+        ends = np.zeros(len(firsts), dtype=np.int64)
+        if len(codes):
+            np.maximum.at(ends, self.bin_run, table.ends)
+        self.chrom_end = ends
+        if limit_chromosome is None:
+            self.limit = -1
+        elif limit_chromosome in table.chrom_names and table.chrom_names.index(limit_chromosome) in self.run_of_code:
+            self.limit = self.run_of_code[table.chrom_names.index(limit_chromosome)]
+        else:
+            self.limit = len(firsts)          # a chromosome the query does not have: no region at all
+        self._dev = {}
+
+    def on(self, device):
+        """(d_first int64, d_n int32, d_strand int32) on ``device``."""
+        device = int(device)
+        if device not in self._dev:
+            t = self.table
+            ctx = get_context(device)
+            dev = torch.device("cuda", device)
+            n = len(t)
+            with torch.cuda.device(dev):
+                up = [torch.from_numpy(np.array(a)).to(dev) for a in
+                      (t.starts - 1, t.ends, self.bin_run, self.chrom_first, self.chrom_end)]
+                d_first = torch.empty(2 * n, dtype=torch.int64, device=dev)
+                d_n = torch.empty(2 * n, dtype=torch.int32, device=dev)
+                d_strand = torch.empty(2 * n, dtype=torch.int32, device=dev)
+                d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+                ws = torch.empty(13 * max(n, 1), dtype=torch.uint8, device=dev)
+                check(lib.chess_background_regions(ctx.handle, _ptr(up[0]), _ptr(up[1]), _ptr(up[2]), _ptr(up[3]),
+                                                   _ptr(up[4]), n, self.size, self.limit, _ptr(d_first), _ptr(d_n),
+                                                   _ptr(d_strand), _ptr(d_count), _ptr(ws), _stream_ptr(dev)),
+                      ctx.handle, "chess_background_regions")
+                m = int(d_count.cpu()[0])
+            self._dev[device] = (d_first[:m], d_n[:m], d_strand[:m])
+        return self._dev[device]
+
+    def host(self, device):
+        return tuple(a.cpu().numpy() for a in self.on(device))
+
+
 class CompareEngine(object):
     """Batched replacement for the worker pool of bin/chess:189-225.
 
@@ -558,6 +616,11 @@ class CompareEngine(object):
         ref_n = np.ascontiguousarray(ref_n, dtype=np.int32)
         ref_strand = np.ascontiguousarray(ref_strand, dtype=np.int32)
         pair_ssim = np.ascontiguousarray(pair_ssim, dtype=np.float64)
+        bg_set = bg_first if isinstance(bg_first, QueryBackgroundSet) else None
+        if bg_set is not None:          # regions enumerated on the device; the host only needs their bin counts
+            bg_n = bg_set.on(self.devices[0])[1].cpu().numpy()
+            bg_first = np.zeros(0, dtype=np.int64)
+            bg_strand = np.zeros(0, dtype=np.int32)
         bg_first = np.ascontiguousarray(bg_first, dtype=np.int64)
         bg_n = np.ascontiguousarray(bg_n, dtype=np.int32)
         bg_strand = np.ascontiguousarray(bg_strand, dtype=np.int32)
@@ -570,7 +633,8 @@ class CompareEngine(object):
         if total == 0:
             return z_bg, p_bg
         self.ref.check_span(ref_first, ref_n, "reference region")
-        self.qry.check_span(bg_first, bg_n, "background region")
+        if bg_set is None:
+            self.qry.check_span(bg_first, bg_n, "background region")
         if own is not None:
             self.qry.check_span(own[0], own[1], "query region")
         max_n = int(max(ref_n.max(), bg_n.max() if len(bg_n) else 1, 1))
@@ -603,7 +667,9 @@ class CompareEngine(object):
                 rw, rband, rsample = self.ref.sample_on(device, max_n, default_value)
                 qw, qband, qsample = self.qry.sample_on(device, max_n, default_value)
                 up = [torch.from_numpy(a).to(dev) for a in (ref_first[lo:hi], ref_n[lo:hi], ref_strand[lo:hi],
-                                                            pair_ssim[lo:hi], bg_first, bg_n, bg_strand)]
+                                                            pair_ssim[lo:hi])]
+                up += list(bg_set.on(device)) if bg_set is not None else \
+                    [torch.from_numpy(a).to(dev) for a in (bg_first, bg_n, bg_strand)]
                 d_z = torch.empty(hi - lo, dtype=torch.float64, device=dev)
                 d_p = torch.empty(hi - lo, dtype=torch.float64, device=dev)
                 d_exc = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -614,7 +680,7 @@ class CompareEngine(object):
                     o0 = o1 = o2 = None
                 check(lib.chess_background_batch(ctx.handle, C.byref(rsample), C.byref(qsample), _ptr(up[0]),
                                                  _ptr(up[1]), _ptr(up[2]), o0, o1, o2, _ptr(up[3]), hi - lo, _ptr(up[4]),
-                                                 _ptr(up[5]), _ptr(up[6]), len(bg_first), max_n, C.byref(p),
+                                                 _ptr(up[5]), _ptr(up[6]), len(bg_n), max_n, C.byref(p),
                                                  _ptr(d_z), _ptr(d_p), _ptr(d_exc), _stream_ptr(dev)),
                       ctx.handle, "chess_background_batch")
             pending.append((dev, lo, hi, d_z, d_p, d_exc, up))
@@ -671,7 +737,7 @@ class CompareEngine(object):
         return ids, ssim, sn, status
 
 
-def compare_dense_pairs(references, queries, flips, device=None, default_value=1, **params):
+def compare_dense_pairs(references, queries, flips, device=None, default_value=1, symmetric=False, **params):
     """Compare already-dense matrix pairs (lists of square float64 arrays).
 
     The matrices are packed back to back in one device buffer per side and
@@ -706,6 +772,9 @@ def compare_dense_pairs(references, queries, flips, device=None, default_value=1
     for k, (r, q) in enumerate(zip(references, queries)):
         tab[k] = (r_offs[k], q_offs[k], r.shape[0], q.shape[0], r.shape[0], q.shape[0], 1 if flips[k] else 0, 0)
     max_n = int(max([r.shape[0] for r in references] + [q.shape[0] for q in queries] + [1]))
+    if symmetric:       # the caller vouches for symmetric matrices: the upper-triangle kernels may take the batch
+        params["flags"] = params.get("flags", 0) | _native.FLAG_SYMMETRIC | (
+            _native.FLAG_EQUAL_SIZES if len({m.shape[0] for m in list(references) + list(queries)}) == 1 else 0)
     p = _native.make_params(default_value=default_value, **params)
     ssim = np.empty(n_pairs)
     sn = np.empty(n_pairs)

@@ -67,8 +67,10 @@ def truth_and_controls(reference, query, pool, rel_window, data_range=2.0, devic
     """
     n = max([reference.shape[0], query.shape[0]] + [t.shape[0] for t in pool])
     queries = [query] + list(pool)
+    # symmetric matrices of one size (what the script generates) may take the upper-triangle kernels
+    symmetric = all(m.shape == (n, n) and np.array_equal(m, m.T) for m in [reference] + queries)
     ssim, _, _ = compare_dense_pairs([reference] * len(queries), queries, [0] * len(queries), device=device,
-                                     **_params(n, rel_window, data_range))
+                                     symmetric=symmetric, **_params(n, rel_window, data_range))
     truth, control = float(ssim[0]), ssim[1:]
     p = float(np.sum(control >= truth)) / max(len(pool), 1)
     allv = np.concatenate([control, [truth]])
@@ -91,6 +93,8 @@ class OneVsMany(object):
         if any(m.shape != (self.n, self.n) for m in [reference] + mats):
             raise ValueError("OneVsMany expects square matrices of one size")
         self.n_pool = len(pool)
+        # Hi-C matrices are symmetric; when every matrix of the batch is (checked, not assumed), the batch may take
+        # the upper-triangle kernels (CHESS_FLAG_SYMMETRIC): they need nothing of a dense matrix but its pointer
         dev = torch.device("cuda", self.device)
         self.ctx = get_context(self.device)
         n2 = self.n * self.n
@@ -100,6 +104,10 @@ class OneVsMany(object):
             for k, m in enumerate(mats):
                 self.d_pool[k * n2:(k + 1) * n2] = torch.from_numpy(
                     np.ascontiguousarray(m, dtype=np.float64).ravel()).to(dev, non_blocking=True)
+            # (the comparison runs where the matrices already are: one pass over the uploaded buffers)
+            pool3 = self.d_pool.view(len(mats), self.n, self.n)
+            ref2 = self.d_ref.view(self.n, self.n)
+            self.symmetric = bool(torch.equal(pool3, pool3.transpose(1, 2)) and torch.equal(ref2, ref2.t()))
             tab = np.zeros(len(mats), dtype=PAIR_DTYPE)
             for k in range(len(mats)):
                 tab[k] = (0, k * n2, self.n, self.n, self.n, self.n, 0, 0)
@@ -111,7 +119,8 @@ class OneVsMany(object):
         """(truth_ssim, control_ssim, p, z) for one relative window (run_synthetic_test.py:105-115)."""
         dev = torch.device("cuda", self.device)
         P = self.P
-        p = _native.make_params(**_params(self.n, rel_window, data_range))
+        flags = (_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES) if self.symmetric else 0
+        p = _native.make_params(flags=flags, **_params(self.n, rel_window, data_range))
         base = self.d_res.data_ptr()
         with torch.cuda.device(dev):
             check(lib.chess_compare_batch(self.ctx.handle, _ptr(self.d_ref), _ptr(self.d_pool), _ptr(self.d_tab), P,

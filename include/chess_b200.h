@@ -267,6 +267,20 @@ int chess_zscore(chess_ctx *ctx, const double *ssim, int64_t n, double *z, void 
  * their results and the reductions never leave the device.  n_exceeds (nullable) receives the
  * number of comparisons whose window exceeds the compacted matrix -- where skimage raises and the
  * reference run aborts.  params->compute_sn is ignored.  All pointers DEVICE.                  */
+/* Background regions of `chess sim --background-query`, bin/chess:272-298, made on the device (ABI 4): for every
+ * query bin (bin_begin, bin_end, chromosome id; bins of a chromosome contiguous
+ * and sorted, chrom_first[c] = its first bin, n_chrom + 1 entries; chrom_end_bp[c] = largest bin end) the region
+ * [start, start + size] on both strands, kept where start + size <= chrom_end_bp (and, limit_chrom >= 0, on that
+ * chromosome only), each looked up like helpers.py:212-242 does (half-open overlap with [start - 1, start + size)).
+ * bin_begin[i] is the tree interval's begin, i.e. region.start - 1 where region.start is the BED start as
+ * load_regions keeps it.  Output in the reference's order (bin order, '+' then '-'): bg_first / bg_n / bg_strand
+ * (codes 0 / 1) hold up to 2 * n_bins entries, n_regions[0] the number written.  workspace: 13 * n_bins bytes.
+ * All pointers DEVICE.                                                                                        */
+int chess_background_regions(chess_ctx *ctx, const int64_t *bin_begin, const int64_t *bin_end,
+                             const int32_t *bin_chrom, const int64_t *chrom_first, const int64_t *chrom_end_bp,
+                             int64_t n_bins, int64_t size, int32_t limit_chrom, int64_t *bg_first, int32_t *bg_n,
+                             int32_t *bg_strand, int64_t *n_regions, void *workspace, void *stream);
+
 int chess_background_batch(chess_ctx *ctx, const chess_sample *ref, const chess_sample *qry,
                            const int64_t *ref_first, const int32_t *ref_n, const int32_t *ref_strand,
                            const int64_t *own_first, const int32_t *own_n, const int32_t *own_strand,

@@ -365,3 +365,31 @@ def test_ranged_bands_and_device_resident_triples(cb, hg38_like, tmp_path):
     assert coo_facts(t.src, t.sink, 0) == [0, 4, 0, 2]
     dc = DeviceContacts.from_device(t, n_bins=6)
     assert dc[3] == {4: 3.0} and dc[0] == {1: 2.0} and dc[1] == {1: 4.0} and dc.n_bins == 6
+
+
+def test_background_regions_enumerated_on_the_device(cb, toy, hg38_like):
+    """chess_background_regions (bin/chess:272-298 on the GPU) against the host columns and, through them
+    (tests/test_host_logic.py), against the reference's loop: same regions, same order, same bin spans."""
+    from chess_b200 import cli, helpers as H
+    from chess_b200.engine import QueryBackgroundSet
+    table, _ = H.load_regions_table(toy("qry.bed"))
+    trees = H.region_interval_trees(table)
+    cases = [(table, trees, H.GenomicRegion(chromosome="chrA", start=4001, end=28000, strand="+"), True),
+             (table, trees, H.GenomicRegion(chromosome="chrB", start=1, end=20000, strand="-"), False),
+             (table, trees, H.GenomicRegion(chromosome="chrQ", start=1, end=20000), True)]
+    genome = hg38_like[0]
+    big = H.RegionTable(genome.names, np.repeat(np.arange(len(genome.names)), genome.sizes),
+                        [r.start for r in hg38_like[1]], [r.end for r in hg38_like[1]])
+    big_trees = H.region_interval_trees(big)
+    cases += [(big, big_trees, H.GenomicRegion(chromosome="chr2", start=1, end=2000000), True),
+              (big, big_trees, H.GenomicRegion(chromosome="chr1", start=10001, end=1230000), False)]
+    for t, tr, q, limit in cases:
+        want = cli._background_spans_from_query(t, tr, q, limit)
+        bg = QueryBackgroundSet(t, q.end - q.start, q.chromosome if limit else None)
+        assert bg.ok
+        got = bg.host(0)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (q.chromosome, limit, len(a), len(b))
+    # an irregular BED (bins out of order) is left to the host path
+    odd = H.RegionTable(["c"], [0, 0, 0], [20, 0, 10], [30, 10, 20])
+    assert not QueryBackgroundSet(odd, 10).ok
