@@ -98,6 +98,7 @@ SIGNATURES = {
     "chess_band_build": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _dbl, _vp, _vp]),
     "chess_band_build_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _dbl, _vp, _vp]),
     "chess_coo_check": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "chess_symmetric_check": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "chess_gather_submatrix": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "chess_compare_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),
     "chess_compare_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _PP, _vp, _vp, _vp, _vp]),

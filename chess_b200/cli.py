@@ -34,8 +34,9 @@ class _StageClock(object):
         if sync:
             try:
                 import torch
+                from .engine import _contexts
                 if torch.cuda.is_available():
-                    for d in range(torch.cuda.device_count()):
+                    for d in list(_contexts):        # only GPUs this run has touched (a sync would create a context)
                         torch.cuda.synchronize(d)
             except Exception:
                 pass
@@ -266,14 +267,20 @@ def run_sim(args):
     clock = _StageClock()
 
     loader = load_oe_contacts if args.oe_input else load_contacts
-    devices = visible_devices()
-    if len(devices) > 1:
-        # CUDA contexts cost about a second each: create them side by side, not one after the other
+    all_devices = visible_devices()
+    devices = all_devices[:2]          # the two samples are loaded side by side; more GPUs join when the work
+                                       # is worth their context (engine.plan_devices, below)
+
+    def start_contexts(devs):
+        # CUDA contexts cost about a second each: start them side by side
         from concurrent.futures import ThreadPoolExecutor
         from .engine import get_context
         import torch
-        with ThreadPoolExecutor(len(devices)) as pool:
-            list(pool.map(lambda d: (torch.cuda.synchronize(d), get_context(d)), devices))
+        with ThreadPoolExecutor(max(len(devs), 1)) as pool:
+            list(pool.map(lambda d: (torch.cuda.synchronize(d), get_context(d)), devs))
+
+    if len(devices) > 1:
+        start_contexts(devices)
         clock.mark("create GPU contexts", sync=False)
     query_job = None
     if len(devices) > 1:
@@ -333,6 +340,22 @@ def run_sim(args):
             sys.exit()
 
     clock.mark("load pairs, bin-size guard")
+    # GPUs for the comparisons: as many as the work is worth (comparisons x bins^2 against a second per context)
+    from .engine import plan_devices
+    bins_ref = max(ref_bp // max(reference_bin_size - 1, 1), 1) + 1
+    work = float(len(pairs)) * bins_ref * bins_ref
+    if args.background_query:
+        n_bins_query = len(query_regions)
+        per_pair = 2.0 * (n_bins_query / max(len(query_trees), 1) if args.limit_background else n_bins_query)
+        work += float(len(pairs)) * per_pair * bins_ref * bins_ref
+    elif args.background_regions is not None:
+        with open(os.path.expanduser(args.background_regions)) as fh:
+            work += float(len(pairs)) * sum(1 for _ in fh) * bins_ref * bins_ref
+    planned = plan_devices(all_devices, work)
+    if len(planned) > len(devices):
+        start_contexts(planned[len(devices):])
+        clock.mark("create GPU contexts", sync=False)
+    devices = planned
     logger.info("Launching comparison engine on GPU(s) {}".format(devices))
     engine = CompareEngine(reference_edges, reference_trees, query_edges, query_trees, devices=devices)
     params = dict(min_bins=20, keep_unmappable_bins=args.keep_unmappable_bins,

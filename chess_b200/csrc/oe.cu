@@ -273,6 +273,24 @@ __global__ void coo_check_kernel(const int *__restrict__ src, const int *__restr
   }
 }
 
+// out[0] |= 1 if any of `count` dense n x n matrices packed back to back differs from its transpose (bit
+// pattern of the doubles; NaNs therefore count as equal to themselves)
+__global__ void symmetric_check_kernel(const double *__restrict__ base, int n, long long count, int *out) {
+  const long long per = (long long)n * n;
+  const long long total = per * count;
+  int bad = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / per, r = t - k * per;
+    const int i = (int)(r / n), j = (int)(r - (long long)i * n);
+    if (j > i) {
+      const double a = base[t], b = base[k * per + (long long)j * n + i];
+      bad |= __double_as_longlong(a) != __double_as_longlong(b);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(out, 1);
+}
+
 __global__ void coo_check_init_kernel(long long *out) {
   out[0] = 0x7fffffffffffffffll; out[1] = -1; out[2] = 0; out[3] = 0;
 }
@@ -412,6 +430,22 @@ extern "C" int chess_band_build_range(chess_ctx *ctx, const int32_t *src, const 
   if (nnz > 0) {
     band_scatter_range_kernel<<<grid_for(nnz, 256, ctx->sm_count), 256, 0, stream>>>(src, sink, value, nnz, W, bin_lo,
                                                                                      n_range, band);
+    ctx->launches += 1;
+  }
+  CHESS_CUDA(ctx, cudaGetLastError());
+  return CHESS_OK;
+}
+
+extern "C" int chess_symmetric_check(chess_ctx *ctx, const double *base, int32_t n, int64_t count, int32_t *out,
+                                     void *stream_) {
+  if (!ctx) return CHESS_ERR_ARG;
+  if (!base || !out || n <= 0 || count < 0) { ctx->err = "chess_symmetric_check: bad arguments"; return CHESS_ERR_ARG; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CHESS_CUDA(ctx, cudaSetDevice(ctx->device));
+  CHESS_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(int32_t), stream));
+  if (count > 0) {
+    symmetric_check_kernel<<<grid_for((long long)n * n * count, 256, ctx->sm_count), 256, 0, stream>>>(base, n, count,
+                                                                                                    out);
     ctx->launches += 1;
   }
   CHESS_CUDA(ctx, cudaGetLastError());

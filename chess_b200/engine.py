@@ -46,6 +46,21 @@ def visible_devices():
     return list(range(torch.cuda.device_count()))
 
 
+def plan_devices(devices, pixel_pairs, per_gpu_rate=2.5e11, context_cost_s=1.0):
+    """How many of ``devices`` a run of ``pixel_pairs`` (comparisons x bins^2) should use.  A CUDA context costs
+    about a second to create (and contexts are created one after the other by the driver), a GPU compares
+    roughly 2.5e11 pixel pairs per second: a further GPU pays off once it saves more than it costs.  At least
+    two when there are two (the two samples of a run are loaded side by side)."""
+    devices = list(devices)
+    if len(devices) <= 2:
+        return devices
+    seconds = float(pixel_pairs) / per_gpu_rate
+    n = 2
+    while n < len(devices) and seconds / n - seconds / (n + 1) > context_cost_s:
+        n += 1
+    return devices[:n]
+
+
 def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 

@@ -171,6 +171,10 @@ int chess_band_build_range(chess_ctx *ctx, const int32_t *src, const int32_t *si
  * bin ranges are contiguous slices.                                                                           */
 int chess_coo_check(chess_ctx *ctx, const int32_t *src, const int32_t *sink, int64_t nnz, int64_t *out4,
                     void *stream);
+/* out[0] (DEVICE int32) = 1 if any of `count` dense n x n matrices packed back to back at `base` differs from its
+ * transpose, else 0 (ABI 4).  What CHESS_FLAG_SYMMETRIC asserts for the dense batches of
+ * utils/run_synthetic_test.py:97-121, checked where the matrices already are.                                */
+int chess_symmetric_check(chess_ctx *ctx, const double *base, int32_t n, int64_t count, int32_t *out, void *stream);
 
 /* Dense copy of one submatrix view, out[r*n + c] = base[off + r*pitch + c]:
  * the return value of sub_matrix_from_edges_dict, chess/helpers.py:286-306.   */
