@@ -270,3 +270,14 @@ def test_background_spans_and_table_text_match_the_loops(toy):
     vals = np.concatenate([rng.normal(0, 1, 2000) * 10.0 ** rng.integers(-20, 20, 2000),
                            [np.nan, 0.0, -0.0, 1.0, 1e16, 1e-5, 123456789.125, np.inf, -np.inf, 5e-324, 1.7976931348623157e308]])
     assert cli._float_column(vals) == ["{}".format(np.float64(v)) for v in vals]
+
+
+def test_gpus_are_planned_by_the_work():
+    """A CUDA context costs about a second, so `chess sim` adds GPUs only when the comparisons are worth it."""
+    from chess_b200.engine import plan_devices
+    eight = list(range(8))
+    assert plan_devices([0], 1e15) == [0] and plan_devices([0, 1], 1.0) == [0, 1]
+    assert plan_devices(eight, 101354 * 201 ** 2) == [0, 1]                 # configs[2]: 40 ms of work
+    assert plan_devices(eight, 101354 * 26000.0 * 201 ** 2) == eight         # the same list with --background-query
+    n = [len(plan_devices(eight, w)) for w in (1e9, 1e11, 1e12, 3e12, 1e13, 1e14)]
+    assert n == sorted(n) and n[0] == 2 and n[-1] == 8
