@@ -639,17 +639,22 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
     ctx = get_context(R.local_rank)
     sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     table = res.table(lo, hi)
-    h_ssim, h_sn, h_z = np.empty(n_local), np.empty(n_local), np.empty(n_local)
-    h_status = np.empty(n_local, dtype=np.int32)
+    # the caller's host buffers are page-locked (the contract's "pinned host memory"): the library then copies
+    # straight from / into them instead of staging through its own pinned area
+    def pinned(n, dtype):
+        return torch.empty(n, dtype=dtype).pin_memory().numpy()
+    pinned_table = torch.from_numpy(table.view(np.uint8)).pin_memory()
+    h_table = pinned_table.numpy()
+    h_ssim, h_sn, h_z = pinned(n_local, torch.float64), pinned(n_local, torch.float64), pinned(n_local, torch.float64)
+    h_status = pinned(n_local, torch.int32)
 
     # ---- the two host-buffer C-ABI calls
     def host_sim():        # N = 1: pair table in; ssim, SN, status and z_ssim out
-        check(lib.chess_sim_band_batch_host(ctx.handle, C.byref(res.rsample), C.byref(res.qsample), _np_ptr(table),
+        check(lib.chess_sim_band_batch_host(ctx.handle, C.byref(res.rsample), C.byref(res.qsample), _np_ptr(h_table),
                                             n_local, res.max_n, C.byref(p), _np_ptr(h_ssim), _np_ptr(h_sn),
                                             _np_ptr(h_status), _np_ptr(h_z), sp), ctx.handle, "chess_sim_band_batch_host")
         return h_ssim, h_sn, h_status, h_z
 
-    pinned_table = torch.from_numpy(table.view(np.uint8)).pin_memory() if strong else None
     e_tab = torch.empty(table.nbytes, dtype=torch.uint8, device=dev) if strong else None
     e_ssim = torch.empty(n_local, dtype=torch.float64, device=dev)
     e_sn = torch.empty(n_local, dtype=torch.float64, device=dev)

@@ -153,6 +153,14 @@ extern "C" int chess_compare_band_batch(chess_ctx *ctx, const chess_sample *ref,
   return chess_compare_batch(ctx, ref->band, qry->band, pairs, n_pairs, max_n, &p, ssim, sn, status, stream_);
 }
 
+// Page-locked host memory the device can DMA from / into without staging (cudaHostAlloc, cudaHostRegister,
+// torch's pinned allocator).  Pageable memory reports cudaMemoryTypeUnregistered.
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // Shared body of the *_host entry points: stage the pair table, run `launch`, (optionally) the run-level
 // z-score on the device, copy the results back in one transfer.
 template <typename Launch>
@@ -173,11 +181,16 @@ static int host_roundtrip(chess_ctx *ctx, const chess_pair *pairs_host, int64_t 
   if ((rc = grow(ctx, &ctx->d_results, &ctx->d_results_bytes, res_bytes, false))) return rc;
   if ((rc = grow(ctx, &ctx->h_pinned, &ctx->h_pinned_bytes, res_off + res_bytes, true))) return rc;
   char *hp = reinterpret_cast<char *>(ctx->h_pinned);
-  // pageable -> pinned (one memcpy on the host), then either one DMA or direct reads by the kernels
-  std::memcpy(hp, pairs_host, pair_bytes);
+  // A caller that already holds page-locked buffers (torch pinned tensors, cudaHostAlloc) is served by DMA
+  // straight from / into them; pageable buffers go through the context's pinned staging area (one memcpy on
+  // the host each way: 0.5 ms of the 13.7 ms call on the genome-wide table).
+  const bool direct = zc == 0 && is_pinned(pairs_host) && is_pinned(ssim_host) && is_pinned(sn_host) &&
+                      is_pinned(status_host) && (!z_host || is_pinned(z_host));
+  if (!direct) std::memcpy(hp, pairs_host, pair_bytes);
   const chess_pair *k_pairs = reinterpret_cast<const chess_pair *>(hp);
   if (zc == 0) {
-    CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, hp, pair_bytes, cudaMemcpyHostToDevice, stream));
+    CHESS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, direct ? (const void *)pairs_host : (const void *)hp, pair_bytes,
+                                    cudaMemcpyHostToDevice, stream));
     k_pairs = reinterpret_cast<const chess_pair *>(ctx->d_pairs);
   }
   double *d_ssim = reinterpret_cast<double *>(zc == 2 ? (void *)(hp + res_off) : ctx->d_results);
@@ -187,11 +200,20 @@ static int host_roundtrip(chess_ctx *ctx, const chess_pair *pairs_host, int64_t 
   rc = launch(k_pairs, d_ssim, d_sn, d_status);
   if (rc) return rc;
   if (z_host && (rc = chess_zscore(ctx, d_ssim, n_pairs, d_z, stream))) return rc;
+  const size_t col = (size_t)n_pairs * sizeof(double);
+  if (direct) {
+    CHESS_CUDA(ctx, cudaMemcpyAsync(ssim_host, d_ssim, col, cudaMemcpyDeviceToHost, stream));
+    CHESS_CUDA(ctx, cudaMemcpyAsync(sn_host, d_sn, col, cudaMemcpyDeviceToHost, stream));
+    if (z_host) CHESS_CUDA(ctx, cudaMemcpyAsync(z_host, d_z, col, cudaMemcpyDeviceToHost, stream));
+    CHESS_CUDA(ctx, cudaMemcpyAsync(status_host, d_status, (size_t)n_pairs * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, stream));
+    CHESS_CUDA(ctx, cudaStreamSynchronize(stream));
+    return CHESS_OK;
+  }
   if (zc != 2)
     CHESS_CUDA(ctx, cudaMemcpyAsync(hp + res_off, ctx->d_results, res_bytes, cudaMemcpyDeviceToHost, stream));
   CHESS_CUDA(ctx, cudaStreamSynchronize(stream));
   const char *h = hp + res_off;
-  const size_t col = (size_t)n_pairs * sizeof(double);
   std::memcpy(ssim_host, h, col);
   std::memcpy(sn_host, h + col, col);
   if (z_host) std::memcpy(z_host, h + 2 * col, col);

@@ -48,6 +48,23 @@ def main():
     print("\nstall reasons (all samples):")
     for s, v in sorted(stall_tot.items(), key=lambda kv: -kv[1])[:10]:
         print("  %-24s %8d %5.1f%%" % (s, v, 100.0 * v / max(tot_samp, 1)))
+    # how often each instruction ran: set-up / finish code runs once per item, the row loop once per warp-row --
+    # classes of equal execution count (within 10 %) split the kernel into its phases
+    print("\ninstructions by execution count (phases of the kernel):")
+    classes = []
+    for samp, inst, addr, src, st in sorted(per, key=lambda t: -t[1]):
+        if inst == 0:
+            continue
+        if classes and inst >= 0.9 * classes[-1][0]:
+            classes[-1][1] += 1
+            classes[-1][2] += inst
+            classes[-1][3] += samp
+        else:
+            classes.append([inst, 1, inst, samp])
+    print("  %14s %8s %14s %7s %7s" % ("runs (each)", "SASS", "warp inst", "share", "samples"))
+    for runs, count, inst, samp in sorted(classes, key=lambda c: -c[2])[:12]:
+        print("  %14d %8d %14d %6.1f%% %6.1f%%" % (runs, count, inst, 100.0 * inst / max(tot_inst, 1),
+                                                    100.0 * samp / max(tot_samp, 1)))
     print("\nhottest instructions by samples:")
     for samp, inst, addr, src, st in sorted(per, key=lambda t: -t[0])[:top]:
         main_st = max(st.items(), key=lambda kv: kv[1]) if st else ("", 0)
