@@ -26,9 +26,11 @@ Numbers on the JSON line
                 time of K steps, L2 flushed before every step, max over ranks.  At N > 1 a step includes the
                 all-gather of the ssim values (NCCL, 8 B per pair) that the run-level z-score needs.
   e2e           the same work through the host-buffer C-ABI calls: pair table from host memory, results back
-                in host memory and z-scores, every step.  N = 1: one `chess_sim_band_batch_host` call.  N > 1:
-                `chess_compare_band_batch_host` on every rank's range, `distributed.gather_to_rank0` (host
-                buffers, 20 B per pair) and `distributed.run_zscores` on rank 0 -- all inside the timed region.
+                in host memory and z-scores, every step, host arrays page-locked.  N = 1: one
+                `chess_sim_band_batch_host` call.  N > 1: every rank copies its range of the pair table to its
+                GPU and compares it, the ssim values are all-gathered and z-scored on the device, and
+                `distributed.gather_tensors_to_rank0` brings ssim, SN, status and z (28 B per pair) to rank 0's
+                host memory in one NCCL gather and one copy -- all inside the timed region.
   roofline      compare kernel only: algorithmic bytes (2*n*n*8 + 24 per pair) / its CUDA-event
                 duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes
                 of one launch from an ncu pass this very run makes on a child process (N = 1; null if ncu is
@@ -620,7 +622,7 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
     from chess_b200 import _native
     from chess_b200._native import lib, check
     from chess_b200.engine import get_context
-    from chess_b200.distributed import gather_tensors_to_rank0, run_zscores, my_shard
+    from chess_b200.distributed import gather_tensors_to_rank0, my_shard
 
     steps = steps or args.steps
     warmup = max(warmup or args.warmup, 3)
@@ -656,19 +658,24 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
         return h_ssim, h_sn, h_status, h_z
 
     e_tab = torch.empty(table.nbytes, dtype=torch.uint8, device=dev) if strong else None
-    e_ssim = torch.empty(n_local, dtype=torch.float64, device=dev)
+    e_pad = torch.full((longest,), float("nan"), dtype=torch.float64, device=dev)    # the pad entry stays NaN
+    e_ssim = e_pad[:n_local]
     e_sn = torch.empty(n_local, dtype=torch.float64, device=dev)
     e_status = torch.empty(n_local, dtype=torch.int32, device=dev)
+    e_all = torch.empty(longest * world, dtype=torch.float64, device=dev) if strong else None
+    e_zall = torch.empty(longest * world, dtype=torch.float64, device=dev) if strong else None
 
-    def host_sharded():    # N > 1: this rank's range; results gathered on rank 0 and copied to its host; z there
+    def host_sharded():    # N > 1: this rank's range; z_ssim on the device; everything gathered to rank 0's host
         e_tab.copy_(pinned_table, non_blocking=True)                      # the host pair table of this range
         check(lib.chess_compare_band_batch(ctx.handle, C.byref(res.rsample), C.byref(res.qsample), _ptr(e_tab),
                                            n_local, res.max_n, C.byref(p), _ptr(e_ssim), _ptr(e_sn), _ptr(e_status),
                                            sp), ctx.handle, "chess_compare_band_batch")
-        got = gather_tensors_to_rank0((e_ssim, e_sn, e_status), total, rank, world, R.dist)
-        if rank != 0:
-            return None
-        return got + (run_zscores(got[0]),)           # bin/chess:216-233 on the gathered values
+        # the run-level z (bin/chess:216-233) needs every rank's ssim: 8 B per pair all-gathered over NVLink,
+        # K6 on every rank, and each rank's slice of z travels with its ssim, SN and status
+        R.dist.all_gather_into_tensor(e_all, e_pad)
+        check(lib.chess_zscore(ctx.handle, _ptr(e_all), e_all.numel(), _ptr(e_zall), sp), ctx.handle, "chess_zscore")
+        e_z = e_zall[rank * longest:rank * longest + n_local]
+        return gather_tensors_to_rank0((e_ssim, e_sn, e_status, e_z), total, rank, world, R.dist)
 
     host_step = host_sharded if strong else host_sim
     t0 = time.perf_counter()
@@ -793,11 +800,12 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
                                   "compare (gather+mask+SSIM+SN), %.1f us per launch, %d pairs on this rank"
                                   % (kern_ms * 1e3, n_local), traffic), traffic_source=traffic_note),
         "e2e": {"value": all_pairs * steps / e2e_s, "unit": "pairs/s", "ms_per_step": 1e3 * e2e_s / steps,
-                "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_local * (28 if not strong else 20)),
+                "h2d_bytes_per_step": int(table.nbytes), "d2h_bytes_per_step": int(n_local * 28),
                 "call": ("every rank: its range of the host pair table -> GPU, chess_compare_band_batch; "
-                         "distributed.gather_tensors_to_rank0 (ssim, SN, status of all ranks in one NCCL gather, 20 B "
-                         "per pair, then ONE copy to rank 0's host memory); distributed.run_zscores on rank 0 -- all "
-                         "timed" if strong else
+                         "all-gather of ssim (8 B per pair) + chess_zscore on every rank; "
+                         "distributed.gather_tensors_to_rank0 (ssim, SN, status, z_ssim of all ranks in one NCCL "
+                         "gather, 28 B per pair, then ONE copy into rank 0's page-locked host memory) -- all timed"
+                         if strong else
                          "chess_sim_band_batch_host (host pair table in; ssim, SN, status, z_ssim out to host arrays; "
                          "up to 8192 pairs the kernels read / write the pinned staging buffer directly, larger "
                          "batches use one DMA each way)")},

@@ -381,8 +381,8 @@ __device__ __noinline__ void tri_r1_finish(const double *recs, int np_, int win,
 // (HYBRID; strips of 5 .. 8 columns run half items only: the bookkeeping costs them more registers than the
 // saved set-up returns).  A pair gives the same bits whichever way it ran: the parts are reduced over the
 // warp separately and added in the order the combine adds two records.
-template <int G, bool WITH_SN, bool HYBRID>
-__global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2))
+template <int G, bool WITH_SN, bool HYBRID, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 compare_r1_tri_kernel(chess_item_args a) {
   __shared__ int s_susp[4][kSuspCap];
   __shared__ int s_susp_n[4];
@@ -494,9 +494,9 @@ compare_r1_tri_kernel(chess_item_args a) {
   }
 }
 
-template <int G, bool WITH_SN, bool HYBRID>
+template <int G, bool WITH_SN, bool HYBRID, int MINB>
 int launch_tri_impl(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  auto kern = compare_r1_tri_kernel<G, WITH_SN, HYBRID>;
+  auto kern = compare_r1_tri_kernel<G, WITH_SN, HYBRID, MINB>;
   constexpr int RING = 7 * G * 32;
   const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
   const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 256 * 3;
@@ -532,14 +532,22 @@ int launch_tri_impl(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
 
 template <int G, bool WITH_SN>
 int launch_tri(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  return launch_tri_impl<G, WITH_SN, true>(ctx, a, stream);
+  // strips of 3 / 4 columns: 128 registers and 16 warps per SM -- or 168 registers and 12 warps without spills for
+  // the one-pass layout of small matrices in batches of many waves (41 bins, 100 k pairs: 1.60 -> 1.48 ms; two
+  // parts at 81 bins lose 1 %, and a batch of one wave -- 2 402 pairs -- needs the 16 warps: 90 -> 104 us)
+  static const int wide_env = getenv("CHESS_TRI_WIDE") ? atoi(getenv("CHESS_TRI_WIDE")) : -1;  // A/B runs
+  int b1, b2, l1, l2;
+  const bool mono = tri_mode(a.max_n, G, b1, b2, l1, l2) == 1;
+  const bool wide = wide_env >= 0 ? wide_env != 0 : (mono && a.n_pairs >= 8LL * ctx->sm_count * 16);
+  if (wide) return launch_tri_impl<G, WITH_SN, true, 3>(ctx, a, stream);
+  return launch_tri_impl<G, WITH_SN, true, 4>(ctx, a, stream);
 }
 
 // Strips of 5 .. 8 columns: two independent half items per pair only (hg38 @ 10 kb, 7 columns per lane: the
 // hybrid scheduling measured 15.3 ms against 14.7 ms).
 template <int G, bool WITH_SN>
 int launch_tri_half(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  return launch_tri_impl<G, WITH_SN, false>(ctx, a, stream);
+  return launch_tri_impl<G, WITH_SN, false, 2>(ctx, a, stream);
 }
 
 }  // namespace

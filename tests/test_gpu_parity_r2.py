@@ -393,3 +393,53 @@ def test_background_regions_enumerated_on_the_device(cb, toy, hg38_like):
     # an irregular BED (bins out of order) is left to the host path
     odd = H.RegionTable(["c"], [0, 0, 0], [20, 0, 10], [30, 10, 20])
     assert not QueryBackgroundSet(odd, 10).ok
+
+
+def test_host_call_serves_pinned_and_pageable_arrays_alike(cb, hg38_like):
+    """chess_sim_band_batch_host copies straight from / into page-locked caller arrays and stages pageable
+    ones through its own pinned area: the same bytes either way, for a table above and one below the 8 192-pair
+    limit of the direct-read path."""
+    import ctypes as C
+    import torch
+    from chess_b200 import _native
+    from chess_b200._native import lib, check
+    from chess_b200.engine import get_context, region_spans, build_pair_table
+    genome, regions, trees, re_, qe, qe2, pairs = hg38_like
+    rf, rn = region_spans(trees, [p[1] for p in pairs])
+    qf, qn = region_spans(trees, [p[2] for p in pairs])
+    max_n = int(max(rn.max(), qn.max()))
+    rw, rband, rsample, r0 = re_.sample_on(0, max_n, None, None, with_origin=True)
+    qw, qband, qsample, q0 = qe.sample_on(0, max_n, None, None, with_origin=True)
+    flip = np.zeros(len(pairs), dtype=np.int32)
+    small = build_pair_table(rf - r0, rn, rw, qf - q0, qn, qw, flip)
+    ctx = get_context(0)
+    sp = C.c_void_p(torch.cuda.current_stream(torch.device("cuda", 0)).cuda_stream)
+    p = _native.make_params(compute_sn=True, flags=_native.FLAG_SYMMETRIC | _native.FLAG_EQUAL_SIZES)
+    for table in (small, np.tile(small, (9000 // len(small)) + 1)):
+        n = len(table)
+        got = {}
+        for kind in ("pageable", "pinned"):
+            if kind == "pinned":
+                h_tab = torch.from_numpy(table.view(np.uint8).copy()).pin_memory().numpy()
+                outs = [torch.empty(n, dtype=dt).pin_memory().numpy()
+                        for dt in (torch.float64, torch.float64, torch.int32, torch.float64)]
+            else:
+                h_tab = table.view(np.uint8).copy()
+                outs = [np.empty(n), np.empty(n), np.empty(n, dtype=np.int32), np.empty(n)]
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+            check(lib.chess_sim_band_batch_host(ctx.handle, C.byref(rsample), C.byref(qsample), ptr(h_tab), n, max_n,
+                                                C.byref(p), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]),
+                                                sp), ctx.handle, kind)
+            got[kind] = [o.copy() for o in outs]
+        for a, b in zip(got["pageable"], got["pinned"]):
+            assert a.tobytes() == b.tobytes()
+        assert (got["pinned"][2] == 0).sum() > 0.8 * n
+        # and the engine (device-resident path) gives the same values for the pairs of the list
+        ids, s, sn, st = cb.CompareEngine(re_, trees, qe, trees).compare(pairs)
+        np.testing.assert_allclose(got["pinned"][0][:len(pairs)], s, rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(got["pinned"][1][:len(pairs)], sn, rtol=1e-10, equal_nan=True)
+        # z_ssim of the call = bin/chess:228-233 over its own ssim column
+        ss = got["pinned"][0]
+        valid = ss[~np.isnan(ss)]
+        np.testing.assert_allclose(got["pinned"][3], (ss - valid.mean()) / valid.std(), rtol=1e-9, atol=1e-12,
+                                   equal_nan=True)

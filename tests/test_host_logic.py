@@ -281,3 +281,14 @@ def test_gpus_are_planned_by_the_work():
     assert plan_devices(eight, 101354 * 26000.0 * 201 ** 2) == eight         # the same list with --background-query
     n = [len(plan_devices(eight, w)) for w in (1e9, 1e11, 1e12, 3e12, 1e13, 1e14)]
     assert n == sorted(n) and n[0] == 2 and n[-1] == 8
+
+
+def test_run_level_zscores_keep_nan_and_match_the_reference_rule():
+    """bin/chess:228-233: nanmean / nanstd (ddof 0) over the non-NaN ssim values; a NaN ssim keeps z = NaN."""
+    from chess_b200.distributed import run_zscores
+    s = np.array([0.5, np.nan, 0.25, 0.75, np.nan, 0.5])
+    z = run_zscores(s)
+    ok = ~np.isnan(s)
+    assert np.all(np.isnan(z[~ok]))
+    np.testing.assert_allclose(z[ok], (s[ok] - np.nanmean(s)) / np.nanstd(s), rtol=1e-15)
+    assert np.all(np.isnan(run_zscores(np.array([np.nan, np.nan])))) and len(run_zscores(np.zeros(0))) == 0
