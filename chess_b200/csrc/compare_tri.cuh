@@ -73,6 +73,7 @@ struct TriItem {
 // for this item to do).
 //   pi        pair index in the launch;   part      which of the pair's items this is (0 writes the soft failures)
 //   n_limit   widest matrix the calling kernel can hold
+template <bool BATCH = true>
 __device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long long pi, int part, int n_limit, int lane,
                                                short *kmap, unsigned char *mflag, TriItem &it) {
   const chess_params &p = a.p;
@@ -98,26 +99,42 @@ __device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long lo
   const int i0q = (int)((d.qry_off - (Wq - 1)) / (2 * Wq - 1));
   int np_ = n, tot_r = 0, tot_q = 0, tot_one_sided = 0;
   if (use_masks) {
-    // four groups of 32 columns at a time: their 16 look-ups per lane are in flight together (one per
-    // iteration, each waiting for the one before, was 2 % of the kernel's stall samples at 201 bins)
-    for (int base = 0; base < n; base += 128) {
-      int lo_r[4], hi_r[4], lo_q[4], hi_q[4];
+    if constexpr (BATCH) {
+      // four groups of 32 columns at a time: their 16 look-ups per lane are in flight together (one per
+      // iteration, each waiting for the one before, was 2 % of the kernel's stall samples at 201 bins)
+      for (int base = 0; base < n; base += 128) {
+        int lo_r[4], hi_r[4], lo_q[4], hi_q[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = base + 32 * u + lane;
-        lo_r[u] = lo_q[u] = 0x7fffffff; hi_r[u] = hi_q[u] = -1;      // "not masked" for columns beyond n
-        if (c < n) {
-          const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
-          lo_r[u] = __ldg(a.ref_lo + jr); hi_r[u] = __ldg(a.ref_hi + jr);
-          lo_q[u] = __ldg(a.qry_lo + jq); hi_q[u] = __ldg(a.qry_hi + jq);
+        for (int u = 0; u < 4; ++u) {
+          const int c = base + 32 * u + lane;
+          lo_r[u] = lo_q[u] = 0x7fffffff; hi_r[u] = hi_q[u] = -1;      // "not masked" for columns beyond n
+          if (c < n) {
+            const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
+            lo_r[u] = __ldg(a.ref_lo + jr); hi_r[u] = __ldg(a.ref_hi + jr);
+            lo_q[u] = __ldg(a.qry_lo + jq); hi_q[u] = __ldg(a.qry_hi + jq);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = base + 32 * u + lane;
+          const bool fr = lo_r[u] < i0r && hi_r[u] >= i0r + n;
+          const bool fq = lo_q[u] < i0q && hi_q[u] >= i0q + n;
+          if (c < n) mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+          tot_r += __popc(__ballot_sync(0xffffffffu, fr));
+          tot_q += __popc(__ballot_sync(0xffffffffu, fq));
+          tot_one_sided += __popc(__ballot_sync(0xffffffffu, fr != fq));
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = base + 32 * u + lane;
-        const bool fr = lo_r[u] < i0r && hi_r[u] >= i0r + n;
-        const bool fq = lo_q[u] < i0q && hi_q[u] >= i0q + n;
-        if (c < n) mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+    } else {
+      for (int base = 0; base < n; base += 32) {
+        const int c = base + lane;
+        bool fr = false, fq = false;
+        if (c < n) {
+          const int jr = i0r + c, jq = i0q + (flip ? n - 1 - c : c);
+          fr = __ldg(a.ref_lo + jr) < i0r && __ldg(a.ref_hi + jr) >= i0r + n;
+          fq = __ldg(a.qry_lo + jq) < i0q && __ldg(a.qry_hi + jq) >= i0q + n;
+          mflag[c] = (unsigned char)((fr ? 1 : 0) | (fq ? 2 : 0));
+        }
         tot_r += __popc(__ballot_sync(0xffffffffu, fr));
         tot_q += __popc(__ballot_sync(0xffffffffu, fq));
         tot_one_sided += __popc(__ballot_sync(0xffffffffu, fr != fq));
@@ -157,28 +174,38 @@ __device__ __forceinline__ bool tri_item_begin(const chess_item_args &a, long lo
 // k removed bins: if none of them reaches the uncompacted extremes, those are attained by cells
 // that stay, and the lookup stands.  Returns true only when that fails too and the caller has to
 // take min / max from all the data.
+template <bool BATCH = true>
 __device__ __forceinline__ bool tri_extrema(const chess_item_args &a, const TriItem &it, int lane,
                                             const unsigned char *mflag, double &xmax, double &xmin) {
   xmax = -CUDART_INF; xmin = CUDART_INF;
   if (a.ref_pmax == nullptr) return true;
   const int n = it.n;
-  for (int r0 = lane; r0 < n; r0 += 128) {     // 16 look-ups per lane in flight together
-    double v[4][4];
+  if constexpr (BATCH) {
+    for (int r0 = lane; r0 < n; r0 += 128) {     // 16 look-ups per lane in flight together
+      double v[4][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + 32 * u;
-      v[u][0] = v[u][1] = -CUDART_INF; v[u][2] = v[u][3] = CUDART_INF;
-      if (r < n) {
-        const size_t ir = (size_t)(it.i0r + r) * (size_t)it.Wr + (size_t)(n - 1 - r);
-        const size_t iq = (size_t)(it.i0q + r) * (size_t)it.Wq + (size_t)(n - 1 - r);
-        v[u][0] = __ldg(a.ref_pmax + ir); v[u][1] = __ldg(a.qry_pmax + iq);
-        v[u][2] = __ldg(a.ref_pmin + ir); v[u][3] = __ldg(a.qry_pmin + iq);
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + 32 * u;
+        v[u][0] = v[u][1] = -CUDART_INF; v[u][2] = v[u][3] = CUDART_INF;
+        if (r < n) {
+          const size_t ir = (size_t)(it.i0r + r) * (size_t)it.Wr + (size_t)(n - 1 - r);
+          const size_t iq = (size_t)(it.i0q + r) * (size_t)it.Wq + (size_t)(n - 1 - r);
+          v[u][0] = __ldg(a.ref_pmax + ir); v[u][1] = __ldg(a.qry_pmax + iq);
+          v[u][2] = __ldg(a.ref_pmin + ir); v[u][3] = __ldg(a.qry_pmin + iq);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xmax = fmax(xmax, fmax(v[u][0], v[u][1]));
+        xmin = fmin(xmin, fmin(v[u][2], v[u][3]));
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      xmax = fmax(xmax, fmax(v[u][0], v[u][1]));
-      xmin = fmin(xmin, fmin(v[u][2], v[u][3]));
+  } else {
+    for (int r = lane; r < n; r += 32) {
+      const size_t ir = (size_t)(it.i0r + r) * (size_t)it.Wr + (size_t)(n - 1 - r);
+      const size_t iq = (size_t)(it.i0q + r) * (size_t)it.Wq + (size_t)(n - 1 - r);
+      xmax = fmax(xmax, fmax(__ldg(a.ref_pmax + ir), __ldg(a.qry_pmax + iq)));
+      xmin = fmin(xmin, fmin(__ldg(a.ref_pmin + ir), __ldg(a.qry_pmin + iq)));
     }
   }
   xmax = warp_max(xmax);
@@ -224,44 +251,70 @@ __device__ __forceinline__ void tri_scan_extrema(const TriItem &it, int lane, co
 // row-prefix arrays; a hit within 1e-7 is summed exactly in the reference's order (rows 0 .. n-1 of
 // the uncompacted matrix).  Returns false if some column is masked after all (per lane; combine
 // with __any_sync).
+template <bool BATCH = true>
 __device__ __forceinline__ bool tri_masks_hold(const chess_item_args &a, const TriItem &it, int lane,
                                                const short *kmap, const unsigned char *mflag) {
   if (!(a.p.mappability_cutoff > 0)) return true;
   const int n = it.n, flip = it.flip;
   const double target = (double)n * a.p.default_value;
   bool bad = false;
-  for (int c0 = lane; c0 < it.np_; c0 += 128) {     // the prefix look-ups of four columns per lane together
-    double sr[4], sq[4];
-    int kcs[4];
+  if constexpr (BATCH) {
+    for (int c0 = lane; c0 < it.np_; c0 += 128) {     // the prefix look-ups of four columns per lane together
+      double sr[4], sq[4];
+      int kcs[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = c0 + 32 * u;
-      double r1 = 0.0, r0 = 0.0, q1 = 0.0, q0 = 0.0;
-      kcs[u] = -1;
-      if (c < it.np_) {
-        const int kc = kmap[c];
-        kcs[u] = kc;
-        const int cq = flip ? n - 1 - kc : kc;
-        const double *pr = a.ref_pre + (size_t)(it.i0r + kc) * (size_t)(2 * it.Wr) + (size_t)(it.Wr - 1 - kc);
-        const double *pq = a.qry_pre + (size_t)(it.i0q + cq) * (size_t)(2 * it.Wq) + (size_t)(it.Wq - 1 - cq);
-        r1 = __ldg(pr + n); r0 = __ldg(pr); q1 = __ldg(pq + n); q0 = __ldg(pq);
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        double r1 = 0.0, r0 = 0.0, q1 = 0.0, q0 = 0.0;
+        kcs[u] = -1;
+        if (c < it.np_) {
+          const int kc = kmap[c];
+          kcs[u] = kc;
+          const int cq = flip ? n - 1 - kc : kc;
+          const double *pr = a.ref_pre + (size_t)(it.i0r + kc) * (size_t)(2 * it.Wr) + (size_t)(it.Wr - 1 - kc);
+          const double *pq = a.qry_pre + (size_t)(it.i0q + cq) * (size_t)(2 * it.Wq) + (size_t)(it.Wq - 1 - cq);
+          r1 = __ldg(pr + n); r0 = __ldg(pr); q1 = __ldg(pq + n); q0 = __ldg(pq);
+        }
+        sr[u] = r1 - r0; sq[u] = q1 - q0;
       }
-      sr[u] = r1 - r0; sq[u] = q1 - q0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kc = kcs[u];
+        if (kc < 0) continue;
+        if (!(mflag[kc] & 1) && fabs(sr[u] - target) <= 1e-7 * (fabs(sr[u]) + fabs(target))) {
+          double s2 = 0.0;
+          for (int r = 0; r < n; ++r) s2 += __ldg(it.R + (size_t)r * it.rp + kc);
+          bad |= s2 == target;
+        }
+        if (!(mflag[kc] & 2) && fabs(sq[u] - target) <= 1e-7 * (fabs(sq[u]) + fabs(target))) {
+          const int cq = flip ? n - 1 - kc : kc;
+          double s2 = 0.0;
+          for (int r = 0; r < n; ++r) s2 += __ldg(it.Q + (size_t)(flip ? n - 1 - r : r) * it.qp + cq);
+          bad |= s2 == target;
+        }
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int kc = kcs[u];
-      if (kc < 0) continue;
-      if (!(mflag[kc] & 1) && fabs(sr[u] - target) <= 1e-7 * (fabs(sr[u]) + fabs(target))) {
-        double s2 = 0.0;
-        for (int r = 0; r < n; ++r) s2 += __ldg(it.R + (size_t)r * it.rp + kc);
-        bad |= s2 == target;
+  } else {
+    for (int c = lane; c < it.np_; c += 32) {
+      const int kc = kmap[c];
+      if (!(mflag[kc] & 1)) {
+        const double *pr = a.ref_pre + (size_t)(it.i0r + kc) * (size_t)(2 * it.Wr) + (size_t)(it.Wr - 1 - kc);
+        const double sr = __ldg(pr + n) - __ldg(pr);
+        if (fabs(sr - target) <= 1e-7 * (fabs(sr) + fabs(target))) {
+          double s2 = 0.0;
+          for (int r = 0; r < n; ++r) s2 += __ldg(it.R + (size_t)r * it.rp + kc);
+          bad |= s2 == target;
+        }
       }
-      if (!(mflag[kc] & 2) && fabs(sq[u] - target) <= 1e-7 * (fabs(sq[u]) + fabs(target))) {
+      if (!(mflag[kc] & 2)) {
         const int cq = flip ? n - 1 - kc : kc;
-        double s2 = 0.0;
-        for (int r = 0; r < n; ++r) s2 += __ldg(it.Q + (size_t)(flip ? n - 1 - r : r) * it.qp + cq);
-        bad |= s2 == target;
+        const double *pq = a.qry_pre + (size_t)(it.i0q + cq) * (size_t)(2 * it.Wq) + (size_t)(it.Wq - 1 - cq);
+        const double sq = __ldg(pq + n) - __ldg(pq);
+        if (fabs(sq - target) <= 1e-7 * (fabs(sq) + fabs(target))) {
+          double s2 = 0.0;
+          for (int r = 0; r < n; ++r) s2 += __ldg(it.Q + (size_t)(flip ? n - 1 - r : r) * it.qp + cq);
+          bad |= s2 == target;
+        }
       }
     }
   }

@@ -7,7 +7,8 @@
 
 namespace {
 
-template <int G>
+// BATCH: the set-up look-ups of an item in batches of four groups (compare_tri.cuh) or one group at a time
+template <int G, bool BATCH>
 __global__ void __launch_bounds__(128, (G <= 4 ? 3 : 2))
 compare_win7_tri_kernel(chess_item_args a) {
   __shared__ int s_susp[4][kSuspCap];
@@ -46,7 +47,7 @@ compare_win7_tri_kernel(chess_item_args a) {
     TriItem it;
     const bool PAIR = HYB && item < n_pair_items;
     const long long half = item - n_pair_items;   // index among the half items
-    if (!tri_item_begin(a, PAIR ? item : n_pair_items + (half >> 1), PAIR ? 0 : (int)(half & 1), 31 * G, lane, kmap,
+    if (!tri_item_begin<BATCH>(a, PAIR ? item : n_pair_items + (half >> 1), PAIR ? 0 : (int)(half & 1), 31 * G, lane, kmap,
                         mflag, it))
       continue;
     const long long pi = it.pi;
@@ -68,7 +69,7 @@ compare_win7_tri_kernel(chess_item_args a) {
     double xmax, xmin;
     // C1 / C2 are needed before the first window: the rare data scan runs up front
     if (p.data_range > 0.0) { xmax = p.data_range; xmin = 0.0; }   // fixed range (chess_params.data_range): no look-up
-    else if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    else if (tri_extrema<BATCH>(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
     if (!(C2 > 0.0)) {
@@ -143,7 +144,7 @@ compare_win7_tri_kernel(chess_item_args a) {
     const double PS = s_part[warp][0], PC = s_part[warp][1], PW = s_part[warp][2];
 
     if (PAIR) {  // the whole pair was walked by this warp: verify the predicted masks and finish
-      bool bad = overflow || !tri_masks_hold(a, it, lane, kmap, mflag);
+      bool bad = overflow || !tri_masks_hold<BATCH>(a, it, lane, kmap, mflag);
       bad = __any_sync(0xffffffffu, bad);
       if (lane == 0) {
         if (bad) {
@@ -176,7 +177,7 @@ compare_win7_tri_kernel(chess_item_args a) {
     __threadfence();
     const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
     bool bad = __ldcg(recs + 14) != 0.0 || __ldcg(recs + kTriRec + 14) != 0.0;
-    bad |= !tri_masks_hold(a, it, lane, kmap, mflag);
+    bad |= !tri_masks_hold<BATCH>(a, it, lane, kmap, mflag);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
       if (bad) {
@@ -195,9 +196,9 @@ compare_win7_tri_kernel(chess_item_args a) {
   }
 }
 
-template <int G>
-int launch_tri7(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
-  auto kern = compare_win7_tri_kernel<G>;
+template <int G, bool BATCH>
+int launch_tri7_impl(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+  auto kern = compare_win7_tri_kernel<G, BATCH>;
   constexpr int RING = 7 * 2 * G * 32;
   const size_t smem = (size_t)4 * RING * sizeof(double) + (size_t)4 * a.ncol_pad * 3;
   const size_t smem_max = (size_t)4 * RING * sizeof(double) + (size_t)4 * 256 * 3;
@@ -228,6 +229,19 @@ int launch_tri7(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
+}
+
+// Strips of 5 .. 8 columns keep the one-group-at-a-time set-up: measured on the genome-wide list at 10 kb
+// (201 bins, 7 columns per lane) the batched look-ups cost 20.6 ms against 20.1 ms -- their bursts of
+// uncoalesced loads get in the way of the row loads of the SM's other seven warps -- while the same kernel on
+// the 25 kb sweep data gains 1 % from them; -r 1 gains on both (12.7 -> 12.5 ms).  CHESS_TRI7_BATCH=0 / 1: A/B.
+template <int G>
+int launch_tri7(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+  static const int batch_env = getenv("CHESS_TRI7_BATCH") ? atoi(getenv("CHESS_TRI7_BATCH")) : -1;
+  if constexpr (G >= 5) {
+    if (batch_env != 1) return launch_tri7_impl<G, false>(ctx, a, stream);
+  }
+  return launch_tri7_impl<G, true>(ctx, a, stream);
 }
 
 }  // namespace
