@@ -10,7 +10,7 @@ namespace {
 
 // NW = warps per CTA: 4, or 1 for windows 9 / 11, whose ring of 9 / 11 rows of x and y (32 / 39 KB per warp at 7
 // columns per lane) lets only ONE 4-warp CTA onto an SM -- one-warp CTAs pack 7 / 5 of them
-template <int G, int H, int NW>
+template <int G, int H, int NW, bool BATCH>
 __global__ void __launch_bounds__(32 * NW, (NW == 1 ? 1 : (G <= 4 ? 3 : 2)))
 compare_win_tri_kernel(chess_item_args a) {
   static_assert((H == 1 || H == 2 || H == 4 || H == 5) && G >= H, "window 3 / 5 / 9 / 11 (window 7 has its own kernel)");
@@ -52,7 +52,7 @@ compare_win_tri_kernel(chess_item_args a) {
     TriItem it;
     const bool PAIR = HYB && item < n_pair_items;
     const long long half = item - n_pair_items;   // index among the half items
-    if (!tri_item_begin(a, PAIR ? item : n_pair_items + (half >> 1), PAIR ? 0 : (int)(half & 1), 31 * G, lane, kmap,
+    if (!tri_item_begin<BATCH>(a, PAIR ? item : n_pair_items + (half >> 1), PAIR ? 0 : (int)(half & 1), 31 * G, lane, kmap,
                         mflag, it))
       continue;
     const long long pi = it.pi;
@@ -74,7 +74,7 @@ compare_win_tri_kernel(chess_item_args a) {
     double xmax, xmin;
     // C1 / C2 are needed before the first window: the rare data scan runs up front
     if (p.data_range > 0.0) { xmax = p.data_range; xmin = 0.0; }   // fixed range (chess_params.data_range): no look-up
-    else if (tri_extrema(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
+    else if (tri_extrema<BATCH>(a, it, lane, mflag, xmax, xmin)) tri_scan_extrema(it, lane, kmap, xmax, xmin);
     const double drange = xmax - xmin;
     const double C1 = (0.01 * drange) * (0.01 * drange), C2 = (0.03 * drange) * (0.03 * drange);
 
@@ -151,7 +151,7 @@ compare_win_tri_kernel(chess_item_args a) {
     const double PS = s_part[warp][0], PC = s_part[warp][1], PW = s_part[warp][2];
 
     if (PAIR) {  // the whole pair was walked by this warp: verify the predicted masks and finish
-      bool bad = overflow || !tri_masks_hold(a, it, lane, kmap, mflag);
+      bool bad = overflow || !tri_masks_hold<BATCH>(a, it, lane, kmap, mflag);
       bad = __any_sync(0xffffffffu, bad);
       if (lane == 0) {
         if (bad) {
@@ -184,7 +184,7 @@ compare_win_tri_kernel(chess_item_args a) {
     __threadfence();
     const double *recs = a.scratch + (size_t)pi * 2 * kTriRec;
     bool bad = __ldcg(recs + 14) != 0.0 || __ldcg(recs + kTriRec + 14) != 0.0;
-    bad |= !tri_masks_hold(a, it, lane, kmap, mflag);
+    bad |= !tri_masks_hold<BATCH>(a, it, lane, kmap, mflag);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
       if (bad) {
@@ -203,10 +203,10 @@ compare_win_tri_kernel(chess_item_args a) {
   }
 }
 
-template <int G, int H>
-int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+template <int G, int H, bool BATCH>
+int launch_triw_impl(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   constexpr int NW = H >= 4 ? 1 : 4;
-  auto kern = compare_win_tri_kernel<G, H, NW>;
+  auto kern = compare_win_tri_kernel<G, H, NW, BATCH>;
   constexpr int D = 2 * H + 1 > 7 ? 2 * H + 1 : 7;
   constexpr int RING = D * 2 * G * 32;
   const size_t smem = (size_t)NW * RING * sizeof(double) + (size_t)NW * a.ncol_pad * 3;
@@ -238,6 +238,16 @@ int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
   ctx->launches += 1;
   CHESS_CUDA(ctx, cudaGetLastError());
   return CHESS_OK;
+}
+
+// set-up look-ups batched or one group at a time (compare_tri7.cuh: launch_tri7); CHESS_TRIW_BATCH=0 / 1: A/B
+template <int G, int H>
+int launch_triw(chess_ctx *ctx, chess_item_args &a, cudaStream_t stream) {
+  static const int batch_env = getenv("CHESS_TRIW_BATCH") ? atoi(getenv("CHESS_TRIW_BATCH")) : -1;
+  if constexpr (G >= 5) {
+    if (batch_env == 0) return launch_triw_impl<G, H, false>(ctx, a, stream);
+  }
+  return launch_triw_impl<G, H, true>(ctx, a, stream);
 }
 
 }  // namespace
