@@ -18,6 +18,9 @@ logger = logging.getLogger('')
 
 # stage -> seconds of the last `run_sim` (development aid, tools/cli_e2e.py prints it)
 LAST_STAGES = {}
+# the command-line entry points set this: a run may then hide GPUs it does not need from the CUDA driver
+# (_limit_visible_gpus); programmatic calls of Chess(argv) leave the process environment alone
+LIMIT_GPUS = False
 
 
 class _StageClock(object):
@@ -250,10 +253,66 @@ def _background_set_from_query(query_regions, query_trees, query_region, limit_b
     return _background_spans_from_query(query_regions, query_trees, query_region, limit_background)
 
 
+def _count_lines(path):
+    with open(os.path.expanduser(path), "rb") as fh:
+        return sum(chunk.count(b"\n") for chunk in iter(lambda: fh.read(1 << 22), b""))
+
+
+def _estimate_work(args):
+    """Comparisons x bins^2 of a run from the first lines and the line counts of its input files -- host only,
+    before CUDA starts.  None when the files do not say (matrix formats that carry their own regions)."""
+    try:
+        if not args.reference_regions or not args.query_regions:
+            return None
+        with open(os.path.expanduser(args.pairs)) as fh:
+            first = fh.readline().split()
+        span = int(first[2]) - int(first[1])
+        with open(os.path.expanduser(args.reference_regions)) as fh:
+            fields = fh.readline().split()
+        bins = span // max(int(fields[2]) - int(fields[1]), 1) + 1
+        n_pairs = _count_lines(args.pairs)
+        per_pair = 1.0
+        if args.background_query:
+            n_query_bins = _count_lines(args.query_regions)
+            per_pair += 2.0 * (n_query_bins / 24.0 if args.limit_background else n_query_bins)
+        elif args.background_regions is not None:
+            per_pair += _count_lines(args.background_regions)
+        return float(n_pairs) * per_pair * bins * bins
+    except (OSError, ValueError, IndexError):
+        return None
+
+
+def _limit_visible_gpus(args):
+    """On a multi-GPU box the CUDA driver initialises every visible GPU when the first one is used (6.7 s of a
+    9.9 s first run on eight B200s, whatever the number of contexts created afterwards).  A run whose work is
+    worth fewer GPUs (engine.plan_devices) hides the others from the driver BEFORE CUDA starts in this process.
+    Nothing happens when the user chose the GPUs (CUDA_VISIBLE_DEVICES, CHESS_B200_DEVICES) or CUDA is up already."""
+    if not LIMIT_GPUS or os.environ.get("CUDA_VISIBLE_DEVICES") is not None or os.environ.get("CHESS_B200_DEVICES"):
+        return
+    import torch
+    if torch.cuda.is_initialized():
+        return
+    work = _estimate_work(args)
+    if work is None:
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        count = pynvml.nvmlDeviceGetCount()
+    except Exception:
+        return
+    from .engine import plan_devices
+    n = len(plan_devices(list(range(count)), work))
+    if n < count:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(d) for d in range(n))
+        logger.info("Using {} of {} GPUs for this run (set CUDA_VISIBLE_DEVICES to choose)".format(n, count))
+
+
 def run_sim(args):
     """Body of `chess sim` (bin/chess:80-359) on the batched engine."""
     from .engine import CompareEngine, region_spans, visible_devices
     from .helpers import load_pairs_table, load_regions, load_contacts, load_oe_contacts, RegionTable
+    _limit_visible_gpus(args)
 
     output_file = args.out
     output_dir = os.path.dirname(output_file)
@@ -437,4 +496,6 @@ def run_sim(args):
 
 
 def main(argv=None):
+    global LIMIT_GPUS
+    LIMIT_GPUS = True
     Chess(argv)

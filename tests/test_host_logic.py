@@ -292,3 +292,35 @@ def test_run_level_zscores_keep_nan_and_match_the_reference_rule():
     assert np.all(np.isnan(z[~ok]))
     np.testing.assert_allclose(z[ok], (s[ok] - np.nanmean(s)) / np.nanstd(s), rtol=1e-15)
     assert np.all(np.isnan(run_zscores(np.array([np.nan, np.nan])))) and len(run_zscores(np.zeros(0))) == 0
+
+
+def test_work_estimate_from_file_heads(tmp_path):
+    """cli._estimate_work: comparisons x bins^2 from the first lines and the line counts, host only."""
+    import argparse
+    from chess_b200 import cli
+    bed = tmp_path / "r.bed"
+    bed.write_text("".join("chr1\t%d\t%d\n" % (i * 10000, (i + 1) * 10000) for i in range(500)))
+    pairs = tmp_path / "p.bedpe"
+    pairs.write_text("".join("chr1\t%d\t%d\tchr1\t%d\t%d\t%d\t.\t+\t+\n" % (s, s + 2000000, s, s + 2000000, k)
+                             for k, s in enumerate(range(0, 3000000, 100000))))
+    args = argparse.Namespace(pairs=str(pairs), reference_regions=str(bed), query_regions=str(bed),
+                              background_query=False, limit_background=False, background_regions=None)
+    assert cli._estimate_work(args) == 30 * 201.0 * 201
+    args.background_query = True
+    assert cli._estimate_work(args) == 30 * (1 + 2 * 500.0) * 201 * 201
+    args.background_query, args.background_regions = False, str(bed)
+    assert cli._estimate_work(args) == 30 * (1 + 500.0) * 201 * 201
+    args.reference_regions = None                       # a matrix format with its own regions: no estimate
+    assert cli._estimate_work(args) is None
+    # the user's choice of GPUs is never overridden
+    before = os.environ.get("CUDA_VISIBLE_DEVICES")
+    cli._limit_visible_gpus(args)                       # programmatic calls leave the environment alone
+    assert os.environ.get("CUDA_VISIBLE_DEVICES") == before
+    os.environ["CHESS_B200_DEVICES"] = "0"
+    cli.LIMIT_GPUS = True
+    try:
+        cli._limit_visible_gpus(args)
+        assert os.environ.get("CUDA_VISIBLE_DEVICES") == before
+    finally:
+        cli.LIMIT_GPUS = False
+        del os.environ["CHESS_B200_DEVICES"]

@@ -78,6 +78,7 @@ def main():
     del ref, qry, pairs
 
     from chess_b200 import cli
+    cli.LIMIT_GPUS = True          # as bin/chess does: the run may hide GPUs it does not need from the driver
     argv = ["chess", "sim", os.path.join(tmp, "ref.sparse"), os.path.join(tmp, "qry.sparse"),
             os.path.join(tmp, "pairs.bedpe"), os.path.join(tmp, "out.tsv"), "--reference-regions",
             os.path.join(tmp, "regions.bed"), "--query-regions", os.path.join(tmp, "regions.bed")]
