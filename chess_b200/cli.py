@@ -286,8 +286,9 @@ def _limit_visible_gpus(args):
     """On a multi-GPU box the CUDA driver initialises every visible GPU when the first one is used (6.7 s of a
     9.9 s first run on eight B200s, whatever the number of contexts created afterwards).  A run whose work is
     worth fewer GPUs (engine.plan_devices) hides the others from the driver BEFORE CUDA starts in this process.
-    Nothing happens when the user chose the GPUs (CUDA_VISIBLE_DEVICES, CHESS_B200_DEVICES) or CUDA is up already."""
-    if not LIMIT_GPUS or os.environ.get("CUDA_VISIBLE_DEVICES") is not None or os.environ.get("CHESS_B200_DEVICES"):
+    A CUDA_VISIBLE_DEVICES list is narrowed to its first entries; nothing happens when the GPUs were named with
+    CHESS_B200_DEVICES or CUDA is up already."""
+    if not LIMIT_GPUS or os.environ.get("CHESS_B200_DEVICES"):
         return
     import torch
     if torch.cuda.is_initialized():
@@ -295,17 +296,21 @@ def _limit_visible_gpus(args):
     work = _estimate_work(args)
     if work is None:
         return
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        count = pynvml.nvmlDeviceGetCount()
-    except Exception:
-        return
+    chosen = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if chosen is not None:                       # the user's set is kept as the superset: its first n entries
+        ids = [v for v in chosen.split(",") if v.strip() != ""]
+    else:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            ids = [str(d) for d in range(pynvml.nvmlDeviceGetCount())]
+        except Exception:
+            return
     from .engine import plan_devices
-    n = len(plan_devices(list(range(count)), work))
-    if n < count:
-        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(d) for d in range(n))
-        logger.info("Using {} of {} GPUs for this run (set CUDA_VISIBLE_DEVICES to choose)".format(n, count))
+    n = len(plan_devices(list(range(len(ids))), work))
+    if n < len(ids):
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(ids[:n])
+        logger.info("Using {} of {} GPUs for this run (CHESS_B200_DEVICES chooses them explicitly)".format(n, len(ids)))
 
 
 def run_sim(args):

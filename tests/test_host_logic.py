@@ -313,14 +313,23 @@ def test_work_estimate_from_file_heads(tmp_path):
     args.reference_regions = None                       # a matrix format with its own regions: no estimate
     assert cli._estimate_work(args) is None
     # the user's choice of GPUs is never overridden
+    args.reference_regions = str(bed)
     before = os.environ.get("CUDA_VISIBLE_DEVICES")
     cli._limit_visible_gpus(args)                       # programmatic calls leave the environment alone
     assert os.environ.get("CUDA_VISIBLE_DEVICES") == before
-    os.environ["CHESS_B200_DEVICES"] = "0"
     cli.LIMIT_GPUS = True
     try:
+        os.environ["CHESS_B200_DEVICES"] = "0"          # GPUs named explicitly: nothing is hidden
         cli._limit_visible_gpus(args)
         assert os.environ.get("CUDA_VISIBLE_DEVICES") == before
+        del os.environ["CHESS_B200_DEVICES"]
+        os.environ["CUDA_VISIBLE_DEVICES"] = "3,5,6,7"  # a list is narrowed to the GPUs the work is worth
+        cli._limit_visible_gpus(args)
+        assert os.environ["CUDA_VISIBLE_DEVICES"] == "3,5"
     finally:
         cli.LIMIT_GPUS = False
-        del os.environ["CHESS_B200_DEVICES"]
+        os.environ.pop("CHESS_B200_DEVICES", None)
+        if before is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = before

@@ -55,6 +55,7 @@ def main():
     args = ap.parse_args()
     if args.devices:
         os.environ["CHESS_B200_DEVICES"] = args.devices
+    visible_at_start = os.environ.get("CUDA_VISIBLE_DEVICES")
     import bench
     t0 = time.perf_counter()
     genome, ref, qry, pairs = bench.make_workload(bench.workload_spec(bench.parse_args(["--workload", args.workload])))
@@ -101,6 +102,7 @@ def main():
     import torch
     print(json.dumps({"workload": args.workload, "pairs": n_pairs, "contacts_per_sample": n_contacts,
                       "devices": os.environ.get("CHESS_B200_DEVICES") or "all (%d)" % torch.cuda.device_count(),
+                      "cuda_visible_devices": {"at_start": visible_at_start, "after": os.environ.get("CUDA_VISIBLE_DEVICES")},
                       "argv": argv[2:], "input_bytes": sizes, "runs": runs}))
 
 
