@@ -287,8 +287,20 @@ __global__ void __launch_bounds__(1024) zscore_kernel(const double *__restrict__
   }
   __syncthreads();
   const double pivot = pivot_s;
+  // one CTA is latency-bound: 16 loads per thread in flight (one at a time cost 46 us for the 101 354 values of
+  // the genome-wide list, 2.7 % of an 8-GPU step); the order of the additions per thread is unchanged
+  constexpr int U = 16;
   double cnt = 0.0, sum = 0.0, ssq = 0.0;
-  for (long long i = threadIdx.x; i < n; i += 1024) {
+  long long i = threadIdx.x;
+  for (; i + (long long)(U - 1) * 1024 < n; i += (long long)U * 1024) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = s[i + (long long)u * 1024];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (v[u] == v[u]) { const double d = v[u] - pivot; cnt += 1.0; sum += d; ssq = fma(d, d, ssq); }
+  }
+  for (; i < n; i += 1024) {
     const double v = s[i];
     if (v == v) { const double d = v - pivot; cnt += 1.0; sum += d; ssq = fma(d, d, ssq); }
   }
@@ -304,7 +316,15 @@ __global__ void __launch_bounds__(1024) zscore_kernel(const double *__restrict__
   const double dmean = red[1][32] / cnt;                 // mean - pivot
   const double var = red[2][32] / cnt - dmean * dmean;   // population variance (ddof 0)
   const double sd = sqrt(var > 0.0 ? var : 0.0);
-  for (long long i = threadIdx.x; i < n; i += 1024) {
+  i = threadIdx.x;
+  for (; i + (long long)(U - 1) * 1024 < n; i += (long long)U * 1024) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = s[i + (long long)u * 1024];
+#pragma unroll
+    for (int u = 0; u < U; ++u) z[i + (long long)u * 1024] = isfinite(v[u]) ? ((v[u] - pivot) - dmean) / sd : CUDART_NAN;
+  }
+  for (; i < n; i += 1024) {
     const double v = s[i];
     z[i] = isfinite(v) ? ((v - pivot) - dmean) / sd : CUDART_NAN;
   }
