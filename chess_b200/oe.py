@@ -5,9 +5,6 @@ The per-diagonal sums, the mappable-pair counts and the O/E division run in
 the K1 / K2 kernels (chess_b200/csrc/oe.cu); the Python below only lays out
 the chromosome table and converts results to the reference's return types.
 """
-import ctypes as C
-from collections import defaultdict
-
 import numpy as np
 import torch
 

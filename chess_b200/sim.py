@@ -5,7 +5,6 @@ return types and NaN / exception behaviour.  The arithmetic (gather, masking,
 SSIM, SN) runs in the CUDA kernels behind ``chess_compare_batch``; the
 functions below translate the reference's call shapes into batches.
 """
-import ctypes as C
 import logging
 import uuid
 

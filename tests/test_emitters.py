@@ -2,7 +2,6 @@
 CLI (tests/golden/make_golden_emitters.py), and the array generators behind them."""
 import os
 
-import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))

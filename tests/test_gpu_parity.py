@@ -4,7 +4,6 @@ and against the golden vectors produced by the reference's own code.
 Tolerances (BASELINE.json north_star, fp64 mode): SSIM, SN and z within 1e-6
 relative; masks, NaN pattern, pair order and every integer quantity exact.
 """
-import os
 import queue
 
 import numpy as np
