@@ -33,7 +33,7 @@ Numbers on the JSON line
                 host memory in one NCCL gather and one copy -- all inside the timed region.
   roofline      compare kernel only: algorithmic bytes (2*n*n*8 + 24 per pair) / its CUDA-event
                 duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes
-                of one launch from an ncu pass this very run makes on a child process (N = 1; null if ncu is
+                of one pass from an ncu pass this very run makes on a child process (N = 1; null if ncu is
                 not usable); `secondary` = the FP64 bound: algorithmic flops / the same duration
                 against the measured FP64 FMA peak (profiles/r01_microbench.txt).
   run           run-specific facts (pairs that gave a result, sharding identity, cold start, ...); `config`
@@ -281,15 +281,15 @@ def roofline(alg_bytes, kernel_ms, n_pixels, window, compute_sn, what, traffic=N
 
 
 def ncu_traffic(args, timeout_s=240):
-    """DRAM bytes (read + write) of ONE launch of the compare kernel on this workload: a child process sets the
-    same workload up and launches the kernel three times under `ncu --metrics dram__bytes_*`; the third launch
-    is captured.  Returns (bytes, note); bytes is None when ncu cannot run here."""
+    """DRAM bytes (read + write) of ONE PASS of the compare kernel over this workload: a child process sets the
+    same workload up and makes PROBE_STEPS passes under `ncu --metrics dram__bytes_*`; the passes after the first
+    are averaged (parse_ncu_traffic).  Returns (bytes, note); bytes is None when ncu cannot run here."""
     import shutil
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return None, "ncu not found"
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
-           "--kernel-name", "regex:^compare_(r1|win)", "--launch-count", "16", "--csv",
+           "--kernel-name", "regex:^compare_(r1|win)", "--launch-count", "48", "--csv",
            sys.executable, os.path.abspath(__file__), "--probe-kernel", "--workload", args.workload,
            "--window", args.window, "--kernel", str(args.kernel)]
     if args.bin_size:
@@ -306,9 +306,15 @@ def ncu_traffic(args, timeout_s=240):
     return parse_ncu_traffic(out.stdout, out.returncode, out.stderr)
 
 
-def parse_ncu_traffic(text, rc=0, err=""):
-    """Sum dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu's csv; the kernel that moves the most
-    bytes is the dominant one, its first launch (cold module, cold band) is left out of the mean."""
+PROBE_STEPS = 3          # passes the --probe-kernel child makes
+
+
+def parse_ncu_traffic(text, rc=0, err="", probe_steps=PROBE_STEPS):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE PASS of the compare kernel from ncu's csv of the probe
+    child (`probe_steps` passes).  The kernel that moves the most bytes is the dominant one; a pass launches it once
+    per chunk of <= 65 536 pairs, so its launches are summed per pass (like `achieved`, which divides the
+    algorithmic bytes of the whole pass by the time of the whole pass); the first pass (cold module, cold band) is
+    left out."""
     import csv
     unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rows = [r for r in csv.reader(text.splitlines()) if len(r) > 10]
@@ -330,10 +336,18 @@ def parse_ncu_traffic(text, rc=0, err=""):
     by_name = {}
     for k in sorted(per_launch, key=int):
         by_name.setdefault(names[k], []).append(per_launch[k])
-    name = max(by_name, key=lambda n: np.mean(by_name[n]))
-    vals = by_name[name][1:] or by_name[name]
+    name = max(by_name, key=lambda n: np.sum(by_name[n]))
+    vals = by_name[name]
+    if probe_steps > 1 and len(vals) % probe_steps == 0:
+        per_pass = len(vals) // probe_steps
+        warm = vals[per_pass:]
+        return int(np.sum(warm) / (probe_steps - 1)), (
+            "ncu dram__bytes_read.sum + dram__bytes_write.sum of one pass = %d launch(es) of %s, mean of %d passes in a "
+            "child process of this run (L2 flushed before each)" % (per_pass, name, probe_steps - 1))
+    vals = vals[1:] or vals
     return int(np.mean(vals)), ("ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches of %s in a child "
-                                "process of this run (L2 flushed before each)" % (len(vals), name))
+                                "process of this run (L2 flushed before each; launches per pass unknown)"
+                                % (len(vals), name))
 
 
 # --------------------------------------------------------------------------- CPU arms (oracle port)
@@ -706,7 +720,7 @@ def measure_pairs(args, R, w, res=None, steps=None, warmup=None, want_cpu=True, 
             e2.record()
 
     if args.probe_kernel:
-        for _ in range(3):
+        for _ in range(PROBE_STEPS):
             flush.zero_()
             device_step()
         torch.cuda.synchronize(dev)
