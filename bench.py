@@ -306,13 +306,14 @@ def ncu_traffic(args, timeout_s=240):
     return parse_ncu_traffic(out.stdout, out.returncode, out.stderr)
 
 
-PROBE_STEPS = 3          # passes the --probe-kernel child makes
+PROBE_STEPS = 3          # device-timed passes the --probe-kernel child makes ...
+PROBE_PASSES = PROBE_STEPS + 1   # ... after the one cold host-buffer call every run starts with
 
 
-def parse_ncu_traffic(text, rc=0, err="", probe_steps=PROBE_STEPS):
+def parse_ncu_traffic(text, rc=0, err="", probe_steps=PROBE_PASSES):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE PASS of the compare kernel from ncu's csv of the probe
-    child (`probe_steps` passes).  The kernel that moves the most bytes is the dominant one; a pass launches it once
-    per chunk of <= 65 536 pairs, so its launches are summed per pass (like `achieved`, which divides the
+    child (`probe_steps` passes in all).  The kernel that moves the most bytes is the dominant one; a pass
+    launches it once per chunk of <= 65 536 pairs, so its launches are summed per pass (like `achieved`, which divides the
     algorithmic bytes of the whole pass by the time of the whole pass); the first pass (cold module, cold band) is
     left out."""
     import csv
