@@ -193,15 +193,75 @@ class _TableRows(object):
         return self.table._make(int(self.rows[k]))
 
 
+def _arrow_table(file_name, string_cols=()):
+    """A plain tab-separated table through pyarrow's multithreaded reader (101 354 BEDPE lines: 7 ms against 200 ms
+    in pandas' C parser), or None unless the file is exactly that: no comment or blank lines, no spaces, quotes or
+    carriage returns, the same number of fields on every line.  Whatever is not plain is left to the slower
+    readers, which end in the reference's own loops."""
+    try:
+        import pyarrow as pa
+        import pyarrow.csv as pc
+    except ImportError:
+        return None
+    try:
+        if is_gzipped(file_name):
+            return None
+        with open(file_name, "rb") as fh:
+            data = fh.read()
+        if not data or data[:1] == b"\n" or b"\n\n" in data or any(c in data for c in (b" ", b"#", b'"', b"\r")):
+            return None
+        table = pc.read_csv(
+            pa.BufferReader(data), read_options=pc.ReadOptions(autogenerate_column_names=True),
+            parse_options=pc.ParseOptions(delimiter="\t", quote_char=False, ignore_empty_lines=False),
+            convert_options=pc.ConvertOptions(column_types={"f%d" % k: pa.string() for k in string_cols},
+                                              strings_can_be_null=False))
+        for k, col in enumerate(table.columns):
+            if col.null_count:
+                return None
+            if pa.types.is_string(col.type) and k in string_cols:
+                import pyarrow.compute as pcomp
+                if pcomp.any(pcomp.equal(pcomp.utf8_length(col), 0)).as_py():
+                    return None
+        return table
+    except Exception:
+        return None
+
+
+def _arrow_codes(col):
+    """(names in order of first appearance, int codes) of a string column."""
+    enc = col.combine_chunks().dictionary_encode()
+    return enc.dictionary.to_numpy(zero_copy_only=False).tolist(), enc.indices.to_numpy(zero_copy_only=False).astype(np.int64)
+
+
+def _arrow_int64(col):
+    import pyarrow as pa
+    if not pa.types.is_int64(col.type):
+        raise ValueError("not an integer column")
+    return col.to_numpy()
+
+
 def load_regions_table(file_name, ignore_ix=False):
     """``load_regions`` for the batched engine: (RegionTable, ix_converter).  The BED is read by the pandas C
     parser; a file it cannot take as a plain table (ragged lines, blank lines in the middle, a name column) goes
     through ``load_regions`` itself, so behaviour and errors are the reference's in every case."""
     import pandas as pd
     try:
+        table = _arrow_table(file_name, string_cols=(0,))
+        if table is not None and table.num_columns >= 3:
+            import pyarrow as pa
+            plain = True
+            if table.num_columns > 3 and not ignore_ix:          # a name column: only "." everywhere is plain
+                col = table.column(3)
+                plain = pa.types.is_string(col.type) and col.unique().to_pylist() == ["."]
+            if plain:
+                names, codes = _arrow_codes(table.column(0))
+                return RegionTable(names, codes, _arrow_int64(table.column(1)), _arrow_int64(table.column(2))), None
+    except Exception:
+        pass
+    try:
         with _open(file_name, "r") as fh:
             frame = pd.read_csv(fh, sep=r"\s+", header=None, comment=None, skip_blank_lines=False, engine="c",
-                                dtype={0: str}, keep_default_na=False)
+                                dtype={0: str}, keep_default_na=False, quoting=3)     # 3 = csv.QUOTE_NONE
         plain = frame.shape[1] >= 3 and not frame.isnull().any().any() and not (frame.astype(str) == "").any().any()
         if plain and frame.shape[1] > 3 and not ignore_ix:
             plain = bool((frame[3].astype(str) == ".").all())
@@ -270,12 +330,30 @@ def load_pairs_table(file_name, chromosomes, sep=None):
     ``load_pairs_for_chroms`` itself, so errors and corner cases are the reference's."""
     import pandas as pd
     try:
+        table = _arrow_table(file_name, string_cols=(0, 3, 6, 7, 8, 9)) if sep is None else None
+        if table is not None and table.num_columns == 10:
+            ids = table.column(6).to_numpy(zero_copy_only=False).tolist()   # (to_pylist is 10 x slower)
+            if len(set(ids)) == len(ids):                        # a duplicate ID: the reference's error, below
+                known = set(chromosomes)
+                (n1, c1), (n2, c2) = _arrow_codes(table.column(0)), _arrow_codes(table.column(3))
+                (s1, k1), (s2, k2) = _arrow_codes(table.column(8)), _arrow_codes(table.column(9))
+                keep = np.array([n in known for n in n1], dtype=bool)[c1] & np.array([n in known for n in n2], dtype=bool)[c2]
+                dropped = int((~keep).sum())
+                obj = lambda names, codes: np.asarray(names, dtype=object)[codes[keep]]  # noqa: E731
+                ints = [_arrow_int64(table.column(k))[keep] for k in (1, 2, 4, 5)]
+                if not keep.all():
+                    ids = [v for v, k in zip(ids, keep.tolist()) if k]
+                return PairTable(ids, obj(n1, c1), ints[0] + 1, ints[1], obj(s1, k1),
+                                 obj(n2, c2), ints[2] + 1, ints[3], obj(s2, k2)), dropped
+    except Exception:
+        pass
+    try:
         with _open(file_name, "r") as fh:
             text = fh.read()
         if "#" in text or sep is not None:
             raise ValueError("not a plain table")
         frame = pd.read_csv(io.StringIO(text), sep=r"\s+", header=None, engine="c", dtype=str, keep_default_na=False,
-                            skip_blank_lines=False)
+                            skip_blank_lines=False, quoting=3)                        # 3 = csv.QUOTE_NONE
         if frame.shape[1] != 10 or frame.isnull().any().any() or (frame == "").any().any():
             raise ValueError("not a plain table")
         ids = frame[6]

@@ -333,3 +333,87 @@ def test_work_estimate_from_file_heads(tmp_path):
             os.environ.pop("CUDA_VISIBLE_DEVICES", None)
         else:
             os.environ["CUDA_VISIBLE_DEVICES"] = before
+
+
+def _same_outcome(fast, slow):
+    """Both callables give the same value, or raise the same exception class."""
+    try:
+        want = slow()
+    except Exception as exc:        # noqa: BLE001  (the class is the contract)
+        with pytest.raises(type(exc)):
+            fast()
+        return None
+    got = fast()
+    return got, want
+
+
+def test_table_loaders_hand_over_whatever_is_not_a_plain_table(tmp_path):
+    """The pyarrow fast path of load_regions_table / load_pairs_table takes plain tab-separated files only; every
+    other spelling the reference's loops accept (or reject) must come out as those loops decide."""
+    from chess_b200 import helpers as H
+    row = "chr1\t%d\t%d\tchr2\t%d\t%d\t%s\t.\t+\t-\n"
+    plain = "".join(row % (k * 100, k * 100 + 500, k * 50, k * 50 + 500, "id%d" % k) for k in range(40))
+    variants = {
+        "plain": plain,
+        "no_final_newline": plain.rstrip("\n"),
+        "spaces": plain.replace("\t", " "),
+        "mixed_whitespace": plain.replace("\t.\t", " \t . \t"),
+        "crlf": plain.replace("\n", "\r\n"),
+        "comment": "#header\n" + plain,
+        "blank_middle": plain.replace("id7\t", "id7\t", 1).replace("\n", "\n\n", 1),
+        "blank_end": plain + "\n",
+        "trailing_tab": plain.replace("-\n", "-\t\n", 1),
+        "ragged": plain + "chr1\t1\t2\n",
+        "eleven": plain + (row % (1, 2, 3, 4, "x")).rstrip("\n") + "\textra\n",
+        "duplicate_id": plain + row % (1, 2, 3, 4, "id3"),
+        "plus_sign": plain + "chr1\t+5\t900\tchr2\t7\t800\tplus\t.\t+\t+\n",
+        "float_start": plain + "chr1\t5.0\t900\tchr2\t7\t800\tfl\t.\t+\t+\n",
+        "empty_field": plain + "chr1\t\t900\tchr2\t7\t800\tempty\t.\t+\t+\n",
+        "na_names": plain + "NA\t1\t900\tnull\t7\t800\tNaN\t.\t+\t+\n",
+        "numeric_chroms": plain.replace("chr1", "1").replace("chr2", "2"),
+        "quotes": plain.replace("id5", '"id5"'),
+        "unknown_chrom": plain + "chrZ\t1\t900\tchr2\t7\t800\tz\t.\t+\t+\n",
+        "empty": "",
+    }
+    chroms = {"chr1", "chr2", "NA", "null", "1", "2"}
+    for name, text in variants.items():
+        path = tmp_path / (name + ".bedpe")
+        path.write_text(text)
+        out = _same_outcome(lambda: H.load_pairs_table(str(path), chroms),
+                            lambda: H.load_pairs_for_chroms(str(path), chroms))
+        if out is None:
+            continue
+        (table, dropped), (want, dropped0) = out
+        assert dropped == dropped0 and len(table) == len(want), name
+        for a, b in zip(table, want):
+            assert a[0] == b[0] and a[1].__dict__ == b[1].__dict__ and a[2].__dict__ == b[2].__dict__, name
+        assert [type(v) for v in table.ids] == [str] * len(table), name
+    bed = "".join("chr%d\t%d\t%d\n" % (1 + k // 30, (k % 30) * 1000, (k % 30 + 1) * 1000) for k in range(60))
+    beds = {
+        "plain": bed,
+        "dots": bed.replace("\n", "\t.\n"),
+        "names": "".join(line + "\tbin%d\n" % k for k, line in enumerate(bed.splitlines())),
+        "int_names": "".join(line + "\t%d\n" % (k + 1) for k, line in enumerate(bed.splitlines())),
+        "one_name": bed.replace("\n", "\t.\n").replace("\t.\n", "\tx\n", 1),
+        "spaces": bed.replace("\t", "  "),
+        "crlf": bed.replace("\n", "\r\n"),
+        "blank_middle": bed.replace("\n", "\n\n", 1),
+        "short_line": bed + "chr3\t5\n" + "chr3\t0\t1000\n",
+        "five_columns": bed.replace("\n", "\t.\t0\n"),
+        "bad_int": bed + "chr3\tx\t1000\n",
+        "plus_sign": bed + "chr3\t+0\t1000\n",
+        "numeric_chroms": bed.replace("chr", ""),
+        "empty": "",
+    }
+    for name, text in beds.items():
+        path = tmp_path / (name + ".bed")
+        path.write_text(text)
+        for ignore_ix in (False, True):
+            out = _same_outcome(lambda: H.load_regions_table(str(path), ignore_ix=ignore_ix),
+                                lambda: H.load_regions(str(path), ignore_ix=ignore_ix))
+            if out is None:
+                continue
+            (table, conv), (want, conv0, _) = out
+            assert conv == conv0 and len(table) == len(want), (name, ignore_ix)
+            assert all(a.__dict__ == b.__dict__ for a, b in zip(table, want)), (name, ignore_ix)
+            assert all(type(r.chromosome) is str for r in table), name
