@@ -443,3 +443,28 @@ def test_host_call_serves_pinned_and_pageable_arrays_alike(cb, hg38_like):
         valid = ss[~np.isnan(ss)]
         np.testing.assert_allclose(got["pinned"][3], (ss - valid.mean()) / valid.std(), rtol=1e-9, atol=1e-12,
                                    equal_nan=True)
+
+
+def test_kernels_match_reference_golden_at_201_bins(cb):
+    """The CUDA path against results of the REFERENCE's own compare_pair at the north-star shape (10 kb bins,
+    2 Mb regions = 201 bins; tests/golden/make_golden_201.py), both strands, six parameter sets."""
+    from tests.test_oracle_golden import _golden_201_inputs, GOLDEN_201_PARAMS
+    g, genome, a, b = _golden_201_inputs()
+    regions = genome.regions(cb.GenomicRegion)      # (the generator module was loaded by file path: no package)
+    trees = cb.region_interval_trees(regions)
+    re_ = cb.observed_expected_arrays(regions, a)
+    qe = cb.observed_expected_arrays(regions, b)
+    bin_size = int(g["bin"])
+    pairs = []
+    for k, st in enumerate(int(v) for v in g["starts"]):
+        for strand in ("+", "-"):
+            r = cb.GenomicRegion(chromosome="chr1", start=st * bin_size + 1, end=st * bin_size + 2000000, strand="+")
+            q = cb.GenomicRegion(chromosome="chr1", start=st * bin_size + 1, end=st * bin_size + 2000000, strand=strand)
+            pairs.append(("p%d%s" % (k, strand), r, q))
+    eng = cb.CompareEngine(re_, trees, qe, trees)
+    for tag, kw in GOLDEN_201_PARAMS.items():
+        for kernel in (0, 1):
+            ids, s, sn, st = eng.compare(pairs, kernel=kernel, **kw)
+            for k in range(len(pairs)):
+                assert close(s[k], g["ssim_" + tag][k], RTOL), (tag, kernel, k, s[k], g["ssim_" + tag][k])
+                assert close(sn[k], g["sn_" + tag][k], RTOL), (tag, kernel, k, sn[k], g["sn_" + tag][k])

@@ -4,11 +4,13 @@ Fixtures come from tests/golden/make_golden.py (reference executed in the build
 container).  Everything here is CPU-only and bit-exact: the oracle performs the
 same numpy operations in the same order as the reference.
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import chess_oracle as O
-from tests.conftest import unhex, unhex_arr, same_float
+from tests.conftest import unhex, unhex_arr, same_float, close, GOLDEN_DIR, ROOT
 
 
 def test_sn_matches_reference(golden):
@@ -194,3 +196,59 @@ def test_extract_head_oracle_matches_reference_golden(toy):
         pos, neg, std, mp, mn = O.log_ratio_stage(edges[0], trees[0], edges[1], trees[1], pair)
         assert np.array_equal(pos, gold["pos_" + pid]) and np.array_equal(neg, gold["neg_" + pid])
         assert [std, mp, mn] == gold["stats_" + pid].tolist()
+
+
+# ---------------------------------------------------------------- north-star shape: 201 bins
+def _golden_201_inputs():
+    """The sample pair of tests/golden/make_golden_201.py, regenerated from its seeds; skipped (loudly) if the
+    generator no longer reproduces the contacts the reference's code was run on."""
+    import hashlib
+    import importlib.util
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_201.npz"))
+    spec = importlib.util.spec_from_file_location("synth_for_golden", os.path.join(ROOT, "chess_b200", "synth.py"))
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    genome = S.Genome([("chr1", int(g["n_bins"]))], int(g["bin"]))
+    s = [int(v) for v in g["seeds"]]
+    a = S.synthetic_sample(genome, 215, seed=s[0], structure_seed=s[1])
+    b = S.synthetic_sample(genome, 215, seed=s[2], structure_seed=s[3], perturb=0.1)
+    h = hashlib.sha256()
+    for smp in (a, b):
+        h.update(np.asarray(smp[0], dtype=np.int64).tobytes())
+        h.update(np.asarray(smp[1], dtype=np.int64).tobytes())
+        h.update(np.asarray(smp[2], dtype=np.float64).tobytes())
+    if h.hexdigest() != str(g["inputs_sha256"]):
+        pytest.skip("chess_b200/synth.py no longer reproduces the inputs of golden_201.npz: regenerate the golden")
+    return g, genome, a, b
+
+
+GOLDEN_201_PARAMS = {"default": dict(), "abs7": dict(absolute_window_size=7), "abs3": dict(absolute_window_size=3),
+                     "abs11": dict(absolute_window_size=11), "keep": dict(keep_unmappable_bins=True),
+                     "rel05": dict(relative_window_size=0.5)}
+
+
+def test_oracle_matches_reference_at_201_bins():
+    """The oracle against results of the reference's own compare_pair (chess/sim.py:225-380, chess/oe.py) at the
+    shape BASELINE configs[2] is quoted on: 10 kb bins, 2 Mb regions = 201 bins, both strands, six parameter sets."""
+    g, genome, a, b = _golden_201_inputs()
+    regions = genome.regions(O.Region)
+    trees = O.region_trees(regions)
+    edges = []
+    for smp in (a, b):
+        triples = list(zip(smp[0].tolist(), smp[1].tolist(), smp[2].tolist()))
+        edges.append(O.edges_dict(O.observed_expected(regions, triples)))
+    bin_size = int(g["bin"])
+    pairs = []
+    for k, st in enumerate(int(v) for v in g["starts"]):
+        for strand in ("+", "-"):
+            r = O.Region(st * bin_size + 1, st * bin_size + 2000000, "chr1", strand="+")
+            q = O.Region(st * bin_size + 1, st * bin_size + 2000000, "chr1", strand=strand)
+            pairs.append(("p%d%s" % (k, strand), r, q))
+    m, _ = O.sub_matrix_from_edges_dict(edges[0], trees, pairs[0][1], 1.0)
+    assert m.shape[0] == int(g["bins_first_pair"]) == 201
+    assert np.array_equal(O.find_masked_rows(m, masking_value=1), g["masked_first_pair_ref"])
+    for tag, kw in GOLDEN_201_PARAMS.items():
+        for k, pair in enumerate(pairs):
+            _, s, sn = O.compare_pair(pair, edges[0], trees, edges[1], trees, compute_sn=True, **kw)
+            assert close(s, g["ssim_" + tag][k], 1e-12), (tag, k, s, g["ssim_" + tag][k])
+            assert close(sn, g["sn_" + tag][k], 1e-12), (tag, k, sn, g["sn_" + tag][k])
