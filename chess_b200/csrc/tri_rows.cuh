@@ -110,7 +110,8 @@ __host__ __device__ __forceinline__ int tri_mode(int np_, int G, int &B1, int &B
   return (G <= 4 && L + 1 + L1 + 1 + L2 <= 31) ? 1 : 2;
 }
 
-// Geometry of one lane in one part of a pair.
+// Geometry of one lane in one part of a pair.  (tri_lane / blk_lane compile for the host too:
+// tests/tri_geometry_harness.cu checks on the CPU that the lanes of every layout tile the triangle exactly.)
 struct TriLane {
   int lo, hi;      // rows of the lane's band
   int cbase;       // first column of the lane's strip (1 << 20: idle lane)
@@ -119,7 +120,7 @@ struct TriLane {
   double wl;       // weight of the lane's columns: 0 halo, 1 diagonal block, 2 right of it
 };
 
-__device__ __forceinline__ TriLane tri_lane(int part, int lane, int G, int np_, int B1, int B2, int L1, int L2,
+__host__ __device__ __forceinline__ TriLane tri_lane(int part, int lane, int G, int np_, int B1, int B2, int L1, int L2,
                                             int halo) {
   TriLane g;
   g.lo = 0; g.hi = 0; g.cbase = 1 << 20;
@@ -147,7 +148,7 @@ __device__ __forceinline__ TriLane tri_lane(int part, int lane, int G, int np_, 
 // on and above the diagonal are the work items.  Block (bi, bj): rows [bi side, ...), columns [bj side, ...) plus
 // one whole lane of halo columns on either side that exists; the block's lanes weigh 1 on the diagonal (its full
 // square is summed once) and 2 above it (it stands for its mirror image), halo lanes 0.
-__device__ __forceinline__ TriLane blk_lane(int bi, int bj, int side, int lane, int G, int np_, int halo) {
+__host__ __device__ __forceinline__ TriLane blk_lane(int bi, int bj, int side, int lane, int G, int np_, int halo) {
   TriLane g;
   g.lo = min(bi * side, np_); g.hi = min(g.lo + side, np_);
   const int clo = min(bj * side, np_), chi = min(clo + side, np_);
