@@ -97,25 +97,29 @@ int main() {
       }
     }
   }
-  // block kernels: 94 .. 1024 bins, strips of 5 .. 8 columns, nb x nb blocks of `side` rows (compare_fast.cu)
+  // block kernels: strips of 5 .. 8 columns, nb x nb blocks (the launcher fixes nb from the widest pair of the
+  // batch: 2 .. 7); a pair's compacted size np decides the side of its blocks, a multiple of G of at most 29 strips;
+  // pairs whose blocks would be narrower than 8 bins go to the generic kernel (compare_blk.cuh)
   for (int G = 5; G <= 8; ++G) {
-    for (int np_ = 94; np_ <= 1024; np_ += (np_ < 260 ? 1 : 7)) {
-      const int nb = (np_ + 29 * G - 1) / (29 * G);
-      if (nb < 2 || nb > 7) continue;
-      const int side = (((np_ + nb - 1) / nb + G - 1) / G) * G;
-      std::vector<double> cov((size_t)np_ * np_, 0.0);
-      for (int bi = 0; bi < nb; ++bi) {
-        for (int bj = bi; bj < nb; ++bj) {
-          Lane ln[32];
-          for (int l = 0; l < 32; ++l) {
-            ln[l] = make(blk_lane(bi, bj, side, l, G, np_, 3), G, np_);
-            if (ln[l].used) add_cover(cov, np_, ln[l]);
+    for (int nb = 2; nb <= 7; ++nb) {
+      for (int np_ = 8 * nb - nb + 1; np_ <= nb * 29 * G && np_ <= 1024; np_ += (np_ < 300 ? 1 : 5)) {
+        const int per = (np_ + nb - 1) / nb;
+        if (per < 8 || (per + G - 1) / G > 29) continue;
+        const int side = ((per + G - 1) / G) * G;
+        std::vector<double> cov((size_t)np_ * np_, 0.0);
+        for (int bi = 0; bi < nb; ++bi) {
+          for (int bj = bi; bj < nb; ++bj) {
+            Lane ln[32];
+            for (int l = 0; l < 32; ++l) {
+              ln[l] = make(blk_lane(bi, bj, side, l, G, np_, 3), G, np_);
+              if (ln[l].used) add_cover(cov, np_, ln[l]);
+            }
+            bad += check_lanes(ln, np_, "block", G);
           }
-          bad += check_lanes(ln, np_, "block", G);
         }
+        bad += check_cover(cov, np_, "block", G);
+        ++layouts;
       }
-      bad += check_cover(cov, np_, "block", G);
-      ++layouts;
     }
   }
   std::printf("checked %d layouts, %d failures\n", layouts, bad);
