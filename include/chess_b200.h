@@ -13,8 +13,13 @@
  *  - The caller owns every buffer.  Pointers marked DEVICE are device
  *    pointers of the context's GPU (e.g. torch.Tensor.data_ptr()); the
  *    library never frees caller memory.  The `_host` entry points take HOST
- *    pointers and perform the host<->device copies themselves through
- *    context-owned staging buffers.
+ *    pointers and perform the host<->device copies themselves: by DMA
+ *    straight from / into the caller's arrays when ALL of them are
+ *    page-locked (cudaHostAlloc, cudaHostRegister, torch pinned tensors),
+ *    through context-owned pinned staging buffers otherwise (pageable
+ *    memory: one extra host copy each way).  Tables of up to 8192 pairs are
+ *    read from, and their results written to, the staging area directly
+ *    by the kernels (no DMA on the path of a latency-bound call).
  *  - All launches go to the caller-supplied stream (a cudaStream_t passed as
  *    void*; NULL = legacy default stream).  Device entry points do not
  *    synchronise; `_host` entry points return after the results are in host
